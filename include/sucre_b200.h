@@ -1,0 +1,127 @@
+/* sucre_b200 — C ABI of the B200-native SUCRe hot path (libsucre_b200.so).
+ *
+ * The reference (clementinboittiaux/sucre) has no FFI of its own: its hot path is a chain of PyTorch ATen
+ * calls issued from Python.  Each entry point below replaces a span of reference Python, cited as file:line
+ * into /root/reference/sucre/.  The intended binding is ctypes from the Python replacement of
+ * sucre.restore_image (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; sucre_last_error() then describes it
+ *     (thread-local, valid until the next call on the same thread);
+ *   - all pointers are DEVICE pointers unless the parameter name ends in `_host`;
+ *   - the caller owns all memory; nothing here allocates, frees, or synchronises the device;
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - images are row-major; a target pixel has flat index p = v*width + u; a "tile" is
+ *     SUCRE_TILE_PIXELS (32) consecutive flat pixels, tile k covering p in [32k, 32k+32).
+ *
+ * Observation store produced by the gather and consumed by the fit ("tile-major compact stream"):
+ *   for tile k, blocks blk_off[k] .. blk_off[k+1] list the kept source views with at least one match in the
+ *   tile, in pairing-list order; block b carries a 32-bit lane mask blk_mask[b] (bit i = pixel 32k+i matched
+ *   in that view) and its source-view index blk_view[b]; the matched pixels' records follow one another in
+ *   `records`, starting at rec_off[k] for the tile's first block, popcount(mask) records per block, ordered by
+ *   lane.  One record = float4 {z, I_r, I_g, I_b}: z = ||cP|| the range of the observation in the source
+ *   camera frame (loader.py:113 + sucre.py:53), I = source colour / 255 (loader.py:157, 87).
+ */
+#ifndef SUCRE_B200_H
+#define SUCRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SUCRE_ABI_VERSION 1
+#define SUCRE_TILE_PIXELS 32
+
+/* One view (source or target).  All matrices row-major fp32, computed on the host with the reference's own
+ * expressions so that they are bit-identical to what the reference multiplies by:
+ *   K     Camera.K                        sfm.py:204-208
+ *   Kinv  K.inverse()                     sfm.py:92
+ *   R, t  cam->world Pose                 sfm.py:219-222 (inverse of COLMAP's cam_from_world)
+ *   Ri,ti Pose.inverse(): R.T, -R.T @ t   sfm.py:47
+ * depth: u16 millimetres, height*width (loader.py:167 divides by 1000 -> metres; done in-kernel, IEEE).
+ * rgb:   u8 RGB interleaved, height*width*3 (loader.py:157 divides by 255; done in-kernel, IEEE).
+ * sizeof == 192, 16-byte aligned. */
+typedef struct sucre_view {
+    float K[9], Kinv[9], R[9], t[3], Ri[9], ti[3];
+    int32_t width, height;
+    const uint16_t* depth;
+    const uint8_t* rgb;
+} sucre_view;
+
+int sucre_abi_version(void);
+const char* sucre_last_error(void);
+
+/* ---- stage 1: multi-view correspondence gather ---------------------------------------------------------
+ * Replaces Image.match_images / match_two_way / match_one_way / Matches.map / Matches.__and__
+ * (sfm.py:115-138, 154-159, 171-175), unproject_depth(_map) / project_to_view / Pose.transform
+ * (sfm.py:49-55, 90-107) and load_depth_map's scaling (loader.py:166-170).
+ *
+ * sucre_gather_match: for every target pixel and every listed view, the reference's two-way integer
+ * round-trip test.  masks[k*n_views + s] receives the lane mask of tile k against view s.
+ * n_tiles = ceil(width*height / 32) of the target.  Bit-exact with the reference (SURVEY.md §8a'). */
+int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views,
+                       uint32_t* masks, void* stream);
+
+/* sucre_gather_plan: per-view match counts, the min_cover decision (sfm.py:136: a view is kept iff
+ * count / (width*height) > min_cover, evaluated in double like the reference's Python floats) and the
+ * layout of the observation store.
+ *   view_count[n_views]  (int64)  matches per view, kept or not
+ *   view_kept[n_views]   (uint8)  1 if the view passes min_cover
+ *   rec_off[n_tiles+1], blk_off[n_tiles+1] (int64) exclusive prefix sums over tiles, kept views only
+ *   totals[2] (int64)    {N = total observations, number of blocks}; copy to the host to size the store */
+int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, int64_t target_pixels, double min_cover,
+                      int64_t* view_count, uint8_t* view_kept, int64_t* rec_off, int64_t* blk_off,
+                      int64_t* totals, void* stream);
+
+/* sucre_gather_sample: fills the observation store.  Replaces MatchesFile.save_matches / prepare_matches /
+ * load_matches (loader.py:68-87, 103-118) and load_rgb's scaling (loader.py:156-163); the HDF5 spill file is
+ * replaced by this device-resident store.  rec_src (optional, may be NULL) receives u2 | v2 << 16, the
+ * integer source pixel of every record (what the reference stores as int16 u2, v2). */
+int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views,
+                        const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
+                        const int64_t* blk_off, int n_tiles, float* records, uint32_t* blk_mask,
+                        int32_t* blk_view, uint32_t* rec_src, void* stream);
+
+/* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
+ * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for
+ * light_model=False.  params = {B[3], beta[3], gamma[3]} fp32 (sucre.py:41-43).
+ *
+ * sucre_fit_workspace_bytes: size of the scratch buffer the fit calls need (per-CTA partial sums). */
+size_t sucre_fit_workspace_bytes(void);
+
+/* One evaluation of the closed-form objective (--use-closed-form): per pixel J = sum((I - B(1-e^{-gamma z}))
+ * e^{-beta z}) / sum(e^{-2 beta z}) with the CURRENT params (sucre.py:66-77), then residuals r = I - (J e^{-beta z}
+ * + B(1-e^{-gamma z})) (sucre.py:81) reduced to sums[10] (double):
+ *   sums[0..2] = sum r(1-e^{-gamma z}), sums[3..5] = sum r J z e^{-beta z}, sums[6..8] = sum r B z e^{-gamma z},
+ *   sums[9] = sum r^2 (the `cost` the reference logs, sucre.py:144-146,150).
+ * Multi-GPU callers all-reduce sums between this call and sucre_adam_step. */
+int sucre_fit_sums_closed_form(const float* records, const int64_t* rec_off, const int64_t* blk_off,
+                               const uint32_t* blk_mask, int n_tiles, const float* params, double* sums,
+                               void* workspace, void* stream);
+
+/* Adam step t (1-based) on the 9 parameters from the reduced sums: gradients of sum r^2 / (3 n_obs)
+ * (sucre.py:144-145), update rule of torch.optim.Adam defaults (sucre.py:136,148: betas .9/.999, eps 1e-8,
+ * fp32 state).  adam_state = {m[9], v[9]}.  history_row (optional) receives {params after the step [9], cost}. */
+int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_t n_obs, int t, double lr,
+                    float* history_row, void* stream);
+
+/* The whole single-GPU loop of adam() in closed-form mode: num_iter x {sums, step}, then nothing else
+ * (call sucre_fit_write_J for the final update_J, sucre.py:156).  history = num_iter x 10 floats. */
+int sucre_fit_closed_form(const float* records, const int64_t* rec_off, const int64_t* blk_off,
+                          const uint32_t* blk_mask, int n_tiles, int64_t n_obs, float* params,
+                          float* adam_state, int first_step, int num_iter, double lr, float* history,
+                          void* workspace, void* stream);
+
+/* Closed-form J for the current params written to J[target_pixels*3] (H,W,3); NaN where a pixel has no
+ * observation (0/0 like sucre.py:77). */
+int sucre_fit_write_J(const float* records, const int64_t* rec_off, const int64_t* blk_off,
+                      const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params,
+                      float* J, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUCRE_B200_H */

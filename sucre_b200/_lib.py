@@ -1,0 +1,69 @@
+"""ctypes binding of libsucre_b200.so (include/sucre_b200.h).  No fallback: if the library is missing or a call
+fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / 'libsucre_b200.so'
+ABI_VERSION = 1
+TILE = 32
+
+# numpy mirror of `struct sucre_view` (192 bytes)
+VIEW_DTYPE = np.dtype([('K', '<f4', 9), ('Kinv', '<f4', 9), ('R', '<f4', 9), ('t', '<f4', 3), ('Ri', '<f4', 9),
+                       ('ti', '<f4', 3), ('width', '<i4'), ('height', '<i4'), ('depth', '<u8'), ('rgb', '<u8')])
+assert VIEW_DTYPE.itemsize == 192
+
+
+class SucreError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_SIGNATURES = {
+    'sucre_abi_version': (C.c_int, []),
+    'sucre_last_error': (C.c_char_p, []),
+    'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _VP, _VP]),
+    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_fit_workspace_bytes': (C.c_size_t, []),
+    'sucre_fit_sums_closed_form': (C.c_int, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    'sucre_adam_step': (C.c_int, [_VP, _VP, _VP, _I64, _I, _D, _VP, _VP]),
+    'sucre_fit_closed_form': (C.c_int, [_VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
+    'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise SucreError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                             f'or `make -C sucre_b200/csrc`. sucre_b200 has no CPU fallback.')
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if L.sucre_abi_version() != ABI_VERSION:
+            raise SucreError(f'ABI mismatch: library {L.sucre_abi_version()}, python {ABI_VERSION}')
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise SucreError(f'{what}: {lib().sucre_last_error().decode()}')
+
+
+def view_record(K, Kinv, R, t, Ri, ti, width: int, height: int, depth_ptr: int = 0, rgb_ptr: int = 0) -> np.ndarray:
+    rec = np.zeros((), dtype=VIEW_DTYPE)
+    for name, val in (('K', K), ('Kinv', Kinv), ('R', R), ('t', t), ('Ri', Ri), ('ti', ti)):
+        rec[name] = np.asarray(val, dtype=np.float32).reshape(-1)
+    rec['width'], rec['height'], rec['depth'], rec['rgb'] = width, height, depth_ptr, rgb_ptr
+    return rec

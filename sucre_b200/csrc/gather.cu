@@ -1,0 +1,343 @@
+// Stage 1 — fused multi-view correspondence gather for sm_100a.
+//
+// What the reference does with ~80 whole-image ATen kernels, a reverse index map and four stream
+// compactions per (target, view) pair (sfm.py:115-138, 154-175; 306 B of intermediates per pixel-view)
+// is done here per target pixel, in registers:
+//   match   one thread owns PIX target pixels, keeps their world points, and walks a chunk of 32 source
+//           views whose constants sit in shared memory; the backward projection is evaluated only at the
+//           source pixel the forward projection lands on (one 2-byte gather), and the per-(tile, view)
+//           result is a 32-bit ballot mask.
+//   plan    per-view counts -> min_cover decision -> per-tile record/block counts -> exclusive scan.
+//   sample  one warp per tile re-projects only the matched pixels, fetches depth + colour of the source
+//           pixel and appends {z, I} records to the tile-major compact stream (include/sucre_b200.h).
+//
+// Arithmetic contract (SURVEY.md §8a', pinned by tests against the reference's own outputs): every fp32
+// operation below is a single correctly rounded IEEE op written with an explicit intrinsic, in the order the
+// reference's ATen calls perform them; this file is additionally compiled with -fmad=false.
+#include "common.cuh"
+
+namespace sucre {
+
+// y = M (3x3 row-major) applied to x the way torch.mm(3x3, 3xn) rounds it on the reference's CPU path:
+// per row fma(m2, x2, fma(m1, x1, m0*x0)).
+__device__ __forceinline__ void mat3(const float* M, float x0, float x1, float x2, float& y0, float& y1, float& y2) {
+    y0 = __fmaf_rn(M[2], x2, __fmaf_rn(M[1], x1, __fmul_rn(M[0], x0)));
+    y1 = __fmaf_rn(M[5], x2, __fmaf_rn(M[4], x1, __fmul_rn(M[3], x0)));
+    y2 = __fmaf_rn(M[8], x2, __fmaf_rn(M[7], x1, __fmul_rn(M[6], x0)));
+}
+
+// sfm.py:90-93 unproject_depth with depth = u16 / 1000 (loader.py:167): cP = Kinv @ (d * (u+.5, v+.5, 1))
+__device__ __forceinline__ void unproject(const float* Kinv, int u, int v, float d, float& c0, float& c1, float& c2) {
+    const float x0 = __fmul_rn(d, __fadd_rn((float)u, 0.5f));
+    const float x1 = __fmul_rn(d, __fadd_rn((float)v, 0.5f));
+    mat3(Kinv, x0, x1, d, c0, c1, c2);
+}
+
+// sfm.py:49-55 Pose.transform: (R @ P) + t, the add rounded separately
+__device__ __forceinline__ void rigid(const float* R, const float* t, float x0, float x1, float x2, float& y0, float& y1, float& y2) {
+    mat3(R, x0, x1, x2, y0, y1, y2);
+    y0 = __fadd_rn(y0, t[0]);
+    y1 = __fadd_rn(y1, t[1]);
+    y2 = __fadd_rn(y2, t[2]);
+}
+
+// sfm.py:103-107 project_to_view followed by sfm.py:116-117: .long() truncates toward zero, then
+// 0 <= u < W, 0 <= v < H.  trunc(x) >= 0 <=> x > -1, so (-1,0) is accepted as index 0 exactly like the
+// reference; NaN / inf / huge fail the comparisons (the reference's INT64_MIN fails `0 <=`).
+__device__ __forceinline__ bool project(const float* Ri, const float* ti, const float* K, int W, int H,
+                                        float w0, float w1, float w2, int& u, int& v) {
+    float c0, c1, c2, p0, p1, p2;
+    rigid(Ri, ti, w0, w1, w2, c0, c1, c2);
+    mat3(K, c0, c1, c2, p0, p1, p2);
+    const float px = __fdiv_rn(p0, p2), py = __fdiv_rn(p1, p2);
+    const bool in = px > -1.0f && px < (float)W && py > -1.0f && py < (float)H;
+    u = __float2int_rz(px);
+    v = __float2int_rz(py);
+    return in;
+}
+
+constexpr int kViewWords = sizeof(sucre_view) / 4;  // 48
+constexpr int kChunk = 32;                          // source views per CTA: lane j keeps the mask of view j
+constexpr int kWarps = 8;
+
+template <int PIX>
+__global__ void __launch_bounds__(kWarps * 32)
+gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
+                    uint32_t* __restrict__ masks, int n_tiles) {
+    __shared__ __align__(16) sucre_view sv[kChunk];
+    const int vbase = blockIdx.y * kChunk;
+    const int nv = min(kChunk, n_views - vbase);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(views + vbase);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sv);
+        for (int i = threadIdx.x; i < nv * kViewWords; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile0 = (blockIdx.x * kWarps + warp) * PIX;
+    const int P = T.width * T.height;
+
+    float w[PIX][3];
+    int u1[PIX], v1[PIX];
+    bool valid[PIX];
+#pragma unroll
+    for (int k = 0; k < PIX; ++k) {
+        const int p = (tile0 + k) * kTile + lane;
+        const bool inside = p < P;
+        const float d1 = __fdiv_rn((float)(inside ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
+        valid[k] = d1 > 0.0f;  // sfm.py:96
+        v1[k] = p / T.width;
+        u1[k] = p - v1[k] * T.width;
+        float c0, c1, c2;
+        unproject(T.Kinv, u1[k], v1[k], d1, c0, c1, c2);
+        rigid(T.R, T.t, c0, c1, c2, w[k][0], w[k][1], w[k][2]);
+    }
+
+    uint32_t mine[PIX];
+#pragma unroll
+    for (int k = 0; k < PIX; ++k) mine[k] = 0;
+
+    for (int s = 0; s < nv; ++s) {
+        const sucre_view& S = sv[s];
+#pragma unroll
+        for (int k = 0; k < PIX; ++k) {
+            int u2, v2;
+            bool m = project(S.Ri, S.ti, S.K, S.width, S.height, w[k][0], w[k][1], w[k][2], u2, v2) && valid[k];
+            if (m) {
+                // backward leg, only at the source pixel the forward leg landed on (sfm.py:124, 154-159)
+                const float d2 = __fdiv_rn((float)__ldg(S.depth + (size_t)v2 * S.width + u2), 1000.0f);
+                float c0, c1, c2, b0, b1, b2;
+                unproject(S.Kinv, u2, v2, d2, c0, c1, c2);
+                rigid(S.R, S.t, c0, c1, c2, b0, b1, b2);
+                int ub, vb;
+                const bool back = project(T.Ri, T.ti, T.K, T.width, T.height, b0, b1, b2, ub, vb);
+                m = d2 > 0.0f && back && ub == u1[k] && vb == v1[k];  // sfm.py:96 on S, sfm.py:173
+            }
+            const uint32_t ballot = __ballot_sync(kFull, m);
+            if (lane == s) mine[k] = ballot;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PIX; ++k)
+        if (tile0 + k < n_tiles && lane < nv) masks[(size_t)(tile0 + k) * n_views + vbase + lane] = mine[k];
+}
+
+// ---- plan ------------------------------------------------------------------------------------------------
+// matches per view: lane <-> view (coalesced rows of masks), warps stride over tiles
+__global__ void __launch_bounds__(256)
+count_views_kernel(const uint32_t* __restrict__ masks, int n_tiles, int n_views, unsigned long long* __restrict__ view_count) {
+    __shared__ unsigned long long part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int view = blockIdx.x * 32 + lane;
+    unsigned long long acc = 0;
+    if (view < n_views)
+        for (int tile = blockIdx.y * 8 + warp; tile < n_tiles; tile += gridDim.y * 8)
+            acc += __popc(__ldg(masks + (size_t)tile * n_views + view));
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && view < n_views) {
+        for (int i = 1; i < 8; ++i) acc += part[i][lane];
+        if (acc) atomicAdd(view_count + view, acc);
+    }
+}
+
+__global__ void kept_kernel(const long long* __restrict__ view_count, int n_views, double pixels, double min_cover,
+                            uint8_t* __restrict__ view_kept) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    // sfm.py:136: len(matches) / (width * height) > min_cover, python floats = IEEE double
+    if (v < n_views) view_kept[v] = ((double)view_count[v] / pixels > min_cover) ? 1 : 0;
+}
+
+// records and non-empty blocks per tile over kept views: one warp per tile
+__global__ void __launch_bounds__(256)
+tile_count_kernel(const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept, int n_tiles, int n_views,
+                  long long* __restrict__ rec_cnt, long long* __restrict__ blk_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    int rec = 0, blk = 0;
+    for (int view = lane; view < n_views; view += 32) {
+        const uint32_t m = view_kept[view] ? __ldg(masks + (size_t)tile * n_views + view) : 0u;
+        rec += __popc(m);
+        blk += m != 0;
+    }
+    for (int o = 16; o; o >>= 1) {
+        rec += __shfl_xor_sync(kFull, rec, o);
+        blk += __shfl_xor_sync(kFull, blk, o);
+    }
+    if (lane == 0) {
+        rec_cnt[tile] = rec;
+        blk_cnt[tile] = blk;
+    }
+}
+
+// in-place exclusive scan of two count arrays (n entries -> n+1 offsets), one CTA
+__global__ void __launch_bounds__(1024)
+scan_kernel(long long* __restrict__ a, long long* __restrict__ b, int n, long long* __restrict__ totals) {
+    __shared__ long long sa[1024], sb[1024];
+    const int t = threadIdx.x;
+    const int chunk = (n + 1023) / 1024;
+    const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    long long la = 0, lb = 0;
+    for (int i = lo; i < hi; ++i) {
+        la += a[i];
+        lb += b[i];
+    }
+    sa[t] = la;
+    sb[t] = lb;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const long long xa = t >= off ? sa[t - off] : 0, xb = t >= off ? sb[t - off] : 0;
+        __syncthreads();
+        sa[t] += xa;
+        sb[t] += xb;
+        __syncthreads();
+    }
+    long long pa = sa[t] - la, pb = sb[t] - lb;
+    for (int i = lo; i < hi; ++i) {
+        const long long ca = a[i], cb = b[i];
+        a[i] = pa;
+        b[i] = pb;
+        pa += ca;
+        pb += cb;
+    }
+    if (t == 1023) {
+        a[n] = sa[t];
+        b[n] = sb[t];
+        totals[0] = sa[t];
+        totals[1] = sb[t];
+    }
+}
+
+// ---- sample ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
+                     const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
+                     const long long* __restrict__ rec_off, const long long* __restrict__ blk_off, int n_tiles,
+                     float4* __restrict__ records, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
+                     uint32_t* __restrict__ rec_src) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    const int P = T.width * T.height;
+    const int p = tile * kTile + lane;
+    float w0, w1, w2;
+    {
+        const float d1 = __fdiv_rn((float)(p < P ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
+        const int v1 = p / T.width, u1 = p - v1 * T.width;
+        float c0, c1, c2;
+        unproject(T.Kinv, u1, v1, d1, c0, c1, c2);
+        rigid(T.R, T.t, c0, c1, c2, w0, w1, w2);
+    }
+    long long rec = rec_off[tile], blk = blk_off[tile];
+    for (int base = 0; base < n_views; base += 32) {
+        const int view = base + lane;
+        uint32_t m = 0;
+        if (view < n_views && view_kept[view]) m = __ldg(masks + (size_t)tile * n_views + view);
+        unsigned nz = __ballot_sync(kFull, m != 0);
+        while (nz) {
+            const int j = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t bm = __shfl_sync(kFull, m, j);
+            const int s = base + j;
+            if (lane == 0) {
+                blk_mask[blk] = bm;
+                blk_view[blk] = s;
+            }
+            if ((bm >> lane) & 1u) {
+                const sucre_view* S = views + s;  // warp-uniform addresses: broadcast loads
+                float Ri[9], ti[3], K[9], Kinv[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    Ri[i] = __ldg(&S->Ri[i]);
+                    K[i] = __ldg(&S->K[i]);
+                    Kinv[i] = __ldg(&S->Kinv[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) ti[i] = __ldg(&S->ti[i]);
+                const int Ws = __ldg(&S->width), Hs = __ldg(&S->height);
+                const uint16_t* depth = reinterpret_cast<const uint16_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->depth)));
+                const uint8_t* rgb = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->rgb)));
+                int u2, v2;
+                project(Ri, ti, K, Ws, Hs, w0, w1, w2, u2, v2);
+                const size_t q = (size_t)v2 * Ws + u2;
+                const float d2 = __fdiv_rn((float)__ldg(depth + q), 1000.0f);  // sfm.py:137
+                float c0, c1, c2;
+                unproject(Kinv, u2, v2, d2, c0, c1, c2);                        // loader.py:113
+                // sucre.py:53 cP.norm(dim=0): sequential squares, no fma
+                const float z = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2)));
+                const uint8_t* px = rgb + 3 * q;
+                const float I0 = __fdiv_rn((float)__ldg(px + 0), 255.0f);       // loader.py:157, 87
+                const float I1 = __fdiv_rn((float)__ldg(px + 1), 255.0f);
+                const float I2 = __fdiv_rn((float)__ldg(px + 2), 255.0f);
+                const long long at = rec + __popc(bm & ((1u << lane) - 1u));
+                records[at] = make_float4(z, I0, I1, I2);
+                if (rec_src) rec_src[at] = (uint32_t)u2 | ((uint32_t)v2 << 16);
+            }
+            rec += __popc(bm);
+            ++blk;
+        }
+    }
+}
+
+static int check_view_host(const sucre_view* v, const char* who) {
+    SUCRE_REQUIRE(v != nullptr, "%s: null view", who);
+    SUCRE_REQUIRE(v->width > 0 && v->height > 0 && v->width <= 32767 && v->height <= 32767,
+                  "%s: image size %dx%d outside [1, 32767] (the reference stores pixel indices as int16, loader.py:71-74)",
+                  who, v->width, v->height);
+    SUCRE_REQUIRE((long long)v->width * v->height <= 0x7fffffffLL - 64, "%s: too many pixels", who);
+    SUCRE_REQUIRE(v->depth != nullptr, "%s: null depth pointer", who);
+    return 0;
+}
+
+}  // namespace sucre
+
+using namespace sucre;
+
+extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views,
+                                  uint32_t* masks, void* stream) {
+    clear_error();
+    if (check_view_host(target_host, "sucre_gather_match(target)")) return 1;
+    SUCRE_REQUIRE(views && masks, "sucre_gather_match: null pointer");
+    SUCRE_REQUIRE(n_views > 0, "sucre_gather_match: n_views = %d", n_views);
+    const int P = target_host->width * target_host->height;
+    const int n_tiles = (P + kTile - 1) / kTile;
+    constexpr int PIX = 2;
+    dim3 grid((n_tiles + kWarps * PIX - 1) / (kWarps * PIX), (n_views + kChunk - 1) / kChunk);
+    gather_match_kernel<PIX><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*target_host, views, n_views, masks, n_tiles);
+    return check_launch("gather_match_kernel");
+}
+
+extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, int64_t target_pixels, double min_cover,
+                                 int64_t* view_count, uint8_t* view_kept, int64_t* rec_off, int64_t* blk_off,
+                                 int64_t* totals, void* stream) {
+    clear_error();
+    SUCRE_REQUIRE(masks && view_count && view_kept && rec_off && blk_off && totals, "sucre_gather_plan: null pointer");
+    SUCRE_REQUIRE(n_tiles > 0 && n_views > 0 && target_pixels > 0, "sucre_gather_plan: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    SUCRE_CUDA(cudaMemsetAsync(view_count, 0, sizeof(int64_t) * n_views, st));
+    dim3 cgrid((n_views + 31) / 32, min(64, (n_tiles + 7) / 8));
+    count_views_kernel<<<cgrid, 256, 0, st>>>(masks, n_tiles, n_views, (unsigned long long*)view_count);
+    kept_kernel<<<(n_views + 127) / 128, 128, 0, st>>>((const long long*)view_count, n_views, (double)target_pixels, min_cover, view_kept);
+    tile_count_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(masks, view_kept, n_tiles, n_views, (long long*)rec_off, (long long*)blk_off);
+    scan_kernel<<<1, 1024, 0, st>>>((long long*)rec_off, (long long*)blk_off, n_tiles, (long long*)totals);
+    return check_launch("sucre_gather_plan kernels");
+}
+
+extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views,
+                                   const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
+                                   const int64_t* blk_off, int n_tiles, float* records, uint32_t* blk_mask,
+                                   int32_t* blk_view, uint32_t* rec_src, void* stream) {
+    clear_error();
+    if (check_view_host(target_host, "sucre_gather_sample(target)")) return 1;
+    SUCRE_REQUIRE(views && masks && view_kept && rec_off && blk_off && records && blk_mask && blk_view,
+                  "sucre_gather_sample: null pointer");
+    const int P = target_host->width * target_host->height;
+    SUCRE_REQUIRE(n_tiles == (P + kTile - 1) / kTile, "sucre_gather_sample: n_tiles %d does not match the target", n_tiles);
+    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, "sucre_gather_sample: records must be 16-byte aligned");
+    gather_sample_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        *target_host, views, n_views, masks, view_kept, (const long long*)rec_off, (const long long*)blk_off, n_tiles,
+        reinterpret_cast<float4*>(records), blk_mask, blk_view, rec_src);
+    return check_launch("gather_sample_kernel");
+}

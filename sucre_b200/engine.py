@@ -1,0 +1,289 @@
+"""Device-resident scene, observation store and the thin wrappers that enqueue the CUDA hot path.
+
+PyTorch is used for device memory, streams and copies only; every computation on the hot path is a kernel of
+libsucre_b200.so reached through ctypes (sucre_b200/_lib.py).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TILE
+
+
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class ViewGeom:
+    """Host-side constants of one view, bit-identical to what the reference multiplies by."""
+    K: torch.Tensor      # (3,3) Camera.K                       sfm.py:204-208
+    Kinv: torch.Tensor   # (3,3) K.inverse()                    sfm.py:92
+    R: torch.Tensor      # (3,3) cam->world rotation            sfm.py:219-222
+    t: torch.Tensor      # (3,1) cam->world translation
+    Ri: torch.Tensor     # (3,3) Pose.inverse().R = R.T         sfm.py:47
+    ti: torch.Tensor     # (3,1) Pose.inverse().t = -R.T @ t    sfm.py:47
+    width: int
+    height: int
+
+    @staticmethod
+    def from_pose(K, R, t, width: int, height: int) -> 'ViewGeom':
+        """Derives Kinv, Ri, ti on the host with the reference's own torch expressions."""
+        K = torch.as_tensor(K, dtype=torch.float32).reshape(3, 3).cpu()
+        R = torch.as_tensor(R, dtype=torch.float32).reshape(3, 3).cpu()
+        t = torch.as_tensor(t, dtype=torch.float32).reshape(3, 1).cpu()
+        return ViewGeom(K=K, Kinv=K.inverse(), R=R, t=t, Ri=R.T, ti=-R.T @ t, width=int(width), height=int(height))
+
+    def record(self, depth_ptr: int = 0, rgb_ptr: int = 0) -> np.ndarray:
+        c = lambda x: x.contiguous().numpy()  # noqa: E731
+        return _lib.view_record(c(self.K), c(self.Kinv), c(self.R), c(self.t), c(self.Ri), c(self.ti),
+                                self.width, self.height, depth_ptr, rgb_ptr)
+
+
+class DeviceScene:
+    """Views resident in HBM: u16 millimetre depth + u8 RGB per view and their `sucre_view` records.
+
+    Replaces the reference's per-(target, view) PNG re-decode (sfm.py:130-133, loader.py:156-170) and the
+    float32 images it keeps: 5 bytes per pixel instead of 16, converted in-kernel."""
+
+    def __init__(self, device: str | torch.device = 'cuda'):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.SucreError(f'sucre_b200 runs on CUDA devices only (got {device!r}); there is no CPU path')
+        self.geom: dict = {}
+        self.depth: dict = {}
+        self.rgb: dict = {}
+        self._tables: dict = {}
+
+    def __contains__(self, key):
+        return key in self.geom
+
+    def __len__(self):
+        return len(self.geom)
+
+    def add_view(self, key, geom: ViewGeom, depth_u16: torch.Tensor, rgb_u8: torch.Tensor | None):
+        """depth_u16: (H,W) uint16 (or int16 bit pattern), rgb_u8: (H,W,3) uint8; host (ideally pinned) or device."""
+        assert depth_u16.shape == (geom.height, geom.width), (depth_u16.shape, geom.height, geom.width)
+        assert depth_u16.element_size() == 2
+        self.depth[key] = depth_u16.to(self.device, non_blocking=True).contiguous()
+        if rgb_u8 is not None:
+            assert rgb_u8.shape == (geom.height, geom.width, 3) and rgb_u8.dtype == torch.uint8
+            self.rgb[key] = rgb_u8.to(self.device, non_blocking=True).contiguous()
+        self.geom[key] = geom
+        self._tables.clear()
+
+    def add_views(self, keys, geoms, depth_u16: torch.Tensor, rgb_u8: torch.Tensor):
+        """Bulk form: stacked (V,H,W) / (V,H,W,3) tensors moved with one copy each."""
+        d = depth_u16.to(self.device, non_blocking=True)
+        c = rgb_u8.to(self.device, non_blocking=True)
+        for i, (k, g) in enumerate(zip(keys, geoms)):
+            self.geom[k], self.depth[k], self.rgb[k] = g, d[i], c[i]
+        self._tables.clear()
+
+    def record(self, key) -> np.ndarray:
+        rgb = self.rgb.get(key)
+        return self.geom[key].record(self.depth[key].data_ptr(), 0 if rgb is None else rgb.data_ptr())
+
+    def table(self, keys) -> torch.Tensor:
+        """Device array of `sucre_view` for `keys` (cached)."""
+        keys = tuple(keys)
+        if keys not in self._tables:
+            host = np.stack([self.record(k) for k in keys]).view(np.uint8).reshape(len(keys), -1)
+            self._tables[keys] = torch.from_numpy(host).to(self.device)
+        return self._tables[keys]
+
+
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class ObservationStore:
+    """Tile-major compact observation stream (layout: include/sucre_b200.h).  Replaces the reference's HDF5
+    spill file + MatchesData (loader.py:36-130)."""
+    width: int
+    height: int
+    source_keys: tuple
+    view_count: np.ndarray        # (V,) int64 matches per listed view (host)
+    view_kept: np.ndarray         # (V,) bool  min_cover decision (host)
+    n_obs: int
+    n_blocks: int
+    records: torch.Tensor         # (N,4) f32 {z, I_r, I_g, I_b}
+    rec_off: torch.Tensor         # (n_tiles+1,) int64
+    blk_off: torch.Tensor         # (n_tiles+1,) int64
+    blk_mask: torch.Tensor        # (n_blocks,) int32 (bit pattern of the uint32 lane mask)
+    blk_view: torch.Tensor        # (n_blocks,) int32 index into source_keys
+    rec_src: torch.Tensor | None  # (N,) int32 u2 | v2 << 16
+    stats: dict = field(default_factory=dict)
+
+    @property
+    def n_tiles(self) -> int:
+        return (self.width * self.height + TILE - 1) // TILE
+
+    @property
+    def kept_keys(self) -> list:
+        return [k for k, keep in zip(self.source_keys, self.view_kept) if keep]
+
+    def __len__(self) -> int:
+        return self.n_obs
+
+    def per_record_index(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """(pixel, view) of every record, in store order (device int64 tensors)."""
+        dev = self.records.device
+        nblk_tile = (self.blk_off[1:] - self.blk_off[:-1])
+        blk_tile = torch.repeat_interleave(torch.arange(self.n_tiles, device=dev), nblk_tile)
+        lanes = torch.arange(32, device=dev, dtype=torch.int64)
+        bits = ((self.blk_mask.to(torch.int64)[:, None] >> lanes[None, :]) & 1).bool()
+        blk, lane = bits.nonzero(as_tuple=True)
+        return blk_tile[blk] * TILE + lane, self.blk_view.to(torch.int64)[blk]
+
+    def to_reference_layout(self) -> dict:
+        """Per kept view (in source_keys order) the arrays the reference's MatchesFile/MatchesData hold
+        (loader.py:68-76, 103-118): u1, v1, u2, v2 int16, z f32, I (3,n) f32 — rows ordered row-major over
+        the target like torch.where (sfm.py:96).  Host numpy; meant for parity tests and --keep-matches."""
+        pixel, view = self.per_record_index()
+        out = {}
+        for vi, key in enumerate(self.source_keys):
+            if not self.view_kept[vi]:
+                continue
+            sel = (view == vi).nonzero(as_tuple=True)[0]
+            p = pixel[sel]
+            rec = self.records[sel].cpu().numpy()
+            entry = dict(u1=(p % self.width).to(torch.int16).cpu().numpy(),
+                         v1=(p // self.width).to(torch.int16).cpu().numpy(),
+                         z=rec[:, 0].copy(), I=np.ascontiguousarray(rec[:, 1:4].T))
+            if self.rec_src is not None:
+                src = self.rec_src[sel].cpu().numpy().view(np.uint32)
+                entry['u2'] = (src & 0xffff).astype(np.int16)
+                entry['v2'] = (src >> 16).astype(np.int16)
+            out[key] = entry
+        return out
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
+           target_record: np.ndarray | None = None) -> ObservationStore:
+    """Stage 1 on the device: match -> plan -> (one 16-byte D2H to size the store) -> sample.
+    Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
+    (sfm.py:127-138, loader.py:78-87, 103-118)."""
+    L = _lib.lib()
+    dev = scene.device
+    source_keys = tuple(source_keys)
+    V = len(source_keys)
+    if V == 0:
+        raise _lib.SucreError('gather: empty pairing list')
+    trec = scene.record(target_key) if target_record is None else target_record
+    W, H = int(trec['width']), int(trec['height'])
+    P = W * H
+    n_tiles = (P + TILE - 1) // TILE
+    table = scene.table(source_keys)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        masks = torch.empty((n_tiles, V), dtype=torch.int32, device=dev)
+        view_count = torch.empty(V, dtype=torch.int64, device=dev)
+        view_kept = torch.empty(V, dtype=torch.uint8, device=dev)
+        rec_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
+        blk_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
+        totals = torch.empty(2, dtype=torch.int64, device=dev)
+        tptr = trec.ctypes.data
+        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, masks.data_ptr(), st), 'sucre_gather_match')
+        _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, P, float(min_cover), view_count.data_ptr(),
+                                       view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
+                                       totals.data_ptr(), st), 'sucre_gather_plan')
+        n_obs, n_blocks = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
+        records = torch.empty((max(n_obs, 1), 4), dtype=torch.float32, device=dev)
+        blk_mask = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
+        blk_view = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
+        rec_src = torch.empty(max(n_obs, 1), dtype=torch.int32, device=dev) if keep_src else None
+        if n_obs > 0:
+            missing = [k for k in source_keys if k not in scene.rgb]
+            if missing:
+                raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
+            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, masks.data_ptr(), view_kept.data_ptr(),
+                                             rec_off.data_ptr(), blk_off.data_ptr(), n_tiles, records.data_ptr(),
+                                             blk_mask.data_ptr(), blk_view.data_ptr(),
+                                             0 if rec_src is None else rec_src.data_ptr(), st), 'sucre_gather_sample')
+        vc = view_count.cpu().numpy()
+        vk = view_kept.cpu().numpy().astype(bool)
+    return ObservationStore(width=W, height=H, source_keys=source_keys, view_count=vc, view_kept=vk, n_obs=n_obs,
+                            n_blocks=n_blocks, records=records[:n_obs], rec_off=rec_off, blk_off=blk_off,
+                            blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
+                            rec_src=None if rec_src is None else rec_src[:n_obs])
+
+
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class FitState:
+    """B, beta, gamma (9 floats, sucre.py:41-43) and Adam's fp32 moments, on the device."""
+    params: torch.Tensor   # (9,) f32: B[3], beta[3], gamma[3]
+    moments: torch.Tensor  # (18,) f32: exp_avg[9], exp_avg_sq[9]
+    step: int = 0
+
+    @staticmethod
+    def initial(device, params=None) -> 'FitState':
+        p = torch.full((9,), 0.1, dtype=torch.float32) if params is None else \
+            torch.as_tensor(params, dtype=torch.float32).reshape(9).clone()
+        return FitState(params=p.to(device), moments=torch.zeros(18, dtype=torch.float32, device=device))
+
+
+_workspaces: dict = {}
+
+
+def _workspace(device) -> torch.Tensor:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _workspaces:
+        _workspaces[key] = torch.empty(_lib.lib().sucre_fit_workspace_bytes(), dtype=torch.uint8, device=device)
+    return _workspaces[key]
+
+
+def _store_ptrs(store: ObservationStore):
+    return (store.records.data_ptr(), store.rec_off.data_ptr(), store.blk_off.data_ptr(), store.blk_mask.data_ptr(),
+            store.n_tiles)
+
+
+def fit_closed_form(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05,
+                    n_obs_global: int | None = None) -> torch.Tensor:
+    """num_iter iterations of adam() in --use-closed-form mode (sucre.py:138-148), entirely on the device.
+    Returns the (num_iter, 10) history tensor {params after each step, cost before it} (device)."""
+    if store.n_obs == 0:
+        raise _lib.SucreError('fit: the observation store is empty')
+    dev = store.records.device
+    history = torch.empty((num_iter, 10), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sucre_fit_closed_form(
+            *_store_ptrs(store), store.n_obs if n_obs_global is None else n_obs_global, state.params.data_ptr(),
+            state.moments.data_ptr(), state.step + 1, num_iter, float(lr), history.data_ptr(),
+            _workspace(dev).data_ptr(), _stream(dev)), 'sucre_fit_closed_form')
+    state.step += num_iter
+    return history
+
+
+def fit_sums_closed_form(store: ObservationStore, params: torch.Tensor, sums: torch.Tensor):
+    """One objective evaluation -> sums (10 doubles, device).  Building block of the multi-GPU loop."""
+    dev = store.records.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sucre_fit_sums_closed_form(*_store_ptrs(store), params.data_ptr(), sums.data_ptr(),
+                                                         _workspace(dev).data_ptr(), _stream(dev)),
+                   'sucre_fit_sums_closed_form')
+
+
+def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, history_row: torch.Tensor | None = None):
+    dev = state.params.device
+    state.step += 1
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sucre_adam_step(state.params.data_ptr(), state.moments.data_ptr(), sums.data_ptr(), n_obs,
+                                              state.step, float(lr), 0 if history_row is None else history_row.data_ptr(),
+                                              _stream(dev)), 'sucre_adam_step')
+
+
+def closed_form_J(store: ObservationStore, params: torch.Tensor) -> torch.Tensor:
+    """update_J (sucre.py:66-77) with the given parameters: (H,W,3) f32 on the device, NaN where unobserved."""
+    dev = store.records.device
+    J = torch.empty((store.height, store.width, 3), dtype=torch.float32, device=dev)
+    if store.n_obs == 0:
+        return J.fill_(float('nan'))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sucre_fit_write_J(*_store_ptrs(store), store.width * store.height, params.data_ptr(),
+                                                J.data_ptr(), _stream(dev)), 'sucre_fit_write_J')
+    return J

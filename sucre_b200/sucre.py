@@ -1,0 +1,324 @@
+"""SUCRe restoration with the reference's CLI and Python call surface (reference: sucre/sucre.py), running
+the gather and the fit as sm_100a CUDA kernels.
+
+    python -m sucre_b200.sucre --image-dir ... --depth-dir ... --model-dir ... --output-dir ... --image-name ...
+
+Same flags, defaults and output files as the reference (sucre.py:264-307, 212-215).  Differences a user can see:
+  * `--device` must be a CUDA device (there is no CPU path);
+  * the matches file kept by `--keep-matches` is `<stem>.matches.npz` (+ an empty `<stem>.h5` marker), not HDF5;
+  * `--light-model` is not implemented and raises;
+  * the per-iteration log lines are printed when the device loop returns, not while it runs.
+"""
+from __future__ import annotations
+
+import argparse
+from pathlib import Path
+
+import numpy as np
+import torch
+from PIL import Image
+from torch import Tensor
+from tqdm import tqdm
+
+from . import engine, loader, sfm
+
+
+class SUCRe:
+    """Underwater image formation model I = J e^{-beta z} + B (1 - e^{-gamma z}) (sucre.py:35-82).
+
+    Attributes B, beta, gamma are (3,1) tensors like the reference's Parameters (views of one 9-float device
+    buffer); J is (H,W,3)."""
+
+    def __init__(self, image: sfm.Image, light_model: bool = False, use_closed_form: bool = False):
+        if light_model:
+            raise NotImplementedError('--light-model (sucre.py:44-46, 54-61) is outside the CUDA hot path built so far')
+        self.image = image
+        self.light_model = light_model
+        self.use_closed_form = use_closed_form
+        self.state = engine.FitState(params=torch.full((9,), 0.1, dtype=torch.float32),
+                                     moments=torch.zeros(18, dtype=torch.float32))
+        self.J: Tensor | None = None
+        if not use_closed_form:
+            self.J = image.get_rgb()                              # sucre.py:48
+            self.J[image.get_depth_map() <= 0] = torch.nan        # sucre.py:49
+        self.J_moments: Tensor | None = None
+
+    # -- parameters -------------------------------------------------------------------------------------------
+    @property
+    def B(self) -> Tensor:
+        return self.state.params[0:3].view(3, 1)
+
+    @property
+    def beta(self) -> Tensor:
+        return self.state.params[3:6].view(3, 1)
+
+    @property
+    def gamma(self) -> Tensor:
+        return self.state.params[6:9].view(3, 1)
+
+    @property
+    def device(self) -> torch.device:
+        return self.state.params.device
+
+    def to(self, device) -> SUCRe:
+        self.state.params = self.state.params.to(device)
+        self.state.moments = self.state.moments.to(device)
+        if self.J is not None:
+            self.J = self.J.to(device)
+        if self.J_moments is not None:
+            self.J_moments = self.J_moments.to(device)
+        return self
+
+    def cpu(self) -> SUCRe:
+        return self.to('cpu')
+
+    def state_dict(self) -> dict:
+        sd = {'B': self.B.detach().clone(), 'beta': self.beta.detach().clone(), 'gamma': self.gamma.detach().clone()}
+        if not self.use_closed_form:
+            sd['J'] = self.J.detach().clone()
+        return sd
+
+    def load_state_dict(self, state_dict: dict, strict: bool = True):
+        known = {'B': 0, 'beta': 3, 'gamma': 6}
+        for key, value in state_dict.items():
+            if key in known:
+                self.state.params[known[key]:known[key] + 3] = torch.as_tensor(value, dtype=torch.float32).reshape(3).to(self.device)
+            elif key == 'J' and not self.use_closed_form:
+                self.J = torch.as_tensor(value, dtype=torch.float32).to(self.device)
+            elif strict:
+                raise KeyError(f'unexpected key {key!r} in state_dict')
+
+    # -- model ------------------------------------------------------------------------------------------------
+    def compute_l_z(self, cP: Tensor) -> tuple[float, Tensor]:
+        return 1.0, cP.norm(dim=0)  # sucre.py:53,63 without the light model
+
+    @torch.no_grad()
+    def update_J(self, matches_data: loader.MatchesData, force_update: bool = False):
+        """Closed-form J from the current B, beta, gamma (sucre.py:66-77) — one CUDA kernel over the store."""
+        if self.use_closed_form or force_update:
+            self.J = engine.closed_form_J(matches_data.store, self.state.params)
+
+    @torch.no_grad()
+    def forward(self, u: Tensor, v: Tensor, cP: Tensor) -> Tensor:
+        """I_hat (3,n) at pixels (u,v) with camera-frame points cP (sucre.py:79-82).  Used for the reconstruction
+        plot only; the fit evaluates the model inside its kernels."""
+        l, z = self.compute_l_z(cP)
+        return l * (self.J[v, u].T * torch.exp(-self.beta * z) + self.B * (1 - torch.exp(-self.gamma * z)))
+
+    __call__ = forward
+
+    # -- outputs (sucre.py:84-121), host side, once per image ----------------------------------------------------
+    @torch.no_grad()
+    def plot_J(self) -> Image.Image:
+        J = self.J.cpu().numpy().copy()
+        valid = np.all(~np.isnan(J), axis=2)
+        J_valid = J[valid]
+        J_valid = np.clip(J_valid, np.percentile(J_valid, 1, axis=0), np.percentile(J_valid, 99, axis=0))
+        J_valid = J_valid - np.min(J_valid, axis=0)
+        J_valid = J_valid / np.max(J_valid, axis=0)
+        J[~valid] = 0.0
+        J[valid] = J_valid
+        return Image.fromarray(np.uint8(J * 255))
+
+    @torch.no_grad()
+    def plot_reconstruction(self) -> Image.Image:
+        dev = self.device
+        depth = (self.image.get_depth_u16().to(torch.int32).to(dev).to(torch.float32) / 1000.0)
+        v, u = torch.where(depth > 0)
+        cp = torch.stack([u + 0.5, v + 0.5, torch.ones_like(u)])
+        cP = self.image.geom.Kinv.to(dev) @ (depth[v, u] * cp)
+        I_rec = torch.zeros((self.image.camera.height, self.image.camera.width, 3), device=dev)
+        I_rec[v, u] = self(u=u, v=v, cP=cP).clip(0, 1).T
+        return Image.fromarray(np.uint8(I_rec.cpu().numpy() * 255))
+
+    def save_plots(self, save_dir: Path, iteration: int = None):
+        save_path = (save_dir / self.image.name).with_suffix('.png')
+        suffix = '' if iteration is None else f'_{iteration:04d}'
+        self.plot_J().save(save_path.with_stem(f'{save_path.stem}_rgb{suffix}'))
+        self.plot_reconstruction().save(save_path.with_stem(f'{save_path.stem}_reconstruction{suffix}'))
+
+
+def _log_history(history: np.ndarray, first_iteration: int):
+    for k, row in enumerate(history):
+        with np.printoptions(precision=4):
+            tqdm.write(f'iter: {first_iteration + k:04d}, cost: {row[9]:.4e}, B: {row[0:3]}, '
+                       f'beta: {row[3:6]}, gamma: {row[6:9]}')
+
+
+def adam(
+        sucre: SUCRe,
+        matches_data: loader.MatchesData,
+        lr: float = 0.05,
+        num_iter: int = 200,
+        batch_size: int = 1,
+        save_dir: Path = None,
+        save_interval: int = None,
+        device: str = 'cuda'
+) -> SUCRe:
+    """Full-batch Adam on B, beta, gamma (and J in the default mode), sucre.py:124-157.  `batch_size` only
+    grouped views for memory in the reference (gradients accumulate over all batches before the single
+    optimizer.step()), so it has no effect here: every iteration streams the whole store once."""
+    print(f'Solve least squares with Adam optimizer ({num_iter} iterations).')
+    if not sucre.use_closed_form:
+        raise NotImplementedError('default mode (J as an Adam parameter, sucre.py:47-50) is not built yet; '
+                                  'pass --use-closed-form')
+    # iterations at which the reference saves intermediate plots (sucre.py:153-154): it % save_interval == 0,
+    # after the step of iteration `it`, with J as of the top of that iteration
+    chunk_ends = [num_iter]
+    if save_dir is not None and save_interval is not None:
+        chunk_ends = sorted({it + 1 for it in range(0, num_iter, save_interval)} | {num_iter})
+    done = 0
+    histories = []
+    for end in chunk_ends:
+        n = end - done
+        if save_dir is not None and save_interval is not None and (end - 1) % save_interval == 0 and n > 0:
+            # run up to the iteration to be plotted, evaluate J with its pre-step parameters, then step
+            if n > 1:
+                histories.append(engine.fit_closed_form(matches_data.store, sucre.state, n - 1, lr))
+            sucre.update_J(matches_data)
+            histories.append(engine.fit_closed_form(matches_data.store, sucre.state, 1, lr))
+            sucre.save_plots(save_dir=save_dir, iteration=end - 1)
+        elif n > 0:
+            histories.append(engine.fit_closed_form(matches_data.store, sucre.state, n, lr))
+        done = end
+    if histories:
+        _log_history(torch.cat(histories).cpu().numpy(), 0)
+    sucre.update_J(matches_data=matches_data)  # sucre.py:156
+    sucre.history = torch.cat(histories) if histories else None
+    return sucre
+
+
+def restore_image(
+        image: sfm.Image,
+        colmap_model: sfm.COLMAPModel,
+        output_dir: Path,
+        light_model: bool = False,
+        use_closed_form: bool = False,
+        min_cover: float = 0.000001,
+        image_list: list[sfm.Image] = None,
+        lr: float = 0.05,
+        num_iter: int = 200,
+        batch_size: int = 1,
+        save_interval: int = None,
+        params_path: Path = None,
+        force_compute_matches: bool = False,
+        keep_matches: bool = False,
+        num_workers: int = 0,
+        device: str = 'cuda'
+):
+    """Drop-in for the reference's restore_image (sucre.py:160-219): same arguments, same prints, same files."""
+    print(f'Restore {image.name}.')
+    matches_path = (output_dir / image.name).with_suffix('.h5')
+    matches_file = loader.MatchesFile(matches_path, colmap_model=colmap_model, overwrite=force_compute_matches)
+
+    if image_list is None:
+        image_list = list(colmap_model.images.values())
+
+    if force_compute_matches or not matches_file.exists():
+        print(f'Compute {image.name} matches.')
+        image.match_images(image_list=image_list, matches_file=matches_file, min_cover=min_cover,
+                           num_workers=num_workers, device=device)
+        print('Prepare matches for optimization.')
+        matches_file.prepare_matches(num_workers=num_workers)
+
+    print('Check matches integrity.')
+    matches_file.check_integrity()
+
+    print('Load matches.')
+    matches_data = matches_file.load_matches(pin_memory=False, device=device)
+    print(f'Total of {len(matches_data)} observations.')
+
+    sucre = SUCRe(image=image, light_model=light_model, use_closed_form=use_closed_form).to(device)
+
+    if params_path is not None:
+        sucre.load_state_dict(torch.load(params_path), strict=False)
+
+    adam(sucre=sucre, matches_data=matches_data, lr=lr, num_iter=num_iter, batch_size=batch_size,
+         save_dir=output_dir, save_interval=save_interval, device=device)
+
+    sucre.save_plots(save_dir=output_dir)
+    J = sucre.J.detach().cpu()
+    torch.save({**sucre.cpu().state_dict(), 'J': J}, (output_dir / image.name).with_suffix('.pt'))
+
+    if keep_matches:
+        matches_file.save()
+    else:
+        print(f'Erase {matches_path}.')
+        matches_file.unlink()
+    return None
+
+
+def parse_args(args: argparse.Namespace):
+    print('Loading COLMAP model.')
+    colmap_model = sfm.COLMAPModel(model_dir=args.model_dir, image_dir=args.image_dir, depth_dir=args.depth_dir,
+                                   image_scale=args.image_scale)
+
+    if args.image_name is not None:
+        images = [colmap_model[args.image_name]]
+    elif args.image_list is not None:
+        images = [colmap_model[image_name] for image_name in args.image_list.read_text().splitlines()]
+    else:
+        images = [colmap_model.images[image_id] for image_id in range(*args.image_ids)
+                  if image_id in colmap_model.images]
+
+    # Filter images that should not be used for pairing (sucre.py:237-239)
+    filter_image_names = args.filter_images_path.read_text().splitlines() if args.filter_images_path else []
+    image_list = [im for im in colmap_model.images.values() if im.name not in filter_image_names]
+
+    args.output_dir.mkdir(parents=True, exist_ok=True)
+
+    for image in images:
+        restore_image(
+            image=image, colmap_model=colmap_model, output_dir=args.output_dir, light_model=args.light_model,
+            use_closed_form=args.use_closed_form, min_cover=args.min_cover, image_list=image_list,
+            lr=args.learning_rate, num_iter=args.num_iter, batch_size=args.batch_size,
+            save_interval=args.save_interval, params_path=args.params_path,
+            force_compute_matches=args.force_compute_matches, keep_matches=args.keep_matches,
+            num_workers=args.num_workers, device=args.device)
+
+
+def build_parser() -> argparse.ArgumentParser:
+    """Flag-for-flag the reference's parser (sucre.py:265-305)."""
+    parser = argparse.ArgumentParser(description='SUCRe.', formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument('--image-dir', required=True, type=Path, help='path to images directory.')
+    parser.add_argument('--depth-dir', required=True, type=Path, help='path to depth maps directory.')
+    parser.add_argument('--model-dir', required=True, type=Path, help='path to undistorted COLMAP model directory.')
+    parser.add_argument('--output-dir', required=True, type=Path, help='path to output directory.')
+    parser_images = parser.add_mutually_exclusive_group(required=True)
+    parser_images.add_argument('--image-name', type=str, help='name of image to restore.')
+    parser_images.add_argument('--image-list', type=Path,
+                               help='path to .txt file with names of images to restore, one name per line.')
+    parser_images.add_argument('--image-ids', type=int, nargs=2, metavar=('MIN_ID', 'MAX_ID'),
+                               help='range of ids of images to restore in the COLMAP model [min, max).')
+    parser.add_argument('--light-model', action='store_true', help='model artificial lights.')
+    parser.add_argument('--use-closed-form', action='store_true',
+                        help='use the partial closed-form solution for computing the restored image from '
+                             'absorption, backscatter and light parameters.')
+    parser.add_argument('--min-cover', type=float, default=0.000001,
+                        help='minimum percentile of shared observations to keep the pairs of an image.')
+    parser.add_argument('--image-scale', type=float, default=1.0, help='rescale all images by this factor.')
+    parser.add_argument('--filter-images-path', type=Path,
+                        help='path to a .txt file with names of images to discard when computing matches, '
+                             'one name per line.')
+    parser.add_argument('--learning-rate', type=float, default=0.05, help='learning rate for Adam optimizer.')
+    parser.add_argument('--num-iter', type=int, default=200, help='number of optimization steps.')
+    parser.add_argument('--batch-size', type=int, default=5,
+                        help='batch size for adam optimization (kept for compatibility: the CUDA fit streams all '
+                             'observations every iteration).')
+    parser.add_argument('--save-interval', type=int, help='save restored image every given optimization step.')
+    parser.add_argument('--params-path', type=Path,
+                        help='load underwater image formation model parameters from .pt file.')
+    parser.add_argument('--force-compute-matches', action='store_true',
+                        help='if matches file already exists, erase it and recompute matches.')
+    parser.add_argument('--keep-matches', action='store_true', help='keep matches file (can take a lot a space).')
+    parser.add_argument('--num-workers', type=int, default=0, help='number of decode threads, 0 is the main thread.')
+    parser.add_argument('--device', type=str, default='cuda', help='CUDA device for the computation.')
+    return parser
+
+
+def main(argv=None):
+    parse_args(build_parser().parse_args(argv))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,41 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/sucre_b200.h declares; the product never
+imports the oracle."""
+import ctypes
+import re
+from pathlib import Path
+
+from sucre_b200 import _lib
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_header_symbols_are_exported():
+    header = (ROOT / 'include' / 'sucre_b200.h').read_text()
+    declared = set(re.findall(r'\b(sucre_[A-Za-z_0-9]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()  # binds every symbol; AttributeError if one is missing
+    assert L.sucre_abi_version() == _lib.ABI_VERSION
+    assert L.sucre_fit_workspace_bytes() > 0
+    assert L.sucre_last_error() == b''
+
+
+def test_view_struct_layout_matches_header():
+    header = (ROOT / 'include' / 'sucre_b200.h').read_text()
+    assert 'float K[9], Kinv[9], R[9], t[3], Ri[9], ti[3];' in header
+    assert _lib.VIEW_DTYPE.itemsize == 192
+    assert [_lib.VIEW_DTYPE.fields[n][1] for n in ('K', 'Kinv', 'R', 't', 'Ri', 'ti', 'width', 'height', 'depth', 'rgb')] \
+        == [0, 36, 72, 108, 120, 156, 168, 172, 176, 184]
+
+
+def test_argument_errors_without_gpu():
+    L = _lib.lib()
+    assert L.sucre_gather_plan(0, 1, 1, 1, 0.0, 0, 0, 0, 0, 0, 0) != 0
+    assert b'null' in L.sucre_last_error()
+    assert L.sucre_adam_step(0, 0, 0, 1, 1, 0.05, 0, 0) != 0
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / 'sucre_b200').rglob('*'):
+        if path.suffix in ('.py', '.cu', '.cuh', '.h'):
+            text = path.read_text()
+            assert 'oracle' not in text.lower().replace('oracle/ ', ''), f'{path} mentions the oracle'

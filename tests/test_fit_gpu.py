@@ -1,0 +1,109 @@
+"""Parity of the CUDA fit (through the C ABI) with the oracle and the reference's trajectories.
+Tolerances are BASELINE.json's: J within 1e-3 max-abs, B / beta / gamma within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from sucre_b200 import engine
+from sucre_b200.synth import SyntheticScene
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+J_ATOL = 1e-3
+P_RTOL = 1e-4
+
+
+def _rel(a, b, floor=1e-12):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+@pytest.mark.parametrize('case', ['tiny6_closed', 'mixed8_image0004', 'mixed8_image0002'])
+def test_closed_form_fit_vs_reference_golden(golden, case):
+    g = golden(case)
+    ds, _ = helpers.golden_device_scene(g)
+    names = g['names'].tolist()
+    order = sorted((names[i] for i in g.pairing_list()))
+    store = engine.gather(ds, str(g['target']), order, min_cover=float(g['min_cover']))
+    state = engine.FitState.initial(ds.device)
+    hist = engine.fit_closed_form(store, state, int(g['num_iter'])).cpu().numpy()
+    J = engine.closed_form_J(store, state.params).cpu().numpy()
+    ref_p = np.concatenate([g['B'].ravel(), g['beta'].ravel(), g['gamma'].ravel()])
+    assert _rel(state.params.cpu().numpy(), ref_p) < P_RTOL
+    assert _rel(hist[:, :9], g['history'], floor=0.05) < P_RTOL      # whole trajectory; params cross zero mid-run
+    assert _rel(hist[:, 9], g['cost']) < 2e-4                        # reference prints 5 significant digits
+    assert np.array_equal(np.isnan(J), np.isnan(g['J']))             # identical NaN set
+    assert np.nanmax(np.abs(J - g['J'])) < J_ATOL
+
+
+def test_closed_form_fit_vs_oracle_config1():
+    """configs[0] shape, 40 iterations, against the oracle on the same observations."""
+    scene = SyntheticScene(20, 640, 480, seed=0)
+    ds, host = helpers.build_device_scene(scene, range(20), render_device='cuda')
+    store = engine.gather(ds, 8, list(range(20)))
+    kept, _ = helpers.oracle_gather(host, 8, list(range(20)))
+    ref = oracle.fit([o for _, o in kept], 640, 480, closed_form=True, num_iter=40)
+    state = engine.FitState.initial(ds.device)
+    hist = engine.fit_closed_form(store, state, 40).cpu().numpy()
+    J = engine.closed_form_J(store, state.params).cpu().numpy()
+    assert _rel(state.params.cpu().numpy(), ref['params']) < P_RTOL
+    assert _rel(hist[:, :9], ref['history'], floor=0.05) < P_RTOL
+    assert _rel(hist[:, 9], ref['cost']) < 1e-5
+    assert np.array_equal(np.isnan(J), np.isnan(ref['J']))
+    assert np.nanmax(np.abs(J - ref['J'])) < J_ATOL
+
+
+def test_fit_building_blocks_match_fused_loop(golden):
+    """sums + adam_step (the multi-GPU building blocks) reproduce the fused single-GPU loop bit for bit,
+    and splitting a run in two (state carried over) changes nothing."""
+    g = golden('tiny6_closed')
+    ds, _ = helpers.golden_device_scene(g)
+    store = engine.gather(ds, str(g['target']), sorted(g['names'].tolist()))
+    a = engine.FitState.initial(ds.device)
+    ha = engine.fit_closed_form(store, a, 12)
+    b = engine.FitState.initial(ds.device)
+    sums = torch.zeros(10, dtype=torch.float64, device=ds.device)
+    rows = torch.zeros((12, 10), dtype=torch.float32, device=ds.device)
+    for it in range(12):
+        engine.fit_sums_closed_form(store, b.params, sums)
+        engine.adam_step(b, sums, store.n_obs, 0.05, rows[it])
+    assert torch.equal(a.params, b.params) and torch.equal(ha, rows) and a.step == b.step == 12
+    c = engine.FitState.initial(ds.device)
+    hc = torch.cat([engine.fit_closed_form(store, c, 5), engine.fit_closed_form(store, c, 7)])
+    assert torch.equal(a.params, c.params) and torch.equal(ha, hc)
+
+
+def test_fit_is_deterministic(golden):
+    g = golden('mixed8_image0004')
+    ds, _ = helpers.golden_device_scene(g)
+    names = g['names'].tolist()
+    store = engine.gather(ds, str(g['target']), sorted(names[i] for i in g.pairing_list()), min_cover=float(g['min_cover']))
+    runs = []
+    for _ in range(2):
+        s = engine.FitState.initial(ds.device)
+        runs.append((engine.fit_closed_form(store, s, 10).clone(), s.params.clone()))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+
+
+def test_recovers_ground_truth_parameters():
+    """Size-independent property: on noise-free synthetic data the fit moves toward the generating model —
+    the cost falls by > 10x and closed-form J stays within the texture's range on observed pixels."""
+    scene = SyntheticScene(9, 160, 120, seed=2)
+    ds, _ = helpers.build_device_scene(scene, range(9))
+    store = engine.gather(ds, 4, list(range(9)))
+    state = engine.FitState.initial(ds.device)
+    hist = engine.fit_closed_form(store, state, 200).cpu().numpy()
+    assert hist[-1, 9] < hist[0, 9] / 10
+    J = engine.closed_form_J(store, state.params).cpu().numpy()
+    assert np.nanmin(J) > -0.5 and np.nanmax(J) < 1.5
+
+
+def test_empty_store_raises():
+    scene = SyntheticScene(2, 64, 48, seed=1)
+    ds, _ = helpers.build_device_scene(scene, range(2))
+    store = engine.gather(ds, 0, [0, 1], min_cover=1.0)
+    with pytest.raises(engine._lib.SucreError):
+        engine.fit_closed_form(store, engine.FitState.initial(ds.device), 3)
+    assert torch.isnan(engine.closed_form_J(store, engine.FitState.initial(ds.device).params)).all()

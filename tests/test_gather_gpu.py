@@ -1,0 +1,78 @@
+"""Parity of the CUDA gather (through the C ABI) with the oracle and with the reference's own outputs."""
+import numpy as np
+import pytest
+import torch
+
+from sucre_b200 import engine
+from sucre_b200.synth import SyntheticScene
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+FULL = ['tiny6_closed', 'mixed8_image0004', 'mixed8_image0002']
+
+
+@pytest.mark.parametrize('case', FULL)
+def test_gather_vs_reference_golden(golden, case):
+    """Bit-exact against arrays captured from the unmodified reference (indices, z, I; kept views; order)."""
+    g = golden(case)
+    ds, _ = helpers.golden_device_scene(g)
+    names = g['names'].tolist()
+    order = sorted((names[i] for i in g.pairing_list()))
+    store = engine.gather(ds, str(g['target']), order, min_cover=float(g['min_cover']), keep_src=True)
+    assert store.kept_keys == g['kept'].tolist()
+    got = store.to_reference_layout()
+    total = 0
+    for name in g['kept'].tolist():
+        ref = g.matches(name)
+        for f in ('u1', 'v1', 'u2', 'v2'):
+            assert np.array_equal(got[name][f], ref[f]), (name, f)
+        assert np.array_equal(got[name]['z'].view(np.uint32), ref['z'].view(np.uint32)), (name, 'z')
+        assert np.array_equal(got[name]['I'].view(np.uint32), ref['I'].view(np.uint32)), (name, 'I')
+        total += len(ref['u1'])
+    assert store.n_obs == total == len(store)
+
+
+def test_gather_vs_oracle_config1():
+    """BASELINE.json configs[0] shape (20 views 640x480): every pixel-view against the oracle."""
+    scene = SyntheticScene(20, 640, 480, seed=0)
+    ds, host = helpers.build_device_scene(scene, range(20), render_device='cuda')
+    kept, stats = helpers.oracle_gather(host, 8, list(range(20)))
+    store = engine.gather(ds, 8, list(range(20)), keep_src=True)
+    assert store.view_count.tolist() == [stats[i][0] for i in range(20)]
+    bad = helpers.compare_store_with_oracle(store, kept)
+    assert bad['idx'] == 0 and bad['z'] == 0 and bad['I'] == 0, bad
+    assert bad['n'] == store.n_obs > 3_000_000
+
+
+def test_gather_ragged_and_degenerate():
+    """Edge cases: image size not a multiple of the 32-pixel tile, a target that is not in the pairing list,
+    a min_cover that drops every view, views with all-invalid depth."""
+    scene = SyntheticScene(5, 75, 41, seed=5)  # 3075 pixels = 96 tiles + 3 pixels
+    ds, host = helpers.build_device_scene(scene, range(5))
+    # target excluded from its own pairing list: some valid pixels end up unobserved
+    src = [0, 1, 3, 4]
+    kept, stats = helpers.oracle_gather(host, 2, src)
+    store = engine.gather(ds, 2, src, keep_src=True)
+    assert helpers.compare_store_with_oracle(store, kept) == dict(idx=0, z=0, I=0, n=store.n_obs)
+    # min_cover = 1.0 can never be exceeded -> empty store
+    empty = engine.gather(ds, 2, src, min_cover=1.0)
+    assert empty.n_obs == 0 and empty.n_blocks == 0 and not empty.view_kept.any()
+    assert empty.view_count.tolist() == [stats[i][0] for i in src]
+    # a view whose depth map is all zero never matches and is dropped
+    geom = ds.geom[1]
+    ds.add_view('blank', geom, torch.zeros((geom.height, geom.width), dtype=torch.uint16), ds.rgb[1])
+    store2 = engine.gather(ds, 2, [0, 'blank', 1])
+    assert store2.view_count[1] == 0 and not store2.view_kept[1] and store2.view_kept[0] and store2.view_kept[2]
+
+
+def test_gather_api_errors():
+    scene = SyntheticScene(2, 64, 48, seed=1)
+    ds, _ = helpers.build_device_scene(scene, range(2))
+    with pytest.raises(engine._lib.SucreError):
+        engine.gather(ds, 0, [])
+    with pytest.raises(engine._lib.SucreError):
+        engine.DeviceScene('cpu')
+    L = engine._lib.lib()
+    assert L.sucre_gather_match(0, 0, 1, 0, 0) != 0 and b'null' in L.sucre_last_error()
