@@ -89,18 +89,33 @@ int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, 
  * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for
  * light_model=False.  params = {B[3], beta[3], gamma[3]} fp32 (sucre.py:41-43).
  *
- * sucre_fit_workspace_bytes: size of the scratch buffer the fit calls need (per-CTA partial sums). */
+ * mode SUCRE_FIT_CLOSED_FORM  --use-closed-form: per pixel J = sum((I - B(1-e^{-gamma z})) e^{-beta z}) /
+ *                             sum(e^{-2 beta z}) from the CURRENT params (sucre.py:66-77), residuals against it.
+ *                             J[pixels*3] is a work buffer (zero it before the first iteration): it carries the
+ *                             J of the previous iteration, the reference point of the single-sweep statistics.
+ * mode SUCRE_FIT_PARAM_J      default CLI mode: J[pixels*3] is an Adam parameter (sucre.py:47-50), initialised by
+ *                             the caller to the target image with NaN where target depth <= 0; J_moments
+ *                             [pixels*6] = per pixel {exp_avg[3], exp_avg_sq[3]}, zero-initialised.
+ * Every iteration reads each record exactly once. */
+#define SUCRE_FIT_CLOSED_FORM 0
+#define SUCRE_FIT_PARAM_J 1
+
+/* Size of the scratch buffer of the fit calls (16-byte aligned, one per observation store). */
 size_t sucre_fit_workspace_bytes(void);
 
-/* One evaluation of the closed-form objective (--use-closed-form): per pixel J = sum((I - B(1-e^{-gamma z}))
- * e^{-beta z}) / sum(e^{-2 beta z}) with the CURRENT params (sucre.py:66-77), then residuals r = I - (J e^{-beta z}
- * + B(1-e^{-gamma z})) (sucre.py:81) reduced to sums[10] (double):
+/* Once per observation store, before any other fit call on `workspace`: partitions the tiles over the
+ * resident warps by block count (static => reproducible summation order). */
+int sucre_fit_prepare(const int64_t* blk_off, int n_tiles, void* workspace, void* stream);
+
+/* One evaluation of the objective at `params`, reduced to sums[10] (double):
  *   sums[0..2] = sum r(1-e^{-gamma z}), sums[3..5] = sum r J z e^{-beta z}, sums[6..8] = sum r B z e^{-gamma z},
- *   sums[9] = sum r^2 (the `cost` the reference logs, sucre.py:144-146,150).
- * Multi-GPU callers all-reduce sums between this call and sucre_adam_step. */
-int sucre_fit_sums_closed_form(const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                               const uint32_t* blk_mask, int n_tiles, const float* params, double* sums,
-                               void* workspace, void* stream);
+ *   sums[9] = sum r^2 (the `cost` the reference logs, sucre.py:144-146,150),
+ * r = I - (J e^{-beta z} + B(1-e^{-gamma z})) (sucre.py:81).  In SUCRE_FIT_PARAM_J mode the per-pixel Adam step t of
+ * J (gradient -(2/(3 n_obs)) sum r e^{-beta z}) is applied in the same pass; n_obs, t, lr are ignored otherwise.
+ * Multi-GPU callers all-reduce sums between this call and sucre_adam_step; n_obs is then the global count. */
+int sucre_fit_sums(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
+                   const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params, float* J,
+                   float* J_moments, int64_t n_obs, int t, double lr, double* sums, void* workspace, void* stream);
 
 /* Adam step t (1-based) on the 9 parameters from the reduced sums: gradients of sum r^2 / (3 n_obs)
  * (sucre.py:144-145), update rule of torch.optim.Adam defaults (sucre.py:136,148: betas .9/.999, eps 1e-8,
@@ -108,18 +123,19 @@ int sucre_fit_sums_closed_form(const float* records, const int64_t* rec_off, con
 int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_t n_obs, int t, double lr,
                     float* history_row, void* stream);
 
-/* The whole single-GPU loop of adam() in closed-form mode: num_iter x {sums, step}, then nothing else
- * (call sucre_fit_write_J for the final update_J, sucre.py:156).  history = num_iter x 10 floats. */
-int sucre_fit_closed_form(const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                          const uint32_t* blk_mask, int n_tiles, int64_t n_obs, float* params,
-                          float* adam_state, int first_step, int num_iter, double lr, float* history,
-                          void* workspace, void* stream);
+/* The whole single-GPU loop of adam() (sucre.py:138-148): num_iter kernels, each = one sweep + the Adam step of
+ * the 9 scalars (steps first_step .. first_step+num_iter-1).  history (optional) = num_iter x 10 floats.
+ * For the final update_J of closed-form mode (sucre.py:156) call sucre_fit_write_J. */
+int sucre_fit(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
+              const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, int64_t n_obs, float* params,
+              float* adam_state, float* J, float* J_moments, int first_step, int num_iter, double lr,
+              float* history, void* workspace, void* stream);
 
 /* Closed-form J for the current params written to J[target_pixels*3] (H,W,3); NaN where a pixel has no
- * observation (0/0 like sucre.py:77). */
+ * observation (0/0 like sucre.py:77).  J_ref (optional): a previous J used as the reference point. */
 int sucre_fit_write_J(const float* records, const int64_t* rec_off, const int64_t* blk_off,
                       const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params,
-                      float* J, void* stream);
+                      const float* J_ref, float* J, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
 ABI_VERSION = 1
 TILE = 32
+FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
 
 # numpy mirror of `struct sucre_view` (192 bytes)
 VIEW_DTYPE = np.dtype([('K', '<f4', 9), ('Kinv', '<f4', 9), ('R', '<f4', 9), ('t', '<f4', 3), ('Ri', '<f4', 9),
@@ -32,10 +33,11 @@ _SIGNATURES = {
     'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
     'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
     'sucre_fit_workspace_bytes': (C.c_size_t, []),
-    'sucre_fit_sums_closed_form': (C.c_int, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
+    'sucre_fit_prepare': (C.c_int, [_VP, _I, _VP, _VP]),
+    'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
     'sucre_adam_step': (C.c_int, [_VP, _VP, _VP, _I64, _I, _D, _VP, _VP]),
-    'sucre_fit_closed_form': (C.c_int, [_VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
-    'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP]),
+    'sucre_fit': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I, _I64, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
+    'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP, _VP]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -2,110 +2,246 @@
 //
 // One warp owns one tile (32 consecutive target pixels), one lane one pixel.  The tile's observations are a
 // contiguous run of 16-byte records {z, I_r, I_g, I_b}; per block (= source view) the matched lanes read
-// consecutive records, i.e. one coalesced 128-bit load per lane.  Sweep 1 forms the closed-form J of the
-// lane's pixel (sucre.py:66-77), sweep 2 re-reads the same records (L1/L2 hits, the tile was just streamed)
-// and accumulates the residual sums that are the gradients of B, beta, gamma with J held constant
-// (sucre.py:79-82, 144-145).  Per-thread fp32 sums over one tile are promoted to double per tile, reduced
-// with warp shuffles, then one double partial per CTA; a single small CTA finishes the reduction in a fixed
-// order and applies torch.optim.Adam's update to the 9 scalars on the device, so 200 iterations need no host
-// round trip.
+// consecutive records: one coalesced 128-bit load per lane, four blocks in flight per warp.
+//
+// Every Adam iteration reads every record exactly ONCE.  The reference makes two passes (update_J, then
+// forward/backward with J held constant, sucre.py:141-146); here both come out of one sweep through per-pixel
+// sufficient statistics of the SHIFTED residual D' = I - B(1 - e^{-gamma z}) - Jref e^{-beta z}, where Jref is
+// the pixel's J of the previous iteration (kept in HBM, 12 B/pixel):
+//     S1 = sum D' a   S2 = sum a^2   S3 = sum D' h   S4 = sum a h   S5 = sum D' z a   S6 = sum z a^2
+//     S7 = sum D' z g S8 = sum a z g S9 = sum D'^2            (a = e^{-beta z}, g = e^{-gamma z}, h = 1 - g)
+//     delta = S1 / S2,  J = Jref + delta                      (closed form, sucre.py:66-77)
+//     sum r h = S3 - delta S4, sum r z a = S5 - delta S6, sum r z g = S7 - delta S8, sum r^2 = S9 - delta S1
+// with r = I - (J a + B h) the reference's residual (sucre.py:81).  Shifting by Jref keeps every product at
+// residual scale, so the subtraction-of-sums above does not cancel (an unshifted one-sweep form loses ~3 digits).
+// In the default mode (J is itself an Adam parameter, sucre.py:47-50) Jref IS J, delta = 0, and the pixel's own
+// Adam update is applied in the same kernel.
+//
+// Global sums: per-pixel values are promoted to double per thread, reduced by warp shuffles, one double row per
+// CTA; the last CTA to finish (ticket counter) reduces the rows in a fixed order and applies torch.optim.Adam's
+// update to the 9 scalars, so an iteration is ONE kernel and 200 iterations need no host round trip.
+// Tiles are statically partitioned over the resident warps by block count (sucre_fit_prepare), so the summation
+// order — and therefore every bit of the result — is reproducible run to run.
 #include "common.cuh"
 
 namespace sucre {
 
 constexpr int kFitThreads = 256;
+constexpr int kFitWarps = kFitThreads / 32;
 constexpr int kMaxFitCtas = 2048;
 constexpr int kSums = 10;
+constexpr float kLog2e = 1.4426950408889634f;
 
-struct Params9 {
-    float B[3], beta[3], gamma[3];
+// workspace layout (bytes)
+constexpr size_t kWsPartials = 0;                                                   // double[kMaxFitCtas][kSums]
+constexpr size_t kWsPartition = kWsPartials + sizeof(double) * kSums * kMaxFitCtas;  // int[kMaxFitCtas*kFitWarps + 1]
+constexpr size_t kWsTicket = kWsPartition + sizeof(int) * (kMaxFitCtas * kFitWarps + 1 + 3);  // unsigned, 16-aligned
+constexpr size_t kWsBytes = kWsTicket + 16;
+
+enum FitMode { kClosedForm = 0, kParamJ = 1, kWriteJ = 2 };
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct Coef {
+    float B[3], kb[3], kg[3];  // kb = -beta log2(e), kg = -gamma log2(e): e^{-beta z} = 2^{kb z}
+    float beta[3], gamma[3];
 };
 
-__device__ __forceinline__ Params9 load_params(const float* __restrict__ p) {
-    Params9 q;
+__device__ __forceinline__ Coef load_coef(const float* __restrict__ p) {
+    Coef q;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         q.B[c] = p[c];
         q.beta[c] = p[3 + c];
         q.gamma[c] = p[6 + c];
+        q.kb[c] = -q.beta[c] * kLog2e;
+        q.kg[c] = -q.gamma[c] * kLog2e;
     }
     return q;
 }
 
-// Walks the blocks of one tile; F(record) is called for the lanes whose pixel is matched in the block.
-template <class F>
-__device__ __forceinline__ void for_each_record(const float4* __restrict__ records, const uint32_t* __restrict__ blk_mask,
-                                                long long rec, long long b0, int nb, int lane, F&& f) {
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int j0 = 0; j0 < nb; j0 += 32) {
-        const int nj = min(32, nb - j0);
-        const uint32_t mload = lane < nj ? __ldg(blk_mask + b0 + j0 + lane) : 0u;  // 32 block masks per coalesced load
-#pragma unroll 4
-        for (int j = 0; j < nj; ++j) {
-            const uint32_t m = __shfl_sync(kFull, mload, j);
-            if ((m >> lane) & 1u) f(__ldg(records + rec + __popc(m & lt)));
-            rec += __popc(m);
-        }
-    }
+// torch.optim.Adam (single-tensor, non-capturable CPU branch the reference runs): fp32 state and params,
+// python-float (double) scalars rounded to fp32 where they meet a tensor.  step_size = lr / (1 - 0.9^t),
+// bc2_sqrt = sqrt(1 - 0.999^t) are evaluated in double by the caller.
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float neg_step_size, float bc2_sqrt) {
+    m = m + (float)(1.0 - 0.9) * (g - m);                 // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * (float)0.999 + (float)(1.0 - 0.999) * (g * g);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + (float)1e-8;
+    return p + neg_step_size * (m / denom);               // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-// sweep 1: closed-form J of this lane's pixel.  0/0 = NaN when the pixel has no observation (sucre.py:77).
-__device__ __forceinline__ void closed_form_J(const float4* __restrict__ records, const uint32_t* __restrict__ blk_mask,
-                                              long long rec, long long b0, int nb, int lane, const Params9& q, float J[3]) {
-    float num[3] = {0.f, 0.f, 0.f}, den[3] = {0.f, 0.f, 0.f};
-    for_each_record(records, blk_mask, rec, b0, nb, lane, [&](const float4 r) {
+struct AdamScalars {
+    float neg_step_size, bc2_sqrt;
+    double grad_scale;  // 2 / (3 n_obs): d/dtheta of sum r^2 / n_obs / 3 (sucre.py:145)
+};
+
+static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
+    const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+    AdamScalars s;
+    s.neg_step_size = (float)(-(lr / bc1));
+    s.bc2_sqrt = (float)sqrt(bc2);
+    s.grad_scale = 2.0 / (3.0 * (double)n_obs);
+    return s;
+}
+
+template <int MODE, bool PRECISE>
+struct PixelStats {
+    // closed form: 9 statistics per channel; J parameter: S2, S4, S6, S8 are not needed; write-J: S1, S2 only
+    float S1[3], S2[3], S3[3], S4[3], S5[3], S6[3], S7[3], S8[3], S9[3];
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S1[c] = S2[c] = S3[c] = S4[c] = S5[c] = S6[c] = S7[c] = S8[c] = S9[c] = 0.f;
+    }
+
+    __device__ __forceinline__ void add(const float4 r, const Coef& q, const float Jref[3]) {
+        const float z = r.x;
         const float I[3] = {r.y, r.z, r.w};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float a = expf(-q.beta[c] * r.x);
-            const float bs = q.B[c] * (1.0f - expf(-q.gamma[c] * r.x));
-            num[c] += (I[c] - bs) * a;
-            den[c] += a * a;
+            const float a = PRECISE ? expf(-q.beta[c] * z) : fast_exp2(q.kb[c] * z);
+            const float g = PRECISE ? expf(-q.gamma[c] * z) : fast_exp2(q.kg[c] * z);
+            const float D = fmaf(q.B[c], g, I[c] - q.B[c]);  // I - B (1 - g)
+            const float Dp = fmaf(-Jref[c], a, D);           // shifted residual
+            S1[c] = fmaf(Dp, a, S1[c]);
+            if (MODE != kParamJ) S2[c] = fmaf(a, a, S2[c]);
+            if (MODE == kWriteJ) continue;
+            const float h = 1.0f - g, za = z * a, zg = z * g;
+            S3[c] = fmaf(Dp, h, S3[c]);
+            S5[c] = fmaf(Dp, za, S5[c]);
+            S7[c] = fmaf(Dp, zg, S7[c]);
+            S9[c] = fmaf(Dp, Dp, S9[c]);
+            if (MODE == kClosedForm) {
+                S4[c] = fmaf(a, h, S4[c]);
+                S6[c] = fmaf(a, za, S6[c]);
+                S8[c] = fmaf(a, zg, S8[c]);
+            }
         }
-    });
-#pragma unroll
-    for (int c = 0; c < 3; ++c) J[c] = num[c] / den[c];
+    }
+};
+
+// Streams the records of one tile through `st`.  Four blocks (source views) per step: their masks are
+// warp-uniform loads, the four 128-bit record loads are issued before any arithmetic.
+template <class Stats>
+__device__ __forceinline__ int sweep_tile(const float4* __restrict__ records, const uint32_t* __restrict__ blk_mask,
+                                          long long rec, long long b0, int nb, int lane, const Coef& q,
+                                          const float Jref[3], Stats& st) {
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t* __restrict__ mk = blk_mask + b0;
+    int seen = 0;
+    int j = 0;
+    for (; j + 4 <= nb; j += 4) {
+        const uint32_t m0 = __ldg(mk + j), m1 = __ldg(mk + j + 1), m2 = __ldg(mk + j + 2), m3 = __ldg(mk + j + 3);
+        const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3);
+        const bool a0 = (m0 >> lane) & 1u, a1 = (m1 >> lane) & 1u, a2 = (m2 >> lane) & 1u, a3 = (m3 >> lane) & 1u;
+        float4 r0, r1, r2, r3;
+        if (a0) r0 = __ldcs(records + rec + __popc(m0 & lt));
+        if (a1) r1 = __ldcs(records + rec + n0 + __popc(m1 & lt));
+        if (a2) r2 = __ldcs(records + rec + n0 + n1 + __popc(m2 & lt));
+        if (a3) r3 = __ldcs(records + rec + n0 + n1 + n2 + __popc(m3 & lt));
+        rec += n0 + n1 + n2 + n3;
+        if (a0) st.add(r0, q, Jref);
+        if (a1) st.add(r1, q, Jref);
+        if (a2) st.add(r2, q, Jref);
+        if (a3) st.add(r3, q, Jref);
+        seen += (int)a0 + (int)a1 + (int)a2 + (int)a3;
+    }
+    for (; j < nb; ++j) {
+        const uint32_t m = __ldg(mk + j);
+        if ((m >> lane) & 1u) {
+            st.add(__ldcs(records + rec + __popc(m & lt)), q, Jref);
+            ++seen;
+        }
+        rec += __popc(m);
+    }
+    return seen;
 }
 
+struct FitArgs {
+    const float4* records;
+    const long long* rec_off;
+    const long long* blk_off;
+    const uint32_t* blk_mask;
+    int n_tiles;
+    long long pixels;
+    float* params;        // 9: B, beta, gamma (read at start; written by the last CTA when do_step)
+    float* moments;       // 18: Adam state of the 9 scalars
+    float* J;             // pixels*3: Jref (closed form, in/out) or the J parameter (in/out)
+    float* J_moments;     // pixels*6: per pixel {m[3], v[3]} (J parameter mode)
+    const int* partition; // per global warp: first tile; [n_warps] = n_tiles
+    double* partials;     // gridDim.x rows of kSums
+    unsigned* ticket;
+    double* sums_out;     // if non-null the last CTA stores the reduced sums here
+    float* history_row;   // if non-null: params after the step + cost
+    int do_step;          // apply Adam to the 9 scalars in the last CTA
+    AdamScalars adam;
+};
+
+template <int MODE, bool PRECISE>
 __global__ void __launch_bounds__(kFitThreads)
-fit_sums_kernel(const float4* __restrict__ records, const long long* __restrict__ rec_off,
-                const long long* __restrict__ blk_off, const uint32_t* __restrict__ blk_mask, int n_tiles,
-                const float* __restrict__ params, double* __restrict__ partials) {
-    const Params9 q = load_params(params);
+fit_kernel(const __grid_constant__ FitArgs A) {
+    const Coef q = load_coef(A.params);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_warps = gridDim.x * (kFitThreads / 32);
+    const int gw = blockIdx.x * kFitWarps + warp;
     double acc[kSums];
 #pragma unroll
     for (int i = 0; i < kSums; ++i) acc[i] = 0.0;
 
-    for (int tile = blockIdx.x * (kFitThreads / 32) + warp; tile < n_tiles; tile += n_warps) {
-        const long long rec = rec_off[tile], b0 = blk_off[tile];
-        const int nb = (int)(blk_off[tile + 1] - b0);
+    const int t_begin = A.partition[gw], t_end = A.partition[gw + 1];
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        const long long b0 = A.blk_off[tile];
+        const int nb = (int)(A.blk_off[tile + 1] - b0);
         if (nb == 0) continue;
-        float J[3];
-        closed_form_J(records, blk_mask, rec, b0, nb, lane, q, J);
-        float s[kSums];
+        const long long p = (long long)tile * kTile + lane;
+        const bool inside = p < A.pixels;
+        float Jref[3] = {0.f, 0.f, 0.f};
+        if (inside) {
+            Jref[0] = A.J[3 * p + 0];
+            Jref[1] = A.J[3 * p + 1];
+            Jref[2] = A.J[3 * p + 2];
+        }
+        PixelStats<MODE, PRECISE> st;
+        st.clear();
+        const int seen = sweep_tile(A.records, A.blk_mask, A.rec_off[tile], b0, nb, lane, q, Jref, st);
+        if (seen == 0) continue;  // this lane's pixel has no observation in any kept view
+        float Jn[3];
 #pragma unroll
-        for (int i = 0; i < kSums; ++i) s[i] = 0.f;
-        for_each_record(records, blk_mask, rec, b0, nb, lane, [&](const float4 r) {
-            const float I[3] = {r.y, r.z, r.w};
+        for (int c = 0; c < 3; ++c) {
+            const float delta = MODE == kClosedForm ? st.S1[c] / st.S2[c] : 0.f;
+            Jn[c] = Jref[c] + delta;
+            const float rh = MODE == kClosedForm ? fmaf(-delta, st.S4[c], st.S3[c]) : st.S3[c];
+            const float rza = MODE == kClosedForm ? fmaf(-delta, st.S6[c], st.S5[c]) : st.S5[c];
+            const float rzg = MODE == kClosedForm ? fmaf(-delta, st.S8[c], st.S7[c]) : st.S7[c];
+            const float rr = MODE == kClosedForm ? fmaf(-delta, st.S1[c], st.S9[c]) : st.S9[c];
+            acc[c] += (double)rh;                   // sum r (1 - e^{-gamma z})
+            acc[3 + c] += (double)(Jn[c] * rza);    // sum r J z e^{-beta z}
+            acc[6 + c] += (double)(q.B[c] * rzg);   // sum r B z e^{-gamma z}
+            acc[9] += (double)rr;                   // sum r^2
+        }
+        if (MODE == kParamJ) {
+            // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step, with the pre-step B, beta, gamma (sucre.py:144-148)
+            float* mv = A.J_moments + 6 * p;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float a = expf(-q.beta[c] * r.x);
-                const float e = expf(-q.gamma[c] * r.x);
-                const float res = I[c] - (J[c] * a + q.B[c] * (1.0f - e));  // sucre.py:81
-                s[c] += res * (1.0f - e);
-                s[3 + c] += res * J[c] * r.x * a;
-                s[6 + c] += res * q.B[c] * r.x * e;
-                s[9] += res * res;
+                float m = mv[c], v = mv[3 + c];
+                const float g = (float)(-A.adam.grad_scale) * st.S1[c];
+                Jn[c] = adam_update(Jref[c], g, m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
+                mv[c] = m;
+                mv[3 + c] = v;
             }
-        });
-#pragma unroll
-        for (int i = 0; i < kSums; ++i) acc[i] += (double)s[i];
+        }
+        A.J[3 * p + 0] = Jn[0];
+        A.J[3 * p + 1] = Jn[1];
+        A.J[3 * p + 2] = Jn[2];
     }
 
-    // warp tree, then one slot per warp, then one partial row per CTA
-    __shared__ double sm[kFitThreads / 32][kSums];
+    // warp tree -> one slot per warp -> one row per CTA
+    __shared__ double sm[kFitWarps][kSums];
+    __shared__ unsigned s_ticket;
 #pragma unroll
     for (int i = 0; i < kSums; ++i) {
         double v = acc[i];
@@ -115,87 +251,126 @@ fit_sums_kernel(const float4* __restrict__ records, const long long* __restrict_
     __syncthreads();
     if (threadIdx.x < kSums) {
         double v = 0.0;
-        for (int wi = 0; wi < kFitThreads / 32; ++wi) v += sm[wi][threadIdx.x];
-        partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v;
+        for (int wi = 0; wi < kFitWarps; ++wi) v += sm[wi][threadIdx.x];
+        A.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v;
+        __threadfence();
     }
-}
-
-// fixed-order reduction of the per-CTA partial rows: warp i sums column i
-__device__ __forceinline__ double reduce_column(const double* __restrict__ partials, int n_rows, int col, int lane) {
-    double v = 0.0;
-    for (int r = lane; r < n_rows; r += 32) v += partials[(size_t)r * kSums + col];
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
-}
-
-__global__ void __launch_bounds__(kSums * 32)
-reduce_partials_kernel(const double* __restrict__ partials, int n_rows, double* __restrict__ sums) {
-    const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
-    const double v = reduce_column(partials, n_rows, col, lane);
-    if (lane == 0) sums[col] = v;
-}
-
-// torch.optim.Adam (single-tensor, non-capturable CPU branch the reference runs): fp32 state and params,
-// python-float (double) scalars rounded to fp32 where they meet a tensor.
-__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, int t, double lr) {
-    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-    m = m + (float)(1.0 - b1) * (g - m);
-    v = v * (float)b2 + (float)(1.0 - b2) * (g * g);
-    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
-    const double step_size = lr / bc1, bc2_sqrt = sqrt(bc2);
-    const float denom = sqrtf(v) / (float)bc2_sqrt + (float)eps;
-    return p + (float)(-step_size) * (m / denom);
-}
-
-// reduces `n_rows` partial rows (n_rows == 1: already reduced sums) and steps the 9 parameters
-__global__ void __launch_bounds__(kSums * 32)
-adam_step_kernel(const double* __restrict__ partials, int n_rows, long long n_obs, int t, double lr,
-                 float* __restrict__ params, float* __restrict__ state, float* __restrict__ history_row) {
-    __shared__ double sums[kSums];
-    const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
-    const double v = reduce_column(partials, n_rows, col, lane);
-    if (lane == 0) sums[col] = v;
     __syncthreads();
-    if (threadIdx.x < 9) {
-        const int i = threadIdx.x;
-        // d/dtheta [ sum r^2 / n_obs / 3 ] (sucre.py:145): B: -2 r (1-e), beta: +2 r J z a, gamma: -2 r B z e
-        const double sc = 2.0 / (3.0 * (double)n_obs);
-        const float g = (float)((i >= 3 && i < 6 ? sc : -sc) * sums[i]);
-        const float p = adam_update(params[i], g, state[i], state[9 + i], t, lr);
-        params[i] = p;
-        if (history_row) history_row[i] = p;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+
+    // last CTA: fixed-order reduction of the rows, then the Adam step of the 9 scalars
+    __threadfence();
+    __shared__ double tot[kSums];
+    for (int col = warp; col < kSums; col += kFitWarps) {
+        double v = 0.0;
+        for (int r = lane; r < (int)gridDim.x; r += 32) v += __ldcg(A.partials + (size_t)r * kSums + col);
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0) tot[col] = v;
     }
-    if (threadIdx.x == 9 && history_row) history_row[9] = (float)sums[9];
+    __syncthreads();
+    if (threadIdx.x < kSums && A.sums_out) A.sums_out[threadIdx.x] = tot[threadIdx.x];
+    if (A.do_step && threadIdx.x < 9) {
+        const int i = threadIdx.x;
+        // B: -2 r (1-g); beta: +2 r J z a; gamma: -2 r B z g   (all times 1 / 3N)
+        const float g = (float)((i >= 3 && i < 6 ? A.adam.grad_scale : -A.adam.grad_scale) * tot[i]);
+        float m = A.moments[i], v = A.moments[9 + i];
+        const float pnew = adam_update(A.params[i], g, m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
+        A.moments[i] = m;
+        A.moments[9 + i] = v;
+        A.params[i] = pnew;
+        if (A.history_row) A.history_row[i] = pnew;
+    }
+    if (threadIdx.x == 9 && A.history_row) A.history_row[9] = (float)tot[9];
+    if (threadIdx.x == 0) *A.ticket = 0u;
 }
 
+// Adam step of the 9 scalars from already reduced sums (multi-GPU: after the all-reduce)
+__global__ void adam_step_kernel(const double* __restrict__ sums, AdamScalars ad, float* __restrict__ params,
+                                 float* __restrict__ moments, float* __restrict__ history_row) {
+    const int i = threadIdx.x;
+    if (i < 9) {
+        const float g = (float)((i >= 3 && i < 6 ? ad.grad_scale : -ad.grad_scale) * sums[i]);
+        float m = moments[i], v = moments[9 + i];
+        const float pnew = adam_update(params[i], g, m, v, ad.neg_step_size, ad.bc2_sqrt);
+        moments[i] = m;
+        moments[9 + i] = v;
+        params[i] = pnew;
+        if (history_row) history_row[i] = pnew;
+    }
+    if (i == 9 && history_row) history_row[9] = (float)sums[9];
+}
+
+// Final update_J (sucre.py:156): J = Jref + sum(D' a) / sum(a^2) for observed pixels, NaN elsewhere (0/0, sucre.py:77)
+template <bool PRECISE>
 __global__ void __launch_bounds__(kFitThreads)
 write_J_kernel(const float4* __restrict__ records, const long long* __restrict__ rec_off,
                const long long* __restrict__ blk_off, const uint32_t* __restrict__ blk_mask, int n_tiles,
-               long long pixels, const float* __restrict__ params, float* __restrict__ Jout) {
-    const Params9 q = load_params(params);
+               long long pixels, const float* __restrict__ params, const float* __restrict__ Jref_in,
+               float* __restrict__ Jout) {
+    const Coef q = load_coef(params);
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (kFitThreads / 32) + (threadIdx.x >> 5);
+    const int tile = blockIdx.x * kFitWarps + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
-    const long long b0 = blk_off[tile];
-    float J[3];
-    closed_form_J(records, blk_mask, rec_off[tile], b0, (int)(blk_off[tile + 1] - b0), lane, q, J);
     const long long p = (long long)tile * kTile + lane;
-    if (p < pixels) {
-        Jout[3 * p + 0] = J[0];
-        Jout[3 * p + 1] = J[1];
-        Jout[3 * p + 2] = J[2];
+    const long long b0 = blk_off[tile];
+    const int nb = (int)(blk_off[tile + 1] - b0);
+    float Jref[3] = {0.f, 0.f, 0.f};
+    if (Jref_in && p < pixels && nb > 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float j = Jref_in[3 * p + c];
+            Jref[c] = j == j ? j : 0.f;  // a NaN reference (never observed so far) is no reference
+        }
     }
+    PixelStats<kWriteJ, PRECISE> st;
+    st.clear();
+    const int seen = nb > 0 ? sweep_tile(records, blk_mask, rec_off[tile], b0, nb, lane, q, Jref, st) : 0;
+    if (p < pixels) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Jout[3 * p + c] = seen ? Jref[c] + st.S1[c] / st.S2[c] : __int_as_float(0x7fc00000);
+    }
+}
+
+// first tile of every global warp: tiles are split so that every warp gets the same weight sum(blocks + 2)
+__global__ void partition_kernel(const long long* __restrict__ blk_off, int n_tiles, int n_warps, int* __restrict__ partition) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > n_warps) return;
+    const long long total = blk_off[n_tiles] + 2LL * n_tiles;
+    const long long target = (total * w + n_warps - 1) / n_warps;
+    int lo = 0, hi = n_tiles;  // smallest t with weight_prefix(t) >= target
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (blk_off[mid] + 2LL * mid >= target) hi = mid; else lo = mid + 1;
+    }
+    partition[w] = w == n_warps ? n_tiles : lo;
+}
+
+static bool precise_exp() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SUCRE_PRECISE_EXP");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 static int fit_grid() {
     static int ctas = 0;
     if (ctas == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_sums_kernel, kFitThreads, 0) != cudaSuccess || per_sm <= 0)
-            per_sm = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<kClosedForm, false>, kFitThreads, 0) != cudaSuccess || per_sm <= 0)
+            per_sm = 2;
         ctas = min(kMaxFitCtas, num_sms() * per_sm);
     }
     return ctas;
+}
+
+template <int MODE>
+static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st) {
+    if (precise_exp()) fit_kernel<MODE, true><<<ctas, kFitThreads, 0, st>>>(a);
+    else fit_kernel<MODE, false><<<ctas, kFitThreads, 0, st>>>(a);
 }
 
 static int check_store(const float* records, const int64_t* rec_off, const int64_t* blk_off, const uint32_t* blk_mask,
@@ -206,24 +381,58 @@ static int check_store(const float* records, const int64_t* rec_off, const int64
     return 0;
 }
 
+static FitArgs base_args(const float* records, const int64_t* rec_off, const int64_t* blk_off, const uint32_t* blk_mask,
+                         int n_tiles, int64_t pixels, void* workspace) {
+    FitArgs a{};
+    a.records = reinterpret_cast<const float4*>(records);
+    a.rec_off = (const long long*)rec_off;
+    a.blk_off = (const long long*)blk_off;
+    a.blk_mask = blk_mask;
+    a.n_tiles = n_tiles;
+    a.pixels = pixels;
+    char* ws = (char*)workspace;
+    a.partials = (double*)(ws + kWsPartials);
+    a.partition = (const int*)(ws + kWsPartition);
+    a.ticket = (unsigned*)(ws + kWsTicket);
+    return a;
+}
+
 }  // namespace sucre
 
 using namespace sucre;
 
-extern "C" size_t sucre_fit_workspace_bytes(void) { return sizeof(double) * kSums * kMaxFitCtas; }
+extern "C" size_t sucre_fit_workspace_bytes(void) { return kWsBytes; }
 
-extern "C" int sucre_fit_sums_closed_form(const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                                          const uint32_t* blk_mask, int n_tiles, const float* params, double* sums,
-                                          void* workspace, void* stream) {
+extern "C" int sucre_fit_prepare(const int64_t* blk_off, int n_tiles, void* workspace, void* stream) {
     clear_error();
-    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit_sums_closed_form")) return 1;
-    SUCRE_REQUIRE(params && sums && workspace, "sucre_fit_sums_closed_form: null pointer");
+    SUCRE_REQUIRE(blk_off && workspace && n_tiles > 0, "sucre_fit_prepare: bad arguments");
+    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sucre_fit_prepare: workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = fit_grid();
-    fit_sums_kernel<<<ctas, kFitThreads, 0, st>>>(reinterpret_cast<const float4*>(records), (const long long*)rec_off,
-                                                  (const long long*)blk_off, blk_mask, n_tiles, params, (double*)workspace);
-    reduce_partials_kernel<<<1, kSums * 32, 0, st>>>((const double*)workspace, ctas, sums);
-    return check_launch("fit_sums_kernel");
+    const int n_warps = fit_grid() * kFitWarps;
+    char* ws = (char*)workspace;
+    SUCRE_CUDA(cudaMemsetAsync(ws + kWsTicket, 0, 16, st));
+    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)blk_off, n_tiles, n_warps, (int*)(ws + kWsPartition));
+    return check_launch("partition_kernel");
+}
+
+extern "C" int sucre_fit_sums(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
+                              const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params, float* J,
+                              float* J_moments, int64_t n_obs, int t, double lr, double* sums, void* workspace,
+                              void* stream) {
+    clear_error();
+    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit_sums")) return 1;
+    SUCRE_REQUIRE(params && J && sums && workspace, "sucre_fit_sums: null pointer");
+    SUCRE_REQUIRE(mode == kClosedForm || (mode == kParamJ && J_moments && n_obs > 0 && t >= 1), "sucre_fit_sums: bad mode/arguments");
+    FitArgs a = base_args(records, rec_off, blk_off, blk_mask, n_tiles, target_pixels, workspace);
+    a.params = const_cast<float*>(params);
+    a.J = J;
+    a.J_moments = J_moments;
+    a.sums_out = sums;
+    a.do_step = 0;
+    if (mode == kParamJ) a.adam = adam_scalars(t, lr, n_obs);
+    if (mode == kClosedForm) launch_fit<kClosedForm>(a, fit_grid(), (cudaStream_t)stream);
+    else launch_fit<kParamJ>(a, fit_grid(), (cudaStream_t)stream);
+    return check_launch("fit_kernel");
 }
 
 extern "C" int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_t n_obs, int t, double lr,
@@ -231,37 +440,47 @@ extern "C" int sucre_adam_step(float* params, float* adam_state, const double* s
     clear_error();
     SUCRE_REQUIRE(params && adam_state && sums, "sucre_adam_step: null pointer");
     SUCRE_REQUIRE(n_obs > 0 && t >= 1, "sucre_adam_step: n_obs = %lld, t = %d", (long long)n_obs, t);
-    adam_step_kernel<<<1, kSums * 32, 0, (cudaStream_t)stream>>>(sums, 1, n_obs, t, lr, params, adam_state, history_row);
+    adam_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, adam_scalars(t, lr, n_obs), params, adam_state, history_row);
     return check_launch("adam_step_kernel");
 }
 
-extern "C" int sucre_fit_closed_form(const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                                     const uint32_t* blk_mask, int n_tiles, int64_t n_obs, float* params,
-                                     float* adam_state, int first_step, int num_iter, double lr, float* history,
-                                     void* workspace, void* stream) {
+extern "C" int sucre_fit(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
+                         const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, int64_t n_obs, float* params,
+                         float* adam_state, float* J, float* J_moments, int first_step, int num_iter, double lr,
+                         float* history, void* workspace, void* stream) {
     clear_error();
-    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit_closed_form")) return 1;
-    SUCRE_REQUIRE(params && adam_state && workspace, "sucre_fit_closed_form: null pointer");
-    SUCRE_REQUIRE(n_obs > 0 && first_step >= 1 && num_iter >= 0, "sucre_fit_closed_form: bad n_obs/first_step/num_iter");
-    cudaStream_t st = (cudaStream_t)stream;
+    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit")) return 1;
+    SUCRE_REQUIRE(params && adam_state && J && workspace, "sucre_fit: null pointer");
+    SUCRE_REQUIRE(mode == kClosedForm || (mode == kParamJ && J_moments), "sucre_fit: bad mode %d", mode);
+    SUCRE_REQUIRE(n_obs > 0 && first_step >= 1 && num_iter >= 0, "sucre_fit: bad n_obs/first_step/num_iter");
+    FitArgs a = base_args(records, rec_off, blk_off, blk_mask, n_tiles, target_pixels, workspace);
+    a.params = params;
+    a.moments = adam_state;
+    a.J = J;
+    a.J_moments = J_moments;
+    a.do_step = 1;
     const int ctas = fit_grid();
     for (int it = 0; it < num_iter; ++it) {
-        fit_sums_kernel<<<ctas, kFitThreads, 0, st>>>(reinterpret_cast<const float4*>(records), (const long long*)rec_off,
-                                                      (const long long*)blk_off, blk_mask, n_tiles, params, (double*)workspace);
-        adam_step_kernel<<<1, kSums * 32, 0, st>>>((const double*)workspace, ctas, n_obs, first_step + it, lr, params,
-                                                   adam_state, history ? history + (size_t)it * kSums : nullptr);
+        a.adam = adam_scalars(first_step + it, lr, n_obs);
+        a.history_row = history ? history + (size_t)it * kSums : nullptr;
+        if (mode == kClosedForm) launch_fit<kClosedForm>(a, ctas, (cudaStream_t)stream);
+        else launch_fit<kParamJ>(a, ctas, (cudaStream_t)stream);
     }
-    return check_launch("sucre_fit_closed_form kernels");
+    return check_launch("sucre_fit kernels");
 }
 
 extern "C" int sucre_fit_write_J(const float* records, const int64_t* rec_off, const int64_t* blk_off,
                                  const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params,
-                                 float* J, void* stream) {
+                                 const float* J_ref, float* J, void* stream) {
     clear_error();
     if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit_write_J")) return 1;
     SUCRE_REQUIRE(params && J && target_pixels > 0, "sucre_fit_write_J: bad arguments");
-    write_J_kernel<<<(n_tiles + kFitThreads / 32 - 1) / (kFitThreads / 32), kFitThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(records), (const long long*)rec_off, (const long long*)blk_off, blk_mask, n_tiles,
-        target_pixels, params, J);
+    const int grid = (n_tiles + kFitWarps - 1) / kFitWarps;
+    if (precise_exp())
+        write_J_kernel<true><<<grid, kFitThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(records), (const long long*)rec_off,
+                                                                             (const long long*)blk_off, blk_mask, n_tiles, target_pixels, params, J_ref, J);
+    else
+        write_J_kernel<false><<<grid, kFitThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(records), (const long long*)rec_off,
+                                                                              (const long long*)blk_off, blk_mask, n_tiles, target_pixels, params, J_ref, J);
     return check_launch("write_J_kernel");
 }

@@ -112,6 +112,7 @@ class ObservationStore:
     blk_mask: torch.Tensor        # (n_blocks,) int32 (bit pattern of the uint32 lane mask)
     blk_view: torch.Tensor        # (n_blocks,) int32 index into source_keys
     rec_src: torch.Tensor | None  # (N,) int32 u2 | v2 << 16
+    workspace: torch.Tensor | None = None  # fit scratch, prepared on first use
     stats: dict = field(default_factory=dict)
 
     @property
@@ -215,57 +216,85 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
 # ------------------------------------------------------------------------------------------------------------
 @dataclass
 class FitState:
-    """B, beta, gamma (9 floats, sucre.py:41-43) and Adam's fp32 moments, on the device."""
-    params: torch.Tensor   # (9,) f32: B[3], beta[3], gamma[3]
-    moments: torch.Tensor  # (18,) f32: exp_avg[9], exp_avg_sq[9]
+    """B, beta, gamma (9 floats, sucre.py:41-43), Adam's fp32 moments and the per-pixel J buffer, on the device.
+
+    closed-form mode: J is the fit's work buffer (J of the last evaluated iteration on observed pixels, 0 elsewhere);
+    J-parameter mode:  J is the Adam parameter (sucre.py:47-50) and J_moments its per-pixel {exp_avg, exp_avg_sq}."""
+    params: torch.Tensor                  # (9,) f32: B[3], beta[3], gamma[3]
+    moments: torch.Tensor                 # (18,) f32: exp_avg[9], exp_avg_sq[9]
+    J: torch.Tensor | None = None         # (H,W,3) f32
+    J_moments: torch.Tensor | None = None  # (H,W,6) f32
     step: int = 0
 
     @staticmethod
-    def initial(device, params=None) -> 'FitState':
+    def initial(device, params=None, J0: torch.Tensor | None = None) -> 'FitState':
+        """J0 = None: closed-form mode; J0 = initial image (NaN where target depth <= 0): J-parameter mode."""
         p = torch.full((9,), 0.1, dtype=torch.float32) if params is None else \
             torch.as_tensor(params, dtype=torch.float32).reshape(9).clone()
-        return FitState(params=p.to(device), moments=torch.zeros(18, dtype=torch.float32, device=device))
+        st = FitState(params=p.to(device), moments=torch.zeros(18, dtype=torch.float32, device=device))
+        if J0 is not None:
+            st.J = J0.to(device=device, dtype=torch.float32).contiguous().clone()
+            st.J_moments = torch.zeros(tuple(st.J.shape[:2]) + (6,), dtype=torch.float32, device=device)
+        return st
+
+    @property
+    def mode(self) -> int:
+        return _lib.FIT_PARAM_J if self.J_moments is not None else _lib.FIT_CLOSED_FORM
+
+    def ensure_J(self, store: 'ObservationStore'):
+        if self.J is None:
+            self.J = torch.zeros((store.height, store.width, 3), dtype=torch.float32, device=store.records.device)
+        assert self.J.shape == (store.height, store.width, 3) and self.J.is_contiguous()
 
 
-_workspaces: dict = {}
-
-
-def _workspace(device) -> torch.Tensor:
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _workspaces:
-        _workspaces[key] = torch.empty(_lib.lib().sucre_fit_workspace_bytes(), dtype=torch.uint8, device=device)
-    return _workspaces[key]
+def _workspace(store: ObservationStore) -> torch.Tensor:
+    """Per-store scratch buffer, partitioned for the fit on first use."""
+    if store.workspace is None:
+        dev = store.records.device
+        store.workspace = torch.empty(_lib.lib().sucre_fit_workspace_bytes(), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().sucre_fit_prepare(store.blk_off.data_ptr(), store.n_tiles, store.workspace.data_ptr(),
+                                                    _stream(dev)), 'sucre_fit_prepare')
+    return store.workspace
 
 
 def _store_ptrs(store: ObservationStore):
     return (store.records.data_ptr(), store.rec_off.data_ptr(), store.blk_off.data_ptr(), store.blk_mask.data_ptr(),
-            store.n_tiles)
+            store.n_tiles, store.width * store.height)
 
 
-def fit_closed_form(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05,
-                    n_obs_global: int | None = None) -> torch.Tensor:
-    """num_iter iterations of adam() in --use-closed-form mode (sucre.py:138-148), entirely on the device.
-    Returns the (num_iter, 10) history tensor {params after each step, cost before it} (device)."""
+def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05) -> torch.Tensor:
+    """num_iter iterations of adam() (sucre.py:138-148) entirely on the device, in the mode `state` was created
+    for.  Returns the (num_iter, 10) history tensor {params after each step, cost before it} (device)."""
     if store.n_obs == 0:
         raise _lib.SucreError('fit: the observation store is empty')
     dev = store.records.device
+    state.ensure_J(store)
     history = torch.empty((num_iter, 10), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().sucre_fit_closed_form(
-            *_store_ptrs(store), store.n_obs if n_obs_global is None else n_obs_global, state.params.data_ptr(),
-            state.moments.data_ptr(), state.step + 1, num_iter, float(lr), history.data_ptr(),
-            _workspace(dev).data_ptr(), _stream(dev)), 'sucre_fit_closed_form')
+        _lib.check(_lib.lib().sucre_fit(
+            state.mode, *_store_ptrs(store), store.n_obs, state.params.data_ptr(), state.moments.data_ptr(),
+            state.J.data_ptr(), 0 if state.J_moments is None else state.J_moments.data_ptr(), state.step + 1, num_iter,
+            float(lr), history.data_ptr(), _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit')
     state.step += num_iter
     return history
 
 
-def fit_sums_closed_form(store: ObservationStore, params: torch.Tensor, sums: torch.Tensor):
-    """One objective evaluation -> sums (10 doubles, device).  Building block of the multi-GPU loop."""
+fit_closed_form = fit  # the mode lives in the FitState
+
+
+def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs_global: int | None = None,
+             lr: float = 0.05):
+    """One objective evaluation at state.params -> sums (10 doubles, device); in J-parameter mode J takes its
+    Adam step state.step+1.  Building block of the multi-GPU loop (all-reduce sums, then adam_step)."""
     dev = store.records.device
+    state.ensure_J(store)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().sucre_fit_sums_closed_form(*_store_ptrs(store), params.data_ptr(), sums.data_ptr(),
-                                                         _workspace(dev).data_ptr(), _stream(dev)),
-                   'sucre_fit_sums_closed_form')
+        _lib.check(_lib.lib().sucre_fit_sums(
+            state.mode, *_store_ptrs(store), state.params.data_ptr(), state.J.data_ptr(),
+            0 if state.J_moments is None else state.J_moments.data_ptr(),
+            store.n_obs if n_obs_global is None else n_obs_global, state.step + 1, float(lr), sums.data_ptr(),
+            _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit_sums')
 
 
 def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, history_row: torch.Tensor | None = None):
@@ -277,13 +306,14 @@ def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, histor
                                               _stream(dev)), 'sucre_adam_step')
 
 
-def closed_form_J(store: ObservationStore, params: torch.Tensor) -> torch.Tensor:
+def closed_form_J(store: ObservationStore, params: torch.Tensor, J_ref: torch.Tensor | None = None) -> torch.Tensor:
     """update_J (sucre.py:66-77) with the given parameters: (H,W,3) f32 on the device, NaN where unobserved."""
     dev = store.records.device
     J = torch.empty((store.height, store.width, 3), dtype=torch.float32, device=dev)
     if store.n_obs == 0:
         return J.fill_(float('nan'))
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().sucre_fit_write_J(*_store_ptrs(store), store.width * store.height, params.data_ptr(),
-                                                J.data_ptr(), _stream(dev)), 'sucre_fit_write_J')
+        _lib.check(_lib.lib().sucre_fit_write_J(*_store_ptrs(store), params.data_ptr(),
+                                                0 if J_ref is None else J_ref.data_ptr(), J.data_ptr(), _stream(dev)),
+                   'sucre_fit_write_J')
     return J

@@ -35,13 +35,13 @@ class SUCRe:
         self.image = image
         self.light_model = light_model
         self.use_closed_form = use_closed_form
-        self.state = engine.FitState(params=torch.full((9,), 0.1, dtype=torch.float32),
-                                     moments=torch.zeros(18, dtype=torch.float32))
-        self.J: Tensor | None = None
+        J0 = None
         if not use_closed_form:
-            self.J = image.get_rgb()                              # sucre.py:48
-            self.J[image.get_depth_map() <= 0] = torch.nan        # sucre.py:49
-        self.J_moments: Tensor | None = None
+            J0 = image.get_rgb_u8().to(torch.float32) / 255.0              # sucre.py:48 (= load_rgb, bit for bit)
+            J0[image.get_depth_u16().to(torch.int32) <= 0] = torch.nan    # sucre.py:49
+        self.state = engine.FitState.initial('cpu', J0=J0)
+        self._J_closed: Tensor | None = None
+        self.history: Tensor | None = None
 
     # -- parameters -------------------------------------------------------------------------------------------
     @property
@@ -57,16 +57,23 @@ class SUCRe:
         return self.state.params[6:9].view(3, 1)
 
     @property
+    def J(self) -> Tensor | None:
+        """Restored image (H,W,3): the Adam parameter in the default mode, the last update_J result otherwise."""
+        return self._J_closed if self.use_closed_form else self.state.J
+
+    @property
     def device(self) -> torch.device:
         return self.state.params.device
 
     def to(self, device) -> SUCRe:
-        self.state.params = self.state.params.to(device)
-        self.state.moments = self.state.moments.to(device)
-        if self.J is not None:
-            self.J = self.J.to(device)
-        if self.J_moments is not None:
-            self.J_moments = self.J_moments.to(device)
+        st = self.state
+        st.params, st.moments = st.params.to(device), st.moments.to(device)
+        if st.J is not None:
+            st.J = st.J.to(device)
+        if st.J_moments is not None:
+            st.J_moments = st.J_moments.to(device)
+        if self._J_closed is not None:
+            self._J_closed = self._J_closed.to(device)
         return self
 
     def cpu(self) -> SUCRe:
@@ -84,7 +91,7 @@ class SUCRe:
             if key in known:
                 self.state.params[known[key]:known[key] + 3] = torch.as_tensor(value, dtype=torch.float32).reshape(3).to(self.device)
             elif key == 'J' and not self.use_closed_form:
-                self.J = torch.as_tensor(value, dtype=torch.float32).to(self.device)
+                self.state.J = torch.as_tensor(value, dtype=torch.float32).to(self.device).contiguous()
             elif strict:
                 raise KeyError(f'unexpected key {key!r} in state_dict')
 
@@ -95,8 +102,10 @@ class SUCRe:
     @torch.no_grad()
     def update_J(self, matches_data: loader.MatchesData, force_update: bool = False):
         """Closed-form J from the current B, beta, gamma (sucre.py:66-77) — one CUDA kernel over the store."""
-        if self.use_closed_form or force_update:
-            self.J = engine.closed_form_J(matches_data.store, self.state.params)
+        if self.use_closed_form:
+            self._J_closed = engine.closed_form_J(matches_data.store, self.state.params, self.state.J)
+        elif force_update:
+            self.state.J = engine.closed_form_J(matches_data.store, self.state.params, None)
 
     @torch.no_grad()
     def forward(self, u: Tensor, v: Tensor, cP: Tensor) -> Tensor:
@@ -159,32 +168,28 @@ def adam(
     grouped views for memory in the reference (gradients accumulate over all batches before the single
     optimizer.step()), so it has no effect here: every iteration streams the whole store once."""
     print(f'Solve least squares with Adam optimizer ({num_iter} iterations).')
-    if not sucre.use_closed_form:
-        raise NotImplementedError('default mode (J as an Adam parameter, sucre.py:47-50) is not built yet; '
-                                  'pass --use-closed-form')
-    # iterations at which the reference saves intermediate plots (sucre.py:153-154): it % save_interval == 0,
-    # after the step of iteration `it`, with J as of the top of that iteration
-    chunk_ends = [num_iter]
-    if save_dir is not None and save_interval is not None:
-        chunk_ends = sorted({it + 1 for it in range(0, num_iter, save_interval)} | {num_iter})
-    done = 0
+    store = matches_data.store
+    # iterations after whose step the reference saves intermediate plots (sucre.py:153-154): it % save_interval == 0
+    plot_its = list(range(0, num_iter, save_interval)) if save_dir is not None and save_interval else []
     histories = []
-    for end in chunk_ends:
-        n = end - done
-        if save_dir is not None and save_interval is not None and (end - 1) % save_interval == 0 and n > 0:
-            # run up to the iteration to be plotted, evaluate J with its pre-step parameters, then step
-            if n > 1:
-                histories.append(engine.fit_closed_form(matches_data.store, sucre.state, n - 1, lr))
+    done = 0
+    for it in plot_its + [None]:
+        end = num_iter if it is None else it + 1
+        if it is not None and sucre.use_closed_form:
+            # the plotted J is the one of the top of iteration `it` (pre-step parameters, sucre.py:141)
+            if it > done:
+                histories.append(engine.fit(store, sucre.state, it - done, lr))
             sucre.update_J(matches_data)
-            histories.append(engine.fit_closed_form(matches_data.store, sucre.state, 1, lr))
-            sucre.save_plots(save_dir=save_dir, iteration=end - 1)
-        elif n > 0:
-            histories.append(engine.fit_closed_form(matches_data.store, sucre.state, n, lr))
+            histories.append(engine.fit(store, sucre.state, 1, lr))
+        elif end > done:
+            histories.append(engine.fit(store, sucre.state, end - done, lr))
         done = end
-    if histories:
-        _log_history(torch.cat(histories).cpu().numpy(), 0)
-    sucre.update_J(matches_data=matches_data)  # sucre.py:156
+        if it is not None:
+            sucre.save_plots(save_dir=save_dir, iteration=it)
     sucre.history = torch.cat(histories) if histories else None
+    if sucre.history is not None:
+        _log_history(sucre.history.cpu().numpy(), 0)
+    sucre.update_J(matches_data=matches_data)  # sucre.py:156 (a no-op in the default mode, like the reference)
     return sucre
 
 

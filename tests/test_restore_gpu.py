@@ -1,0 +1,101 @@
+"""End to end through the reference-facing surface: PNG files + COLMAP model on disk -> CLI / restore_image ->
+.pt and PNG outputs, compared with what the unmodified reference produced for the same scene (golden)."""
+import numpy as np
+import pytest
+import torch
+
+import cv2
+
+from sucre_b200 import sfm, sucre
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_golden_scene(g, root):
+    for d in ('images', 'depth', 'model', 'out'):
+        (root / d).mkdir()
+    names = g['names'].tolist()
+    cams = {}
+    with open(root / 'model' / 'images.txt', 'w') as f:
+        for i, name in enumerate(names):
+            depth, rgb = g.inputs(i)
+            cv2.imwrite(str(root / 'depth' / f'depth_{name}'), depth)
+            cv2.imwrite(str(root / 'images' / name), np.ascontiguousarray(rgb[..., ::-1]))
+            cam = tuple(g[f'in_cam_{i}'].tolist())
+            cam_id = cams.setdefault(cam, len(cams) + 1)
+            q, t = g[f'in_q_{i}'], g[f'in_t_{i}']
+            f.write(' '.join([str(i + 1)] + [repr(float(x)) for x in (*q, *t)] + [str(cam_id), name]) + '\n\n')
+    with open(root / 'model' / 'cameras.txt', 'w') as f:
+        for cam, cam_id in cams.items():
+            W, H, fx, fy, cx, cy = cam
+            f.write(f'{cam_id} PINHOLE {int(W)} {int(H)} {fx!r} {fy!r} {cx!r} {cy!r}\n')
+    return root
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def test_colmap_model_matches_reference_geometry(golden, tmp_path):
+    g = golden('mixed8_image0004')
+    root = _write_golden_scene(g, tmp_path)
+    model = sfm.COLMAPModel(root / 'model', root / 'images', root / 'depth')
+    for i, name in enumerate(g['names'].tolist()):
+        im, a = model[name], g.geom_arrays(i)
+        assert im.id == i + 1 and (im.camera.width, im.camera.height) == tuple(a['wh'])
+        geom = im.geom
+        for k in ('K', 'Kinv', 'R', 't', 'Ri', 'ti'):  # bit-identical to the reference's tensors
+            assert np.array_equal(getattr(geom, k).numpy().reshape(a[k].shape), a[k]), (name, k)
+
+
+@pytest.mark.parametrize('mode', ['closed', 'param'])
+def test_cli_restores_like_the_reference(golden, tmp_path, mode, capsys):
+    g = golden('tiny6_closed')
+    gm = golden(f'tiny6_{mode}')
+    root = _write_golden_scene(g, tmp_path)
+    argv = ['--image-dir', str(root / 'images'), '--depth-dir', str(root / 'depth'), '--model-dir', str(root / 'model'),
+            '--output-dir', str(root / 'out'), '--image-name', str(g['target']), '--num-iter', str(int(gm['num_iter'])),
+            '--batch-size', '2', '--num-workers', '2']
+    if mode == 'closed':
+        argv.append('--use-closed-form')
+    sucre.main(argv)
+    out = capsys.readouterr().out
+    assert f"Restore {g['target']}." in out and 'Total of 26797 observations.' in out and 'iter: 0024' in out
+    stem = str(g['target'])[:-4]
+    saved = torch.load(root / 'out' / f'{stem}.pt')
+    assert set(saved) == ({'B', 'beta', 'gamma', 'J'})
+    for k in ('B', 'beta', 'gamma'):
+        assert saved[k].shape == (3, 1) and _rel(saved[k].numpy(), gm[k]) < 1e-4
+    J = saved['J'].numpy()
+    assert np.array_equal(np.isnan(J), np.isnan(gm['J'])) and np.nanmax(np.abs(J - gm['J'])) < 1e-3
+    assert (root / 'out' / f'{stem}_rgb.png').exists() and (root / 'out' / f'{stem}_reconstruction.png').exists()
+    assert not (root / 'out' / f'{stem}.h5').exists()  # erased without --keep-matches (sucre.py:217-219)
+
+
+def test_keep_matches_and_reuse(golden, tmp_path, capsys):
+    g = golden('tiny6_closed')
+    root = _write_golden_scene(g, tmp_path)
+    model = sfm.COLMAPModel(root / 'model', root / 'images', root / 'depth')
+    image = model[str(g['target'])]
+    kw = dict(colmap_model=model, output_dir=root / 'out', use_closed_form=True, num_iter=3, device='cuda')
+    sucre.restore_image(image, keep_matches=True, **kw)
+    assert (root / 'out' / 'image0002.h5').exists() and (root / 'out' / 'image0002.matches.npz').exists()
+    first = torch.load(root / 'out' / 'image0002.pt')
+    capsys.readouterr()
+    sucre.restore_image(image, keep_matches=False, **kw)          # reuses the kept matches (sucre.py:185)
+    assert 'Compute image0002.png matches.' not in capsys.readouterr().out
+    again = torch.load(root / 'out' / 'image0002.pt')
+    assert torch.equal(first['B'], again['B']) and torch.equal(first['J'].nan_to_num(), again['J'].nan_to_num())
+    assert not (root / 'out' / 'image0002.matches.npz').exists()
+
+
+def test_unknown_image_and_bad_camera(golden, tmp_path):
+    g = golden('tiny6_closed')
+    root = _write_golden_scene(g, tmp_path)
+    model = sfm.COLMAPModel(root / 'model', root / 'images', root / 'depth')
+    with pytest.raises(KeyError):
+        model['nope.png']
+    txt = (root / 'model' / 'cameras.txt').read_text().replace('PINHOLE', 'SIMPLE_RADIAL')
+    (root / 'model' / 'cameras.txt').write_text(txt)
+    with pytest.raises(AssertionError):
+        sfm.COLMAPModel(root / 'model', root / 'images', root / 'depth')

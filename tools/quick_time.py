@@ -50,7 +50,7 @@ print(f'  sample kernel: min {mn:.3f} ms avg {av:.3f}  ({store.n_obs*16/mn/1e6:.
 
 def fit():
     s = engine.FitState.initial('cuda')
-    h = engine.fit_closed_form(store, s, iters)
+    h = engine.fit(store, s, iters)
     return s, h
 mn, av, (s, h) = timed(fit, 3)
 print(f'fit {iters} it: min {mn:.3f} ms avg {av:.3f} ms -> {mn/iters*1e3:.1f} us/iter, {store.n_obs*16*iters/mn/1e6:.0f} GB/s algorithmic')
