@@ -181,62 +181,285 @@ struct FitArgs {
     AdamScalars adam;
 };
 
+// ---- per-warp bulk-copy ring --------------------------------------------------------------------------------
+// The tiles of one warp are consecutive, so its records are ONE contiguous byte range in HBM.  The warp streams
+// that range through a private shared-memory ring with cp.async.bulk (TMA 1-D copies of 4 KB, kStages slots,
+// one mbarrier per slot): HBM latency is covered by the copies in flight instead of by occupancy, and the
+// arithmetic reads 16-byte records from shared memory.
+constexpr int kChunkRecs = 256;                   // records per bulk copy (4 KB)
+constexpr int kStages = 3;                        // ring slots per warp
+constexpr int kRingRecs = kChunkRecs * kStages;   // 768 records = 12 KB per warp, 96 KB per CTA, 2 CTAs per SM
+constexpr size_t kFitSmem = (size_t)kFitWarps * kRingRecs * sizeof(float4);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two records per instruction ------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ float lo(u64 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi(u64 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+template <bool PRECISE>
+__device__ __forceinline__ u64 exp2_pair(u64 x) {  // PRECISE: x holds natural-log exponents, else base-2 exponents
+    return PRECISE ? pk(expf(lo(x)), expf(hi(x))) : pk(fast_exp2(lo(x)), fast_exp2(hi(x)));
+}
+
+// Per-pixel statistics, one packed accumulator per statistic and channel: the low half sums the records of
+// even blocks, the high half those of odd blocks (two source views are processed per step).
 template <int MODE, bool PRECISE>
-__global__ void __launch_bounds__(kFitThreads)
+struct PairStats {
+    u64 S1[3], S2[3], S3[3], S4[3], S5[3], S6[3], S7[3], S8[3], S9[3];
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S1[c] = S2[c] = S3[c] = S4[c] = S5[c] = S6[c] = S7[c] = S8[c] = S9[c] = 0ull;
+    }
+
+    // rA / rB: the lane's record in the even / odd block; w = (1|0, 1|0) says which of the two exist
+    __device__ __forceinline__ void add(const float4 rA, const float4 rB, u64 w, const u64 kb[3], const u64 kg[3],
+                                        const u64 Bp[3], const u64 Bn[3], const u64 Jn[3]) {
+        const u64 z = pk(rA.x, rB.x);
+        const u64 I[3] = {pk(rA.y, rB.y), pk(rA.z, rB.z), pk(rA.w, rB.w)};
+        const u64 one = pk(1.f, 1.f), neg1 = pk(-1.f, -1.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const u64 a = exp2_pair<PRECISE>(mul2(kb[c], z));   // e^{-beta z}
+            const u64 g = exp2_pair<PRECISE>(mul2(kg[c], z));   // e^{-gamma z}
+            const u64 D = fma2(Bp[c], g, add2(I[c], Bn[c]));    // I - B (1 - g)
+            const u64 Dp = fma2(Jn[c], a, D);                   // shifted residual D - Jref a
+            const u64 Dw = mul2(Dp, w);
+            S1[c] = fma2(Dw, a, S1[c]);
+            if (MODE == kParamJ) {
+                const u64 h = fma2(g, neg1, one), za = mul2(z, a), zg = mul2(z, g);
+                S3[c] = fma2(Dw, h, S3[c]);
+                S5[c] = fma2(Dw, za, S5[c]);
+                S7[c] = fma2(Dw, zg, S7[c]);
+                S9[c] = fma2(Dw, Dp, S9[c]);
+            } else {
+                const u64 aw = mul2(a, w);
+                S2[c] = fma2(aw, a, S2[c]);
+                const u64 h = fma2(g, neg1, one), za = mul2(z, a), zg = mul2(z, g);
+                S3[c] = fma2(Dw, h, S3[c]);
+                S4[c] = fma2(aw, h, S4[c]);
+                S5[c] = fma2(Dw, za, S5[c]);
+                S6[c] = fma2(aw, za, S6[c]);
+                S7[c] = fma2(Dw, zg, S7[c]);
+                S8[c] = fma2(aw, zg, S8[c]);
+                S9[c] = fma2(Dw, Dp, S9[c]);
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float sum2(u64 v) { return lo(v) + hi(v); }
+
+template <int MODE, bool PRECISE>
+__global__ void __launch_bounds__(kFitThreads, 2)
 fit_kernel(const __grid_constant__ FitArgs A) {
+    extern __shared__ __align__(128) unsigned char fit_smem[];
+    __shared__ __align__(8) unsigned long long bars[kFitWarps][kStages];
     const Coef q = load_coef(A.params);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
+    const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingRecs;
+    const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(bar_s + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    // packed per-channel constants: exponent scales, +B, -B
+    u64 kb[3], kg[3], Bp[3], Bn[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        kb[c] = PRECISE ? pk(-q.beta[c], -q.beta[c]) : pk(q.kb[c], q.kb[c]);
+        kg[c] = PRECISE ? pk(-q.gamma[c], -q.gamma[c]) : pk(q.kg[c], q.kg[c]);
+        Bp[c] = pk(q.B[c], q.B[c]);
+        Bn[c] = pk(-q.B[c], -q.B[c]);
+    }
+
     double acc[kSums];
 #pragma unroll
     for (int i = 0; i < kSums; ++i) acc[i] = 0.0;
 
     const int t_begin = A.partition[gw], t_end = A.partition[gw + 1];
+    const long long R0 = A.rec_off[t_begin], B0 = A.blk_off[t_begin];
+    const int n_rec = (int)(A.rec_off[t_end] - R0), n_blk = (int)(A.blk_off[t_end] - B0);
+    const int n_chunks = (n_rec + kChunkRecs - 1) / kChunkRecs;
+    const float4* src = A.records + R0;
+
+    // ring bookkeeping, all warp-uniform
+    int next_issue = 0, issue_slot = 0;          // next chunk to copy and the slot it goes to
+    int wait_slot = 0;                           // slot of the next chunk to wait for
+    uint32_t wait_parity = 0;
+    int avail = 0;                               // records that have landed
+    int free_at = kChunkRecs;                    // the oldest slot is recyclable once `rel` reaches this
+    int rel = 0, rpos = 0;                       // records consumed; same, modulo the ring size
+    auto issue = [&]() {  // lane 0: arm the slot's barrier and start the copy of chunk `next_issue`
+        const int first = next_issue * kChunkRecs;
+        const uint32_t bytes = (uint32_t)min(kChunkRecs, n_rec - first) * (uint32_t)sizeof(float4);
+        mbar_expect_tx(bar_s + 8 * issue_slot, bytes);
+        bulk_load(ring_s + issue_slot * kChunkRecs * (uint32_t)sizeof(float4), src + first, bytes, bar_s + 8 * issue_slot);
+    };
+    for (int c = 0; c < min(kStages, n_chunks); ++c) {
+        if (lane == 0) issue();
+        ++next_issue;
+        issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
+    }
+
+    // block masks: lane j of `mcur` holds the mask of block 32*batch + j; `mnext` is the batch after it
+    const uint32_t* __restrict__ mk = A.blk_mask + B0;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t mcur = lane < n_blk ? __ldg(mk + lane) : 0u;
+    uint32_t mnext = 32 + lane < n_blk ? __ldg(mk + 32 + lane) : 0u;
+    int b = 0;  // block index within the warp's range
+
+    long long p_next = (long long)t_begin * kTile + lane;
+    float Jnext[3] = {0.f, 0.f, 0.f};
+    if (t_begin < t_end && p_next < A.pixels) {
+        Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
+    }
+    int b_end_next = t_begin < t_end ? (int)(A.blk_off[t_begin + 1] - B0) : 0;
+
+#pragma unroll 1
     for (int tile = t_begin; tile < t_end; ++tile) {
-        const long long b0 = A.blk_off[tile];
-        const int nb = (int)(A.blk_off[tile + 1] - b0);
-        if (nb == 0) continue;
-        const long long p = (long long)tile * kTile + lane;
-        const bool inside = p < A.pixels;
-        float Jref[3] = {0.f, 0.f, 0.f};
-        if (inside) {
-            Jref[0] = A.J[3 * p + 0];
-            Jref[1] = A.J[3 * p + 1];
-            Jref[2] = A.J[3 * p + 2];
-        }
-        PixelStats<MODE, PRECISE> st;
-        st.clear();
-        const int seen = sweep_tile(A.records, A.blk_mask, A.rec_off[tile], b0, nb, lane, q, Jref, st);
-        if (seen == 0) continue;  // this lane's pixel has no observation in any kept view
-        float Jn[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float delta = MODE == kClosedForm ? st.S1[c] / st.S2[c] : 0.f;
-            Jn[c] = Jref[c] + delta;
-            const float rh = MODE == kClosedForm ? fmaf(-delta, st.S4[c], st.S3[c]) : st.S3[c];
-            const float rza = MODE == kClosedForm ? fmaf(-delta, st.S6[c], st.S5[c]) : st.S5[c];
-            const float rzg = MODE == kClosedForm ? fmaf(-delta, st.S8[c], st.S7[c]) : st.S7[c];
-            const float rr = MODE == kClosedForm ? fmaf(-delta, st.S1[c], st.S9[c]) : st.S9[c];
-            acc[c] += (double)rh;                   // sum r (1 - e^{-gamma z})
-            acc[3 + c] += (double)(Jn[c] * rza);    // sum r J z e^{-beta z}
-            acc[6 + c] += (double)(q.B[c] * rzg);   // sum r B z e^{-gamma z}
-            acc[9] += (double)rr;                   // sum r^2
-        }
-        if (MODE == kParamJ) {
-            // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step, with the pre-step B, beta, gamma (sucre.py:144-148)
-            float* mv = A.J_moments + 6 * p;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float m = mv[c], v = mv[3 + c];
-                const float g = (float)(-A.adam.grad_scale) * st.S1[c];
-                Jn[c] = adam_update(Jref[c], g, m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
-                mv[c] = m;
-                mv[3 + c] = v;
+        const int b_end = b_end_next;
+        const long long p = p_next;
+        const float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
+        if (tile + 1 < t_end) {  // prefetch the next tile's extent and reference J
+            b_end_next = (int)(A.blk_off[tile + 2] - B0);
+            p_next = p + kTile;
+            if (p_next < A.pixels) {
+                Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
             }
         }
-        A.J[3 * p + 0] = Jn[0];
-        A.J[3 * p + 1] = Jn[1];
-        A.J[3 * p + 2] = Jn[2];
+        if (b_end == b) continue;  // warp-uniform
+        const u64 Jn[3] = {pk(-Jref[0], -Jref[0]), pk(-Jref[1], -Jref[1]), pk(-Jref[2], -Jref[2])};
+        PairStats<MODE, PRECISE> st;
+        st.clear();
+        int seen = 0;
+#pragma unroll 1
+        while (b < b_end) {
+            // two blocks (source views) per step, unless the pair would straddle a mask batch or the tile end
+            const int j = b & 31;
+            const bool two = j != 31 && b + 1 < b_end;
+            const uint32_t m0 = __shfl_sync(kFull, mcur, j);
+            const uint32_t m1x = __shfl_sync(kFull, mcur, (j + 1) & 31);
+            const uint32_t m1 = two ? m1x : 0u;
+            const int n0 = __popc(m0), n = n0 + __popc(m1);
+            while (rel + n > avail) {  // the records of this step must have landed
+                mbar_wait(bar_s + 8 * wait_slot, wait_parity);
+                avail += kChunkRecs;
+                if (++wait_slot == kStages) {
+                    wait_slot = 0;
+                    wait_parity ^= 1u;
+                }
+            }
+            const uint32_t w0 = (m0 >> lane) & 1u, w1 = (m1 >> lane) & 1u;
+            if (w0 | w1) {
+                int i0 = rpos + (w0 ? __popc(m0 & lt) : 0);
+                int i1 = rpos + (w1 ? n0 + __popc(m1 & lt) : 0);
+                i0 -= i0 >= kRingRecs ? kRingRecs : 0;
+                i1 -= i1 >= kRingRecs ? kRingRecs : 0;
+                st.add(ring[i0], ring[i1], pk((float)w0, (float)w1), kb, kg, Bp, Bn, Jn);
+                seen += (int)(w0 + w1);
+            }
+            rel += n;
+            rpos += n;
+            rpos -= rpos >= kRingRecs ? kRingRecs : 0;
+            b += two ? 2 : 1;
+            if (rel >= free_at) {  // every lane is done with the oldest slot: refill it
+                __syncwarp();
+                if (next_issue < n_chunks) {
+                    if (lane == 0) issue();
+                    ++next_issue;
+                    issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
+                }
+                free_at += kChunkRecs;
+            }
+            if ((b & 31) < 2 && (b >> 5) != ((b - (two ? 2 : 1)) >> 5)) {  // crossed into the next mask batch
+                mcur = mnext;
+                const int nb2 = ((b >> 5) + 1) * 32 + lane;
+                mnext = nb2 < n_blk ? __ldg(mk + nb2) : 0u;
+            }
+        }
+        if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
+            float Jout[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float S1 = sum2(st.S1[c]), S3 = sum2(st.S3[c]), S5 = sum2(st.S5[c]), S7 = sum2(st.S7[c]), S9 = sum2(st.S9[c]);
+                float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
+                if (MODE == kClosedForm) {
+                    delta = S1 / sum2(st.S2[c]);
+                    rh = fmaf(-delta, sum2(st.S4[c]), S3);
+                    rza = fmaf(-delta, sum2(st.S6[c]), S5);
+                    rzg = fmaf(-delta, sum2(st.S8[c]), S7);
+                    rr = fmaf(-delta, S1, S9);
+                }
+                Jout[c] = Jref[c] + delta;
+                acc[c] += (double)rh;                    // sum r (1 - e^{-gamma z})
+                acc[3 + c] += (double)(Jout[c] * rza);   // sum r J z e^{-beta z}
+                acc[6 + c] += (double)(q.B[c] * rzg);    // sum r B z e^{-gamma z}
+                acc[9] += (double)rr;                    // sum r^2
+                if (MODE == kParamJ) {
+                    // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step with the pre-step B, beta, gamma (sucre.py:144-148)
+                    float* mv = A.J_moments + 6 * p;
+                    float m = mv[c], v = mv[3 + c];
+                    Jout[c] = adam_update(Jref[c], (float)(-A.adam.grad_scale) * S1, m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
+                    mv[c] = m;
+                    mv[3 + c] = v;
+                }
+            }
+            A.J[3 * p + 0] = Jout[0];
+            A.J[3 * p + 1] = Jout[1];
+            A.J[3 * p + 2] = Jout[2];
+        }
     }
 
     // warp tree -> one slot per warp -> one row per CTA
@@ -360,7 +583,11 @@ static int fit_grid() {
     static int ctas = 0;
     if (ctas == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<kClosedForm, false>, kFitThreads, 0) != cudaSuccess || per_sm <= 0)
+        cudaFuncSetAttribute(fit_kernel<kClosedForm, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
+        cudaFuncSetAttribute(fit_kernel<kClosedForm, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
+        cudaFuncSetAttribute(fit_kernel<kParamJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
+        cudaFuncSetAttribute(fit_kernel<kParamJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<kClosedForm, false>, kFitThreads, kFitSmem) != cudaSuccess || per_sm <= 0)
             per_sm = 2;
         ctas = min(kMaxFitCtas, num_sms() * per_sm);
     }
@@ -369,8 +596,8 @@ static int fit_grid() {
 
 template <int MODE>
 static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st) {
-    if (precise_exp()) fit_kernel<MODE, true><<<ctas, kFitThreads, 0, st>>>(a);
-    else fit_kernel<MODE, false><<<ctas, kFitThreads, 0, st>>>(a);
+    if (precise_exp()) fit_kernel<MODE, true><<<ctas, kFitThreads, kFitSmem, st>>>(a);
+    else fit_kernel<MODE, false><<<ctas, kFitThreads, kFitSmem, st>>>(a);
 }
 
 static int check_store(const float* records, const int64_t* rec_off, const int64_t* blk_off, const uint32_t* blk_mask,
