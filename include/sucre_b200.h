@@ -59,31 +59,37 @@ const char* sucre_last_error(void);
  * (sfm.py:115-138, 154-159, 171-175), unproject_depth(_map) / project_to_view / Pose.transform
  * (sfm.py:49-55, 90-107) and load_depth_map's scaling (loader.py:166-170).
  *
- * sucre_gather_match: for every target pixel and every listed view, the reference's two-way integer
- * round-trip test.  masks[k*n_views + s] receives the lane mask of tile k against view s.
- * n_tiles = ceil(width*height / 32) of the target.  Bit-exact with the reference (SURVEY.md §8a'). */
-int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views,
-                       uint32_t* masks, void* stream);
+ * A call may cover the whole target or a band of it: tiles [first_tile, first_tile + n_tiles) (multi-GPU pixel
+ * sharding); masks / rec_off / blk_off / records / J of such a call are local to the band.
+ *
+ * sucre_gather_match: for every target pixel of the band and every listed view, the reference's two-way integer
+ * round-trip test.  masks[k*n_views + s] receives the lane mask of local tile k against view s.
+ * Bit-exact with the reference (SURVEY.md §8a'). */
+int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
+                       int n_tiles, uint32_t* masks, void* stream);
 
-/* sucre_gather_plan: per-view match counts, the min_cover decision (sfm.py:136: a view is kept iff
- * count / (width*height) > min_cover, evaluated in double like the reference's Python floats) and the
- * layout of the observation store.
- *   view_count[n_views]  (int64)  matches per view, kept or not
+/* sucre_gather_count: view_count[n_views] (int64) = matches per view over the band (kept or not).
+ * Multi-GPU callers all-reduce view_count before sucre_gather_plan: min_cover is a whole-image criterion. */
+int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t* view_count, void* stream);
+
+/* sucre_gather_plan: the min_cover decision (sfm.py:136: a view is kept iff count / (width*height) > min_cover,
+ * evaluated in double like the reference's Python floats; view_count and target_pixels are WHOLE-IMAGE figures)
+ * and the layout of the band's observation store.
  *   view_kept[n_views]   (uint8)  1 if the view passes min_cover
- *   rec_off[n_tiles+1], blk_off[n_tiles+1] (int64) exclusive prefix sums over tiles, kept views only
- *   totals[2] (int64)    {N = total observations, number of blocks}; copy to the host to size the store */
-int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, int64_t target_pixels, double min_cover,
-                      int64_t* view_count, uint8_t* view_kept, int64_t* rec_off, int64_t* blk_off,
-                      int64_t* totals, void* stream);
+ *   rec_off[n_tiles+1], blk_off[n_tiles+1] (int64) exclusive prefix sums over the band's tiles, kept views only
+ *   totals[2] (int64)    {N = observations in the band, number of blocks}; copy to the host to size the store */
+int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
+                      int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off,
+                      int64_t* blk_off, int64_t* totals, void* stream);
 
 /* sucre_gather_sample: fills the observation store.  Replaces MatchesFile.save_matches / prepare_matches /
  * load_matches (loader.py:68-87, 103-118) and load_rgb's scaling (loader.py:156-163); the HDF5 spill file is
  * replaced by this device-resident store.  rec_src (optional, may be NULL) receives u2 | v2 << 16, the
  * integer source pixel of every record (what the reference stores as int16 u2, v2). */
-int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views,
-                        const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                        const int64_t* blk_off, int n_tiles, float* records, uint32_t* blk_mask,
-                        int32_t* blk_view, uint32_t* rec_src, void* stream);
+int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
+                        int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
+                        const int64_t* blk_off, float* records, uint32_t* blk_mask, int32_t* blk_view,
+                        uint32_t* rec_src, void* stream);
 
 /* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
  * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for

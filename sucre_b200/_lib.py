@@ -29,9 +29,10 @@ _VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGNATURES = {
     'sucre_abi_version': (C.c_int, []),
     'sucre_last_error': (C.c_char_p, []),
-    'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _VP, _VP]),
-    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
-    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
+    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     'sucre_fit_workspace_bytes': (C.c_size_t, []),
     'sucre_fit_prepare': (C.c_int, [_VP, _I, _VP, _VP]),
     'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),

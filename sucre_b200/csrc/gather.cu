@@ -63,7 +63,7 @@ constexpr int kWarps = 8;
 template <int PIX>
 __global__ void __launch_bounds__(kWarps * 32)
 gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
-                    uint32_t* __restrict__ masks, int n_tiles) {
+                    uint32_t* __restrict__ masks, int first_tile, int n_tiles) {
     __shared__ __align__(16) sucre_view sv[kChunk];
     const int vbase = blockIdx.y * kChunk;
     const int nv = min(kChunk, n_views - vbase);
@@ -75,7 +75,7 @@ gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __re
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile0 = (blockIdx.x * kWarps + warp) * PIX;
+    const int tile0 = (blockIdx.x * kWarps + warp) * PIX;  // local tile index; global tile = first_tile + local
     const int P = T.width * T.height;
 
     float w[PIX][3];
@@ -83,8 +83,8 @@ gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __re
     bool valid[PIX];
 #pragma unroll
     for (int k = 0; k < PIX; ++k) {
-        const int p = (tile0 + k) * kTile + lane;
-        const bool inside = p < P;
+        const int p = (first_tile + tile0 + k) * kTile + lane;
+        const bool inside = p < P && tile0 + k < n_tiles;
         const float d1 = __fdiv_rn((float)(inside ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
         valid[k] = d1 > 0.0f;  // sfm.py:96
         v1[k] = p / T.width;
@@ -214,14 +214,14 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, int n, long lo
 __global__ void __launch_bounds__(256)
 gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                      const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
-                     const long long* __restrict__ rec_off, const long long* __restrict__ blk_off, int n_tiles,
+                     const long long* __restrict__ rec_off, const long long* __restrict__ blk_off, int first_tile, int n_tiles,
                      float4* __restrict__ records, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
                      uint32_t* __restrict__ rec_src) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
     const int P = T.width * T.height;
-    const int p = tile * kTile + lane;
+    const int p = (first_tile + tile) * kTile + lane;
     float w0, w1, w2;
     {
         const float d1 = __fdiv_rn((float)(p < P ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
@@ -295,49 +295,62 @@ static int check_view_host(const sucre_view* v, const char* who) {
 
 using namespace sucre;
 
-extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views,
-                                  uint32_t* masks, void* stream) {
+static int check_tile_range(const sucre_view* t, int first_tile, int n_tiles, const char* who) {
+    const int total = (t->width * t->height + kTile - 1) / kTile;
+    SUCRE_REQUIRE(first_tile >= 0 && n_tiles > 0 && first_tile + n_tiles <= total,
+                  "%s: tiles [%d, %d) outside the target's %d tiles", who, first_tile, first_tile + n_tiles, total);
+    return 0;
+}
+
+extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
+                                  int n_tiles, uint32_t* masks, void* stream) {
     clear_error();
     if (check_view_host(target_host, "sucre_gather_match(target)")) return 1;
     SUCRE_REQUIRE(views && masks, "sucre_gather_match: null pointer");
     SUCRE_REQUIRE(n_views > 0, "sucre_gather_match: n_views = %d", n_views);
-    const int P = target_host->width * target_host->height;
-    const int n_tiles = (P + kTile - 1) / kTile;
+    if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_match")) return 1;
     constexpr int PIX = 2;
     dim3 grid((n_tiles + kWarps * PIX - 1) / (kWarps * PIX), (n_views + kChunk - 1) / kChunk);
-    gather_match_kernel<PIX><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*target_host, views, n_views, masks, n_tiles);
+    gather_match_kernel<PIX><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*target_host, views, n_views, masks, first_tile, n_tiles);
     return check_launch("gather_match_kernel");
 }
 
-extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, int64_t target_pixels, double min_cover,
-                                 int64_t* view_count, uint8_t* view_kept, int64_t* rec_off, int64_t* blk_off,
-                                 int64_t* totals, void* stream) {
+extern "C" int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t* view_count, void* stream) {
     clear_error();
-    SUCRE_REQUIRE(masks && view_count && view_kept && rec_off && blk_off && totals, "sucre_gather_plan: null pointer");
-    SUCRE_REQUIRE(n_tiles > 0 && n_views > 0 && target_pixels > 0, "sucre_gather_plan: bad sizes");
+    SUCRE_REQUIRE(masks && view_count, "sucre_gather_count: null pointer");
+    SUCRE_REQUIRE(n_tiles > 0 && n_views > 0, "sucre_gather_count: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     SUCRE_CUDA(cudaMemsetAsync(view_count, 0, sizeof(int64_t) * n_views, st));
     dim3 cgrid((n_views + 31) / 32, min(64, (n_tiles + 7) / 8));
     count_views_kernel<<<cgrid, 256, 0, st>>>(masks, n_tiles, n_views, (unsigned long long*)view_count);
+    return check_launch("count_views_kernel");
+}
+
+extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
+                                 int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off,
+                                 int64_t* blk_off, int64_t* totals, void* stream) {
+    clear_error();
+    SUCRE_REQUIRE(masks && view_count && view_kept && rec_off && blk_off && totals, "sucre_gather_plan: null pointer");
+    SUCRE_REQUIRE(n_tiles > 0 && n_views > 0 && target_pixels > 0, "sucre_gather_plan: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
     kept_kernel<<<(n_views + 127) / 128, 128, 0, st>>>((const long long*)view_count, n_views, (double)target_pixels, min_cover, view_kept);
     tile_count_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(masks, view_kept, n_tiles, n_views, (long long*)rec_off, (long long*)blk_off);
     scan_kernel<<<1, 1024, 0, st>>>((long long*)rec_off, (long long*)blk_off, n_tiles, (long long*)totals);
     return check_launch("sucre_gather_plan kernels");
 }
 
-extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views,
-                                   const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                                   const int64_t* blk_off, int n_tiles, float* records, uint32_t* blk_mask,
-                                   int32_t* blk_view, uint32_t* rec_src, void* stream) {
+extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
+                                   int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
+                                   const int64_t* blk_off, float* records, uint32_t* blk_mask, int32_t* blk_view,
+                                   uint32_t* rec_src, void* stream) {
     clear_error();
     if (check_view_host(target_host, "sucre_gather_sample(target)")) return 1;
     SUCRE_REQUIRE(views && masks && view_kept && rec_off && blk_off && records && blk_mask && blk_view,
                   "sucre_gather_sample: null pointer");
-    const int P = target_host->width * target_host->height;
-    SUCRE_REQUIRE(n_tiles == (P + kTile - 1) / kTile, "sucre_gather_sample: n_tiles %d does not match the target", n_tiles);
+    if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_sample")) return 1;
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, "sucre_gather_sample: records must be 16-byte aligned");
     gather_sample_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        *target_host, views, n_views, masks, view_kept, (const long long*)rec_off, (const long long*)blk_off, n_tiles,
+        *target_host, views, n_views, masks, view_kept, (const long long*)rec_off, (const long long*)blk_off, first_tile, n_tiles,
         reinterpret_cast<float4*>(records), blk_mask, blk_view, rec_src);
     return check_launch("gather_sample_kernel");
 }

@@ -113,11 +113,26 @@ class ObservationStore:
     blk_view: torch.Tensor        # (n_blocks,) int32 index into source_keys
     rec_src: torch.Tensor | None  # (N,) int32 u2 | v2 << 16
     workspace: torch.Tensor | None = None  # fit scratch, prepared on first use
+    first_tile: int = 0           # band of the target this store covers (multi-GPU pixel sharding): tiles
+    n_tiles: int = 0              # [first_tile, first_tile + n_tiles); 0 = the whole target (set in __post_init__)
     stats: dict = field(default_factory=dict)
 
+    def __post_init__(self):
+        if self.n_tiles == 0:
+            self.n_tiles = (self.width * self.height + TILE - 1) // TILE
+
     @property
-    def n_tiles(self) -> int:
-        return (self.width * self.height + TILE - 1) // TILE
+    def is_band(self) -> bool:
+        return self.first_tile != 0 or self.n_tiles != (self.width * self.height + TILE - 1) // TILE
+
+    @property
+    def local_pixels(self) -> int:
+        """Target pixels covered by this store (flat range starting at first_tile * 32)."""
+        return min(self.width * self.height - self.first_tile * TILE, self.n_tiles * TILE)
+
+    @property
+    def J_shape(self) -> tuple:
+        return (self.local_pixels, 3) if self.is_band else (self.height, self.width, 3)
 
     @property
     def kept_keys(self) -> list:
@@ -134,7 +149,7 @@ class ObservationStore:
         lanes = torch.arange(32, device=dev, dtype=torch.int64)
         bits = ((self.blk_mask.to(torch.int64)[:, None] >> lanes[None, :]) & 1).bool()
         blk, lane = bits.nonzero(as_tuple=True)
-        return blk_tile[blk] * TILE + lane, self.blk_view.to(torch.int64)[blk]
+        return (blk_tile[blk] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[blk]
 
     def to_reference_layout(self) -> dict:
         """Per kept view (in source_keys order) the arrays the reference's MatchesFile/MatchesData hold
@@ -164,10 +179,15 @@ def _stream(device) -> int:
 
 
 def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
-           target_record: np.ndarray | None = None) -> ObservationStore:
-    """Stage 1 on the device: match -> plan -> (one 16-byte D2H to size the store) -> sample.
+           target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
+           reduce_counts=None) -> ObservationStore:
+    """Stage 1 on the device: match -> count -> plan -> (one 16-byte D2H to size the store) -> sample.
     Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
-    (sfm.py:127-138, loader.py:78-87, 103-118)."""
+    (sfm.py:127-138, loader.py:78-87, 103-118).
+
+    tile_range = (first_tile, n_tiles) restricts the call to a band of the target (multi-GPU pixel sharding);
+    reduce_counts(view_count) then sums the per-view match counts over all bands in place (an all-reduce), because
+    min_cover is a whole-image criterion (sfm.py:136)."""
     L = _lib.lib()
     dev = scene.device
     source_keys = tuple(source_keys)
@@ -177,7 +197,7 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
     trec = scene.record(target_key) if target_record is None else target_record
     W, H = int(trec['width']), int(trec['height'])
     P = W * H
-    n_tiles = (P + TILE - 1) // TILE
+    first_tile, n_tiles = (0, (P + TILE - 1) // TILE) if tile_range is None else (int(tile_range[0]), int(tile_range[1]))
     table = scene.table(source_keys)
     with torch.cuda.device(dev):
         st = _stream(dev)
@@ -188,8 +208,12 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
         blk_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
         totals = torch.empty(2, dtype=torch.int64, device=dev)
         tptr = trec.ctypes.data
-        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, masks.data_ptr(), st), 'sucre_gather_match')
-        _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, P, float(min_cover), view_count.data_ptr(),
+        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(), st),
+                   'sucre_gather_match')
+        _lib.check(L.sucre_gather_count(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), st), 'sucre_gather_count')
+        if reduce_counts is not None:
+            reduce_counts(view_count)
+        _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), P, float(min_cover),
                                        view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
                                        totals.data_ptr(), st), 'sucre_gather_plan')
         n_obs, n_blocks = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
@@ -201,16 +225,17 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
             missing = [k for k in source_keys if k not in scene.rgb]
             if missing:
                 raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
-            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, masks.data_ptr(), view_kept.data_ptr(),
-                                             rec_off.data_ptr(), blk_off.data_ptr(), n_tiles, records.data_ptr(),
-                                             blk_mask.data_ptr(), blk_view.data_ptr(),
+            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
+                                             view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
+                                             records.data_ptr(), blk_mask.data_ptr(), blk_view.data_ptr(),
                                              0 if rec_src is None else rec_src.data_ptr(), st), 'sucre_gather_sample')
         vc = view_count.cpu().numpy()
         vk = view_kept.cpu().numpy().astype(bool)
     return ObservationStore(width=W, height=H, source_keys=source_keys, view_count=vc, view_kept=vk, n_obs=n_obs,
                             n_blocks=n_blocks, records=records[:n_obs], rec_off=rec_off, blk_off=blk_off,
                             blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
-                            rec_src=None if rec_src is None else rec_src[:n_obs])
+                            rec_src=None if rec_src is None else rec_src[:n_obs], first_tile=first_tile,
+                            n_tiles=n_tiles)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -243,8 +268,8 @@ class FitState:
 
     def ensure_J(self, store: 'ObservationStore'):
         if self.J is None:
-            self.J = torch.zeros((store.height, store.width, 3), dtype=torch.float32, device=store.records.device)
-        assert self.J.shape == (store.height, store.width, 3) and self.J.is_contiguous()
+            self.J = torch.zeros(store.J_shape, dtype=torch.float32, device=store.records.device)
+        assert tuple(self.J.shape) == store.J_shape and self.J.is_contiguous()
 
 
 def _workspace(store: ObservationStore) -> torch.Tensor:
@@ -260,7 +285,7 @@ def _workspace(store: ObservationStore) -> torch.Tensor:
 
 def _store_ptrs(store: ObservationStore):
     return (store.records.data_ptr(), store.rec_off.data_ptr(), store.blk_off.data_ptr(), store.blk_mask.data_ptr(),
-            store.n_tiles, store.width * store.height)
+            store.n_tiles, store.local_pixels)
 
 
 def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05) -> torch.Tensor:
@@ -309,7 +334,7 @@ def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, histor
 def closed_form_J(store: ObservationStore, params: torch.Tensor, J_ref: torch.Tensor | None = None) -> torch.Tensor:
     """update_J (sucre.py:66-77) with the given parameters: (H,W,3) f32 on the device, NaN where unobserved."""
     dev = store.records.device
-    J = torch.empty((store.height, store.width, 3), dtype=torch.float32, device=dev)
+    J = torch.empty(store.J_shape, dtype=torch.float32, device=dev)
     if store.n_obs == 0:
         return J.fill_(float('nan'))
     with torch.cuda.device(dev):

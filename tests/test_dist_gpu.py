@@ -1,0 +1,96 @@
+"""Pixel-band sharding on the GPU: bands compose to the whole-image result (1 GPU), and the NCCL choreography
+reproduces the single-GPU restoration (>= 2 GPUs, skipped otherwise)."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sucre_b200 import api, engine
+from sucre_b200 import dist as sdist
+from sucre_b200.synth import SyntheticScene
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bands_compose_to_the_whole_image():
+    scene = SyntheticScene(7, 150, 101, seed=9)   # 15150 pixels = 473 tiles + 14 pixels
+    ds, _ = helpers.build_device_scene(scene, range(7))
+    keys = list(range(7))
+    full = engine.gather(ds, 3, keys, min_cover=0.2, keep_src=True)
+    n_tiles = full.n_tiles
+    counts = []
+    for r in range(3):
+        counts.append(engine.gather(ds, 3, keys, min_cover=0.0, tile_range=sdist.tile_band(n_tiles, r, 3)).view_count)
+    total = torch.from_numpy(np.sum(counts, axis=0)).cuda()
+    assert np.array_equal(total.cpu().numpy(), full.view_count)
+    bands = [engine.gather(ds, 3, keys, min_cover=0.2, keep_src=True, tile_range=sdist.tile_band(n_tiles, r, 3),
+                           reduce_counts=lambda vc: vc.copy_(total)) for r in range(3)]
+    assert sum(b.n_obs for b in bands) == full.n_obs and all(np.array_equal(b.view_kept, full.view_kept) for b in bands)
+    whole = full.to_reference_layout()
+    parts = [b.to_reference_layout() for b in bands]
+    for key, ref in whole.items():
+        for f in ('u1', 'v1', 'u2', 'v2', 'z', 'I'):
+            cat = np.concatenate([p[key][f] for p in parts], axis=-1)
+            assert np.array_equal(cat, ref[f]), (key, f)
+    # one objective evaluation: band sums add up to the whole-image sums; band J's tile the whole J
+    state = engine.FitState.initial(ds.device)
+    sums = torch.zeros(10, dtype=torch.float64, device=ds.device)
+    engine.fit_sums(full, state, sums)
+    acc = torch.zeros_like(sums)
+    Js = []
+    for b in bands:
+        sb = engine.FitState.initial(ds.device)
+        s = torch.zeros_like(sums)
+        engine.fit_sums(b, sb, s)
+        acc += s
+        Js.append(engine.closed_form_J(b, sb.params))
+    assert torch.allclose(acc, sums, rtol=1e-12, atol=0)
+    J = engine.closed_form_J(full, state.params).reshape(-1, 3)
+    assert torch.equal(torch.cat(Js).nan_to_num(-7.0), J.nan_to_num(-7.0))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, closed_form, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        scene = SyntheticScene(8, 320, 240, seed=11)
+        ds, _ = helpers.build_device_scene(scene, range(8), device=f'cuda:{rank}')
+        ops = sdist.CudaBandOps(ds, 4, list(range(8)), use_closed_form=closed_form)
+        res = sdist.restore_band_sharded(ops, num_iter=25)
+        if rank == 0:
+            np.savez(out_path, J=res.J.cpu().numpy(), params=res.params.cpu().numpy(), history=res.history.cpu().numpy(),
+                     n_obs=res.n_obs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('closed_form', [True, False])
+def test_band_sharded_nccl_matches_single_gpu(closed_form):
+    world = min(4, torch.cuda.device_count())
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, 'res.npz')
+        mp.spawn(_nccl_worker, args=(world, _free_port(), closed_form, out), nprocs=world, join=True)
+        z = np.load(out)
+    scene = SyntheticScene(8, 320, 240, seed=11)
+    ds, _ = helpers.build_device_scene(scene, range(8))
+    one = api.restore_resident(ds, 4, list(range(8)), use_closed_form=closed_form, num_iter=25)
+    assert int(z['n_obs']) == one.n_obs
+    p1 = one.params.cpu().numpy()
+    assert np.max(np.abs(z['params'] - p1) / np.abs(p1)) < 1e-5
+    J1 = one.J.cpu().numpy()
+    assert np.array_equal(np.isnan(z['J']), np.isnan(J1)) and np.nanmax(np.abs(z['J'] - J1)) < 1e-5
