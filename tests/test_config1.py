@@ -1,0 +1,91 @@
+"""BASELINE.json configs[0] — the reference's own CPU-runnable case (20 views 640x480, --image-name image0008.png,
+--use-closed-form, 200 iterations) — against a summary of the unmodified reference's run (tests/golden/config1_*.npz:
+per-view counts, sha256 of the index / payload arrays, the 200-iteration parameter trajectory, a J subsample).
+The scene is regenerated from the seed (its sha256 is checked first); geometry comes from the fixture."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from sucre_b200.synth import SyntheticScene
+
+
+def _sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _scene(g, device='cpu'):
+    scene = SyntheticScene(int(g['n_views']), int(g['width']), int(g['height']), seed=int(g['seed']))
+    inputs = [tuple(t.cpu().numpy() for t in scene.render(i, device=device)) for i in range(scene.n_views)]
+    h = hashlib.sha256()
+    for d, c in inputs:
+        h.update(d.tobytes())
+        h.update(c.tobytes())
+    if h.hexdigest() != str(g['inputs_sha256']):
+        pytest.skip('synthetic scene differs from the one the fixture was generated on (float64 libm drift)')
+    return scene, inputs
+
+
+def _rel(a, b, floor=1e-12):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def test_oracle_on_config1(golden):
+    g = golden('config1_closed')
+    scene, inputs = _scene(g)
+    geoms = []
+    for i in range(scene.n_views):
+        a = g.geom_arrays(i)
+        geoms.append(oracle.view_geom(a['K'], a['R'], a['t'], a['wh'][0], a['wh'][1], Kinv=a['Kinv'], Ri=a['Ri'], ti=a['ti']))
+    tgt = g.view_index(str(g['target']))
+    sources = [(scene.image_name(i), inputs[i][0], inputs[i][1], geoms[i]) for i in range(scene.n_views)]
+    kept, _ = oracle.gather(inputs[tgt][0], geoms[tgt], sources)
+    assert [k for k, _ in kept] == g['kept'].tolist()
+    assert [len(o['u1']) for _, o in kept] == g['n'].tolist()
+    for (name, o), idx_sha, obs_sha in zip(kept, g['idx_sha256'].tolist(), g['obs_sha256'].tolist()):
+        assert _sha(o['u1'], o['v1'], o['u2'], o['v2']) == idx_sha, name      # bit-exact indices, 3.4 M matches
+        assert _sha(o['d'], o['I'], o['z']) == obs_sha, name                  # bit-exact d, I, z
+    res = oracle.fit([o for _, o in kept], scene.width, scene.height, closed_form=True, num_iter=int(g['num_iter']))
+    assert _rel(res['history'], g['history'], floor=0.05) < 5e-5
+    assert _rel(res['params'], np.concatenate([g['B'].ravel(), g['beta'].ravel(), g['gamma'].ravel()])) < 1e-4
+    assert _rel(res['cost'], g['cost']) < 2e-4
+    s = int(g['J_stride'])
+    Js = res['J'][::s, ::s]
+    assert np.array_equal(np.isnan(Js), np.isnan(g['J_sub'])) and np.nanmax(np.abs(Js - g['J_sub'])) < 1e-4
+    assert int(np.isnan(res['J']).any(axis=2).sum()) == int(g['J_nan_count'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['closed', 'param'])
+def test_cuda_on_config1(golden, mode):
+    from sucre_b200 import api, engine
+    import helpers
+    g = golden(f'config1_{mode}')
+    scene, inputs = _scene(g, device='cuda')
+    vg, _ = helpers.geoms_from_golden(g)
+    ds = engine.DeviceScene('cuda')
+    for i in range(scene.n_views):
+        ds.add_view(scene.image_name(i), vg[i], torch.from_numpy(inputs[i][0]), torch.from_numpy(inputs[i][1]))
+    order = sorted(scene.image_name(i) for i in range(scene.n_views))
+    res = api.restore_resident(ds, str(g['target']), order, use_closed_form=(mode == 'closed'),
+                               num_iter=int(g['num_iter']), keep_src=True)
+    got = res.store.to_reference_layout()
+    assert list(got) == g['kept'].tolist() and [len(o['u1']) for o in got.values()] == g['n'].tolist()
+    for (name, o), idx_sha in zip(got.items(), g['idx_sha256'].tolist()):
+        assert _sha(o['u1'], o['v1'], o['u2'], o['v2']) == idx_sha, name      # bit-exact vs the reference
+    hist = res.history.cpu().numpy()
+    ref_p = np.concatenate([g['B'].ravel(), g['beta'].ravel(), g['gamma'].ravel()])
+    assert _rel(res.params.cpu().numpy(), ref_p) < 1e-4                        # B, beta, gamma: 1e-4 relative
+    assert _rel(hist[:, :9], g['history'], floor=0.05) < 1e-4
+    assert _rel(hist[:, 9], g['cost']) < 2e-4
+    J = res.J.cpu().numpy()
+    s = int(g['J_stride'])
+    assert np.array_equal(np.isnan(J[::s, ::s]), np.isnan(g['J_sub']))
+    assert np.nanmax(np.abs(J[::s, ::s] - g['J_sub'])) < 1e-3                  # J: 1e-3 max-abs
+    assert int(np.isnan(J).any(axis=2).sum()) == int(g['J_nan_count'])
+    assert np.allclose(np.nanmean(J.reshape(-1, 3).astype(np.float64), axis=0), g['J_nanmean'], atol=1e-4)
