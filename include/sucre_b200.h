@@ -12,15 +12,19 @@
  *   - the caller owns all memory; nothing here allocates, frees, or synchronises the device;
  *     work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
  *   - images are row-major; a target pixel has flat index p = v*width + u; a "tile" is
- *     SUCRE_TILE_PIXELS (32) consecutive flat pixels, tile k covering p in [32k, 32k+32).
+ *     SUCRE_TILE_PIXELS (32) consecutive flat pixels, tile k covering p in [32k, 32k+32) — one warp, one lane
+ *     per pixel.
  *
- * Observation store produced by the gather and consumed by the fit ("tile-major compact stream"):
- *   for tile k, blocks blk_off[k] .. blk_off[k+1] list the kept source views with at least one match in the
- *   tile, in pairing-list order; block b carries a 32-bit lane mask blk_mask[b] (bit i = pixel 32k+i matched
- *   in that view) and its source-view index blk_view[b]; the matched pixels' records follow one another in
- *   `records`, starting at rec_off[k] for the tile's first block, popcount(mask) records per block, ordered by
- *   lane.  One record = float4 {z, I_r, I_g, I_b}: z = ||cP|| the range of the observation in the source
- *   camera frame (loader.py:113 + sucre.py:53), I = source colour / 255 (loader.py:157, 87).
+ * Observation store produced by the gather and consumed by the fit ("tile-major segmented stream"):
+ *   `cells` is an array of 16-byte cells.  For tile k the kept source views with at least one match in the tile
+ *   ("blocks", in pairing-list order; lane mask blk_mask[b], view index blk_view[b], b in blk_off[k]..blk_off[k+1])
+ *   are grouped SUCRE_SEGMENT_VIEWS (8) at a time into segments.  A segment is SUCRE_SEGMENT_HEADER_CELLS (2)
+ *   header cells — 32 bytes, byte i = number of records of lane i's pixel in the segment (0..8) — followed by the
+ *   records LANE-MAJOR: lane 0's records (in view order), then lane 1's, ...  One record = float4
+ *   {z, I_r, I_g, I_b}: z = ||cP|| the range of the observation in the source camera frame (loader.py:113 +
+ *   sucre.py:53), I = source colour / 255 (loader.py:157, 87).  The first cell of tile k is
+ *   rec_off[k] + 2*seg_off[k]; tiles follow each other, so any run of tiles is one contiguous byte range (the fit
+ *   streams it with 1-D TMA bulk copies).  Total cells = N + 2 * (number of segments).
  */
 #ifndef SUCRE_B200_H
 #define SUCRE_B200_H
@@ -32,8 +36,10 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 1
+#define SUCRE_ABI_VERSION 2
 #define SUCRE_TILE_PIXELS 32
+#define SUCRE_SEGMENT_VIEWS 8
+#define SUCRE_SEGMENT_HEADER_CELLS 2
 
 /* One view (source or target).  All matrices row-major fp32, computed on the host with the reference's own
  * expressions so that they are bit-identical to what the reference multiplies by:
@@ -51,6 +57,18 @@ typedef struct sucre_view {
     const uint8_t* rgb;
 } sucre_view;
 
+/* The observation store of one target (or of a band of its tiles), as the fit reads it.  A host struct of
+ * device pointers.  sizeof == 48. */
+typedef struct sucre_store {
+    const float* cells;      /* 16-byte cells, 16-byte aligned */
+    const int64_t* rec_off;  /* [n_tiles+1] records before tile k */
+    const int64_t* blk_off;  /* [n_tiles+1] blocks before tile k */
+    const int64_t* seg_off;  /* [n_tiles+1] segments before tile k */
+    int32_t n_tiles;
+    int32_t reserved;
+    int64_t pixels;          /* target pixels covered: min(n_tiles*32, width*height - first_tile*32) */
+} sucre_store;
+
 int sucre_abi_version(void);
 const char* sucre_last_error(void);
 
@@ -60,7 +78,7 @@ const char* sucre_last_error(void);
  * (sfm.py:49-55, 90-107) and load_depth_map's scaling (loader.py:166-170).
  *
  * A call may cover the whole target or a band of it: tiles [first_tile, first_tile + n_tiles) (multi-GPU pixel
- * sharding); masks / rec_off / blk_off / records / J of such a call are local to the band.
+ * sharding); masks / offsets / cells / J of such a call are local to the band.
  *
  * sucre_gather_match: for every target pixel of the band and every listed view, the reference's two-way integer
  * round-trip test.  masks[k*n_views + s] receives the lane mask of local tile k against view s.
@@ -76,20 +94,21 @@ int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t*
  * evaluated in double like the reference's Python floats; view_count and target_pixels are WHOLE-IMAGE figures)
  * and the layout of the band's observation store.
  *   view_kept[n_views]   (uint8)  1 if the view passes min_cover
- *   rec_off[n_tiles+1], blk_off[n_tiles+1] (int64) exclusive prefix sums over the band's tiles, kept views only
- *   totals[2] (int64)    {N = observations in the band, number of blocks}; copy to the host to size the store */
+ *   rec_off, blk_off, seg_off [n_tiles+1] (int64) exclusive prefix sums over the band's tiles, kept views only
+ *   totals[3] (int64)    {N = observations in the band, blocks, segments}; copy to the host to size the store:
+ *                        cells = N + 2*segments, blk_mask / blk_view = blocks entries */
 int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
                       int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off,
-                      int64_t* blk_off, int64_t* totals, void* stream);
+                      int64_t* blk_off, int64_t* seg_off, int64_t* totals, void* stream);
 
 /* sucre_gather_sample: fills the observation store.  Replaces MatchesFile.save_matches / prepare_matches /
  * load_matches (loader.py:68-87, 103-118) and load_rgb's scaling (loader.py:156-163); the HDF5 spill file is
- * replaced by this device-resident store.  rec_src (optional, may be NULL) receives u2 | v2 << 16, the
- * integer source pixel of every record (what the reference stores as int16 u2, v2). */
+ * replaced by this device-resident store.  cell_src (optional, may be NULL; one uint32 per cell) receives
+ * u2 | v2 << 16 at every record cell: the integer source pixel (what the reference stores as int16 u2, v2). */
 int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
                         int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                        const int64_t* blk_off, float* records, uint32_t* blk_mask, int32_t* blk_view,
-                        uint32_t* rec_src, void* stream);
+                        const int64_t* blk_off, const int64_t* seg_off, float* cells, uint32_t* blk_mask,
+                        int32_t* blk_view, uint32_t* cell_src, void* stream);
 
 /* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
  * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for
@@ -102,7 +121,7 @@ int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, 
  * mode SUCRE_FIT_PARAM_J      default CLI mode: J[pixels*3] is an Adam parameter (sucre.py:47-50), initialised by
  *                             the caller to the target image with NaN where target depth <= 0; J_moments
  *                             [pixels*6] = per pixel {exp_avg[3], exp_avg_sq[3]}, zero-initialised.
- * Every iteration reads each record exactly once. */
+ * Every iteration reads each cell exactly once. */
 #define SUCRE_FIT_CLOSED_FORM 0
 #define SUCRE_FIT_PARAM_J 1
 
@@ -111,7 +130,7 @@ size_t sucre_fit_workspace_bytes(void);
 
 /* Once per observation store, before any other fit call on `workspace`: partitions the tiles over the
  * resident warps by block count (static => reproducible summation order). */
-int sucre_fit_prepare(const int64_t* blk_off, int n_tiles, void* workspace, void* stream);
+int sucre_fit_prepare(const sucre_store* store_host, void* workspace, void* stream);
 
 /* One evaluation of the objective at `params`, reduced to sums[10] (double):
  *   sums[0..2] = sum r(1-e^{-gamma z}), sums[3..5] = sum r J z e^{-beta z}, sums[6..8] = sum r B z e^{-gamma z},
@@ -119,9 +138,8 @@ int sucre_fit_prepare(const int64_t* blk_off, int n_tiles, void* workspace, void
  * r = I - (J e^{-beta z} + B(1-e^{-gamma z})) (sucre.py:81).  In SUCRE_FIT_PARAM_J mode the per-pixel Adam step t of
  * J (gradient -(2/(3 n_obs)) sum r e^{-beta z}) is applied in the same pass; n_obs, t, lr are ignored otherwise.
  * Multi-GPU callers all-reduce sums between this call and sucre_adam_step; n_obs is then the global count. */
-int sucre_fit_sums(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                   const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params, float* J,
-                   float* J_moments, int64_t n_obs, int t, double lr, double* sums, void* workspace, void* stream);
+int sucre_fit_sums(int mode, const sucre_store* store_host, const float* params, float* J, float* J_moments,
+                   int64_t n_obs, int t, double lr, double* sums, void* workspace, void* stream);
 
 /* Adam step t (1-based) on the 9 parameters from the reduced sums: gradients of sum r^2 / (3 n_obs)
  * (sucre.py:144-145), update rule of torch.optim.Adam defaults (sucre.py:136,148: betas .9/.999, eps 1e-8,
@@ -132,16 +150,14 @@ int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_
 /* The whole single-GPU loop of adam() (sucre.py:138-148): num_iter kernels, each = one sweep + the Adam step of
  * the 9 scalars (steps first_step .. first_step+num_iter-1).  history (optional) = num_iter x 10 floats.
  * For the final update_J of closed-form mode (sucre.py:156) call sucre_fit_write_J. */
-int sucre_fit(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
-              const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, int64_t n_obs, float* params,
-              float* adam_state, float* J, float* J_moments, int first_step, int num_iter, double lr,
-              float* history, void* workspace, void* stream);
+int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
+              float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
+              void* stream);
 
-/* Closed-form J for the current params written to J[target_pixels*3] (H,W,3); NaN where a pixel has no
- * observation (0/0 like sucre.py:77).  J_ref (optional): a previous J used as the reference point. */
-int sucre_fit_write_J(const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                      const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params,
-                      const float* J_ref, float* J, void* stream);
+/* Closed-form J for the current params written to J[pixels*3]; NaN where a pixel has no observation (0/0 like
+ * sucre.py:77).  J_ref (optional): a previous J used as the reference point of the statistics. */
+int sucre_fit_write_J(const sucre_store* store_host, const float* params, const float* J_ref, float* J,
+                      void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

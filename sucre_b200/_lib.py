@@ -9,8 +9,9 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 1
+ABI_VERSION = 2
 TILE = 32
+SEG_VIEWS, SEG_HEADER_CELLS = 8, 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
 
 # numpy mirror of `struct sucre_view` (192 bytes)
@@ -23,6 +24,15 @@ class SucreError(RuntimeError):
     pass
 
 
+class SucreStore(C.Structure):
+    """ctypes mirror of `struct sucre_store` (host struct of device pointers, 48 bytes)."""
+    _fields_ = [('cells', C.c_void_p), ('rec_off', C.c_void_p), ('blk_off', C.c_void_p), ('seg_off', C.c_void_p),
+                ('n_tiles', C.c_int32), ('reserved', C.c_int32), ('pixels', C.c_int64)]
+
+
+assert C.sizeof(SucreStore) == 48
+
+
 _lib = None
 
 _VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -31,14 +41,14 @@ _SIGNATURES = {
     'sucre_last_error': (C.c_char_p, []),
     'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
-    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP]),
-    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     'sucre_fit_workspace_bytes': (C.c_size_t, []),
-    'sucre_fit_prepare': (C.c_int, [_VP, _I, _VP, _VP]),
-    'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
+    'sucre_fit_prepare': (C.c_int, [_VP, _VP, _VP]),
+    'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
     'sucre_adam_step': (C.c_int, [_VP, _VP, _VP, _I64, _I, _D, _VP, _VP]),
-    'sucre_fit': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I, _I64, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
-    'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _I, _I64, _VP, _VP, _VP, _VP]),
+    'sucre_fit': (C.c_int, [_I, _VP, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
+    'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -1,8 +1,9 @@
 // Stage 2 — per-pixel fit of the underwater image formation model for sm_100a.
 //
-// One warp owns one tile (32 consecutive target pixels), one lane one pixel.  The tile's observations are a
-// contiguous run of 16-byte records {z, I_r, I_g, I_b}; per block (= source view) the matched lanes read
-// consecutive records: one coalesced 128-bit load per lane, four blocks in flight per warp.
+// One warp owns one tile (32 consecutive target pixels), one lane one pixel.  The observation store is a stream
+// of 16-byte cells, tile after tile; within a tile, segments of 8 source views: 2 header cells (32 per-lane
+// record counts) then the records {z, I_r, I_g, I_b} LANE-MAJOR, so every lane walks its own contiguous run and
+// the inner loop carries no mask / popcount / shuffle addressing at all.
 //
 // Every Adam iteration reads every record exactly ONCE.  The reference makes two passes (update_J, then
 // forward/backward with J held constant, sucre.py:141-146); here both come out of one sweep through per-pixel
@@ -88,108 +89,18 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
     return s;
 }
 
-template <int MODE, bool PRECISE>
-struct PixelStats {
-    // closed form: 9 statistics per channel; J parameter: S2, S4, S6, S8 are not needed; write-J: S1, S2 only
-    float S1[3], S2[3], S3[3], S4[3], S5[3], S6[3], S7[3], S8[3], S9[3];
-
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) S1[c] = S2[c] = S3[c] = S4[c] = S5[c] = S6[c] = S7[c] = S8[c] = S9[c] = 0.f;
-    }
-
-    __device__ __forceinline__ void add(const float4 r, const Coef& q, const float Jref[3]) {
-        const float z = r.x;
-        const float I[3] = {r.y, r.z, r.w};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float a = PRECISE ? expf(-q.beta[c] * z) : fast_exp2(q.kb[c] * z);
-            const float g = PRECISE ? expf(-q.gamma[c] * z) : fast_exp2(q.kg[c] * z);
-            const float D = fmaf(q.B[c], g, I[c] - q.B[c]);  // I - B (1 - g)
-            const float Dp = fmaf(-Jref[c], a, D);           // shifted residual
-            S1[c] = fmaf(Dp, a, S1[c]);
-            if (MODE != kParamJ) S2[c] = fmaf(a, a, S2[c]);
-            if (MODE == kWriteJ) continue;
-            const float h = 1.0f - g, za = z * a, zg = z * g;
-            S3[c] = fmaf(Dp, h, S3[c]);
-            S5[c] = fmaf(Dp, za, S5[c]);
-            S7[c] = fmaf(Dp, zg, S7[c]);
-            S9[c] = fmaf(Dp, Dp, S9[c]);
-            if (MODE == kClosedForm) {
-                S4[c] = fmaf(a, h, S4[c]);
-                S6[c] = fmaf(a, za, S6[c]);
-                S8[c] = fmaf(a, zg, S8[c]);
-            }
-        }
-    }
-};
-
-// Streams the records of one tile through `st`.  Four blocks (source views) per step: their masks are
-// warp-uniform loads, the four 128-bit record loads are issued before any arithmetic.
-template <class Stats>
-__device__ __forceinline__ int sweep_tile(const float4* __restrict__ records, const uint32_t* __restrict__ blk_mask,
-                                          long long rec, long long b0, int nb, int lane, const Coef& q,
-                                          const float Jref[3], Stats& st) {
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t* __restrict__ mk = blk_mask + b0;
-    int seen = 0;
-    int j = 0;
-    for (; j + 4 <= nb; j += 4) {
-        const uint32_t m0 = __ldg(mk + j), m1 = __ldg(mk + j + 1), m2 = __ldg(mk + j + 2), m3 = __ldg(mk + j + 3);
-        const int n0 = __popc(m0), n1 = __popc(m1), n2 = __popc(m2), n3 = __popc(m3);
-        const bool a0 = (m0 >> lane) & 1u, a1 = (m1 >> lane) & 1u, a2 = (m2 >> lane) & 1u, a3 = (m3 >> lane) & 1u;
-        float4 r0, r1, r2, r3;
-        if (a0) r0 = __ldcs(records + rec + __popc(m0 & lt));
-        if (a1) r1 = __ldcs(records + rec + n0 + __popc(m1 & lt));
-        if (a2) r2 = __ldcs(records + rec + n0 + n1 + __popc(m2 & lt));
-        if (a3) r3 = __ldcs(records + rec + n0 + n1 + n2 + __popc(m3 & lt));
-        rec += n0 + n1 + n2 + n3;
-        if (a0) st.add(r0, q, Jref);
-        if (a1) st.add(r1, q, Jref);
-        if (a2) st.add(r2, q, Jref);
-        if (a3) st.add(r3, q, Jref);
-        seen += (int)a0 + (int)a1 + (int)a2 + (int)a3;
-    }
-    for (; j < nb; ++j) {
-        const uint32_t m = __ldg(mk + j);
-        if ((m >> lane) & 1u) {
-            st.add(__ldcs(records + rec + __popc(m & lt)), q, Jref);
-            ++seen;
-        }
-        rec += __popc(m);
-    }
-    return seen;
-}
-
-struct FitArgs {
-    const float4* records;
-    const long long* rec_off;
-    const long long* blk_off;
-    const uint32_t* blk_mask;
-    int n_tiles;
-    long long pixels;
-    float* params;        // 9: B, beta, gamma (read at start; written by the last CTA when do_step)
-    float* moments;       // 18: Adam state of the 9 scalars
-    float* J;             // pixels*3: Jref (closed form, in/out) or the J parameter (in/out)
-    float* J_moments;     // pixels*6: per pixel {m[3], v[3]} (J parameter mode)
-    const int* partition; // per global warp: first tile; [n_warps] = n_tiles
-    double* partials;     // gridDim.x rows of kSums
-    unsigned* ticket;
-    double* sums_out;     // if non-null the last CTA stores the reduced sums here
-    float* history_row;   // if non-null: params after the step + cost
-    int do_step;          // apply Adam to the 9 scalars in the last CTA
-    AdamScalars adam;
-};
-
 // ---- per-warp bulk-copy ring --------------------------------------------------------------------------------
-// The tiles of one warp are consecutive, so its records are ONE contiguous byte range in HBM.  The warp streams
-// that range through a private shared-memory ring with cp.async.bulk (TMA 1-D copies of 4 KB, kStages slots,
-// one mbarrier per slot): HBM latency is covered by the copies in flight instead of by occupancy, and the
-// arithmetic reads 16-byte records from shared memory.
-constexpr int kChunkRecs = 256;                   // records per bulk copy (4 KB)
-constexpr int kStages = 3;                        // ring slots per warp
-constexpr int kRingRecs = kChunkRecs * kStages;   // 768 records = 12 KB per warp, 96 KB per CTA, 2 CTAs per SM
-constexpr size_t kFitSmem = (size_t)kFitWarps * kRingRecs * sizeof(float4);
+// The tiles of one warp are consecutive, so its cells are ONE contiguous byte range in HBM.  The warp streams that
+// range through a private shared-memory ring with cp.async.bulk (TMA 1-D copies of 4 KB, kStages slots, one
+// mbarrier per slot): HBM latency is covered by the copies in flight instead of by occupancy, and the arithmetic
+// reads 16-byte records from shared memory.
+constexpr int kChunkCells = 256;                    // cells per bulk copy (4 KB)
+constexpr int kStages = 3;                          // ring slots per warp
+constexpr int kRingCells = kChunkCells * kStages;   // 768 cells = 12 KB per warp, 96 KB per CTA, 2 CTAs per SM
+constexpr size_t kFitSmem = (size_t)kFitWarps * kRingCells * sizeof(float4);
+constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
+constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
+static_assert(kSegHeaderCells + 32 * kSegViews <= kRingCells - kChunkCells, "a segment must fit in the ring next to one copy in flight");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -244,12 +155,12 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
     return d;
 }
 template <bool PRECISE>
-__device__ __forceinline__ u64 exp2_pair(u64 x) {  // PRECISE: x holds natural-log exponents, else base-2 exponents
+__device__ __forceinline__ u64 exp_pair(u64 x) {  // PRECISE: x holds natural-log exponents, else base-2 exponents
     return PRECISE ? pk(expf(lo(x)), expf(hi(x))) : pk(fast_exp2(lo(x)), fast_exp2(hi(x)));
 }
 
-// Per-pixel statistics, one packed accumulator per statistic and channel: the low half sums the records of
-// even blocks, the high half those of odd blocks (two source views are processed per step).
+// Per-pixel statistics, one packed accumulator per statistic and channel: the low half sums the lane's even
+// records, the high half its odd records (two records of the same pixel are processed per step).
 template <int MODE, bool PRECISE>
 struct PairStats {
     u64 S1[3], S2[3], S3[3], S4[3], S5[3], S6[3], S7[3], S8[3], S9[3];
@@ -259,7 +170,7 @@ struct PairStats {
         for (int c = 0; c < 3; ++c) S1[c] = S2[c] = S3[c] = S4[c] = S5[c] = S6[c] = S7[c] = S8[c] = S9[c] = 0ull;
     }
 
-    // rA / rB: the lane's record in the even / odd block; w = (1|0, 1|0) says which of the two exist
+    // rA / rB: two records of this lane's pixel; w = (1|0, 1|0) says which of the two exist
     __device__ __forceinline__ void add(const float4 rA, const float4 rB, u64 w, const u64 kb[3], const u64 kg[3],
                                         const u64 Bp[3], const u64 Bn[3], const u64 Jn[3]) {
         const u64 z = pk(rA.x, rB.x);
@@ -267,13 +178,15 @@ struct PairStats {
         const u64 one = pk(1.f, 1.f), neg1 = pk(-1.f, -1.f);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const u64 a = exp2_pair<PRECISE>(mul2(kb[c], z));   // e^{-beta z}
-            const u64 g = exp2_pair<PRECISE>(mul2(kg[c], z));   // e^{-gamma z}
+            const u64 a = exp_pair<PRECISE>(mul2(kb[c], z));    // e^{-beta z}
+            const u64 g = exp_pair<PRECISE>(mul2(kg[c], z));    // e^{-gamma z}
             const u64 D = fma2(Bp[c], g, add2(I[c], Bn[c]));    // I - B (1 - g)
             const u64 Dp = fma2(Jn[c], a, D);                   // shifted residual D - Jref a
             const u64 Dw = mul2(Dp, w);
             S1[c] = fma2(Dw, a, S1[c]);
-            if (MODE == kParamJ) {
+            if (MODE == kWriteJ) {
+                S2[c] = fma2(mul2(a, w), a, S2[c]);
+            } else if (MODE == kParamJ) {
                 const u64 h = fma2(g, neg1, one), za = mul2(z, a), zg = mul2(z, g);
                 S3[c] = fma2(Dw, h, S3[c]);
                 S5[c] = fma2(Dw, za, S5[c]);
@@ -297,6 +210,27 @@ struct PairStats {
 
 __device__ __forceinline__ float sum2(u64 v) { return lo(v) + hi(v); }
 
+struct FitArgs {
+    const float4* cells;
+    const long long* rec_off;
+    const long long* blk_off;
+    const long long* seg_off;
+    int n_tiles;
+    long long pixels;
+    float* params;         // 9: B, beta, gamma (read at start; written by the last CTA when do_step)
+    float* moments;        // 18: Adam state of the 9 scalars
+    float* J;              // pixels*3: Jref (closed form, in/out), the J parameter (in/out), or Jref (write-J, may be null)
+    float* J_out;          // pixels*3: write-J mode output
+    float* J_moments;      // pixels*6: per pixel {m[3], v[3]} (J parameter mode)
+    const int* partition;  // per global warp: first tile; [n_warps] = n_tiles
+    double* partials;      // gridDim.x rows of kSums
+    unsigned* ticket;
+    double* sums_out;      // if non-null the last CTA stores the reduced sums here
+    float* history_row;    // if non-null: params after the step + cost
+    int do_step;           // apply Adam to the 9 scalars in the last CTA
+    AdamScalars adam;
+};
+
 template <int MODE, bool PRECISE>
 __global__ void __launch_bounds__(kFitThreads, 2)
 fit_kernel(const __grid_constant__ FitArgs A) {
@@ -305,7 +239,8 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     const Coef q = load_coef(A.params);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
-    const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingRecs;
+    const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingCells;
+    const uint8_t* ring_bytes = reinterpret_cast<const uint8_t*>(ring);
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(bar_s + 8 * s, 1);
@@ -329,23 +264,33 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     for (int i = 0; i < kSums; ++i) acc[i] = 0.0;
 
     const int t_begin = A.partition[gw], t_end = A.partition[gw + 1];
-    const long long R0 = A.rec_off[t_begin], B0 = A.blk_off[t_begin];
-    const int n_rec = (int)(A.rec_off[t_end] - R0), n_blk = (int)(A.blk_off[t_end] - B0);
-    const int n_chunks = (n_rec + kChunkRecs - 1) / kChunkRecs;
-    const float4* src = A.records + R0;
+    const long long C0 = A.rec_off[t_begin] + kSegHeaderCells * A.seg_off[t_begin];
+    const int n_cells = (int)(A.rec_off[t_end] + kSegHeaderCells * A.seg_off[t_end] - C0);
+    const int n_chunks = (n_cells + kChunkCells - 1) / kChunkCells;
+    const float4* src = A.cells + C0;
 
     // ring bookkeeping, all warp-uniform
-    int next_issue = 0, issue_slot = 0;          // next chunk to copy and the slot it goes to
-    int wait_slot = 0;                           // slot of the next chunk to wait for
+    int next_issue = 0, issue_slot = 0;  // next chunk to copy and the slot it goes to
+    int wait_slot = 0;                   // slot of the next chunk to wait for
     uint32_t wait_parity = 0;
-    int avail = 0;                               // records that have landed
-    int free_at = kChunkRecs;                    // the oldest slot is recyclable once `rel` reaches this
-    int rel = 0, rpos = 0;                       // records consumed; same, modulo the ring size
+    int avail = 0;                       // cells that have landed
+    int free_at = kChunkCells;           // the oldest slot is recyclable once `pos` reaches this
+    int pos = 0, rpos = 0;               // cells consumed; same, modulo the ring size
     auto issue = [&]() {  // lane 0: arm the slot's barrier and start the copy of chunk `next_issue`
-        const int first = next_issue * kChunkRecs;
-        const uint32_t bytes = (uint32_t)min(kChunkRecs, n_rec - first) * (uint32_t)sizeof(float4);
+        const int first = next_issue * kChunkCells;
+        const uint32_t bytes = (uint32_t)min(kChunkCells, n_cells - first) * (uint32_t)sizeof(float4);
         mbar_expect_tx(bar_s + 8 * issue_slot, bytes);
-        bulk_load(ring_s + issue_slot * kChunkRecs * (uint32_t)sizeof(float4), src + first, bytes, bar_s + 8 * issue_slot);
+        bulk_load(ring_s + issue_slot * kChunkCells * (uint32_t)sizeof(float4), src + first, bytes, bar_s + 8 * issue_slot);
+    };
+    auto acquire = [&](int upto) {  // cells [0, upto) of the warp's stream have landed
+        while (upto > avail) {
+            mbar_wait(bar_s + 8 * wait_slot, wait_parity);
+            avail += kChunkCells;
+            if (++wait_slot == kStages) {
+                wait_slot = 0;
+                wait_parity ^= 1u;
+            }
+        }
     };
     for (int c = 0; c < min(kStages, n_chunks); ++c) {
         if (lane == 0) issue();
@@ -353,83 +298,88 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
     }
 
-    // block masks: lane j of `mcur` holds the mask of block 32*batch + j; `mnext` is the batch after it
-    const uint32_t* __restrict__ mk = A.blk_mask + B0;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t mcur = lane < n_blk ? __ldg(mk + lane) : 0u;
-    uint32_t mnext = 32 + lane < n_blk ? __ldg(mk + 32 + lane) : 0u;
-    int b = 0;  // block index within the warp's range
-
     long long p_next = (long long)t_begin * kTile + lane;
     float Jnext[3] = {0.f, 0.f, 0.f};
-    if (t_begin < t_end && p_next < A.pixels) {
+    if (A.J && t_begin < t_end && p_next < A.pixels) {
         Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
     }
-    int b_end_next = t_begin < t_end ? (int)(A.blk_off[t_begin + 1] - B0) : 0;
+    long long blk_next = t_begin < t_end ? A.blk_off[t_begin + 1] : 0;
+    long long blk_cur = t_begin < t_end ? A.blk_off[t_begin] : 0;
 
 #pragma unroll 1
     for (int tile = t_begin; tile < t_end; ++tile) {
-        const int b_end = b_end_next;
+        const int nb = (int)(blk_next - blk_cur);
         const long long p = p_next;
-        const float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
+        float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
+        blk_cur = blk_next;
         if (tile + 1 < t_end) {  // prefetch the next tile's extent and reference J
-            b_end_next = (int)(A.blk_off[tile + 2] - B0);
+            blk_next = A.blk_off[tile + 2];
             p_next = p + kTile;
-            if (p_next < A.pixels) {
+            if (A.J && p_next < A.pixels) {
                 Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
             }
         }
-        if (b_end == b) continue;  // warp-uniform
-        const u64 Jn[3] = {pk(-Jref[0], -Jref[0]), pk(-Jref[1], -Jref[1]), pk(-Jref[2], -Jref[2])};
+        if (MODE == kWriteJ) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Jref[c] = Jref[c] == Jref[c] ? Jref[c] : 0.f;  // a NaN reference is no reference
+        }
         PairStats<MODE, PRECISE> st;
         st.clear();
         int seen = 0;
+        if (nb > 0) {  // warp-uniform
+            const u64 Jn[3] = {pk(-Jref[0], -Jref[0]), pk(-Jref[1], -Jref[1]), pk(-Jref[2], -Jref[2])};
+            const int nseg = (nb + kSegViews - 1) / kSegViews;
 #pragma unroll 1
-        while (b < b_end) {
-            // two blocks (source views) per step, unless the pair would straddle a mask batch or the tile end
-            const int j = b & 31;
-            const bool two = j != 31 && b + 1 < b_end;
-            const uint32_t m0 = __shfl_sync(kFull, mcur, j);
-            const uint32_t m1x = __shfl_sync(kFull, mcur, (j + 1) & 31);
-            const uint32_t m1 = two ? m1x : 0u;
-            const int n0 = __popc(m0), n = n0 + __popc(m1);
-            while (rel + n > avail) {  // the records of this step must have landed
-                mbar_wait(bar_s + 8 * wait_slot, wait_parity);
-                avail += kChunkRecs;
-                if (++wait_slot == kStages) {
-                    wait_slot = 0;
-                    wait_parity ^= 1u;
+            for (int s = 0; s < nseg; ++s) {
+                acquire(pos + kSegHeaderCells);
+                int hcell = rpos + (lane >> 4);
+                hcell -= hcell >= kRingCells ? kRingCells : 0;
+                const int cnt = ring_bytes[hcell * 16 + (lane & 15)];  // records of this lane's pixel in the segment
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(kFull, incl, o);
+                    incl += lane >= o ? up : 0;
                 }
-            }
-            const uint32_t w0 = (m0 >> lane) & 1u, w1 = (m1 >> lane) & 1u;
-            if (w0 | w1) {
-                int i0 = rpos + (w0 ? __popc(m0 & lt) : 0);
-                int i1 = rpos + (w1 ? n0 + __popc(m1 & lt) : 0);
-                i0 -= i0 >= kRingRecs ? kRingRecs : 0;
-                i1 -= i1 >= kRingRecs ? kRingRecs : 0;
-                st.add(ring[i0], ring[i1], pk((float)w0, (float)w1), kb, kg, Bp, Bn, Jn);
-                seen += (int)(w0 + w1);
-            }
-            rel += n;
-            rpos += n;
-            rpos -= rpos >= kRingRecs ? kRingRecs : 0;
-            b += two ? 2 : 1;
-            if (rel >= free_at) {  // every lane is done with the oldest slot: refill it
-                __syncwarp();
-                if (next_issue < n_chunks) {
-                    if (lane == 0) issue();
-                    ++next_issue;
-                    issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
+                const int n = __shfl_sync(kFull, incl, 31);
+                const int maxc = (int)__reduce_max_sync(kFull, (unsigned)cnt);
+                acquire(pos + kSegHeaderCells + n);
+                int first = rpos + kSegHeaderCells + (incl - cnt);
+                first -= first >= kRingCells ? kRingCells : 0;
+#pragma unroll 1
+                for (int k = 0; k < maxc; k += 2) {
+                    const bool wA = k < cnt, wB = k + 1 < cnt;
+                    int iA = first + k, iB = first + k + 1;
+                    iA -= iA >= kRingCells ? kRingCells : 0;
+                    iB -= iB >= kRingCells ? kRingCells : 0;
+                    // a lane without a record here reads the (finite) header cell and weighs it by zero
+                    const float4 rA = ring[wA ? iA : rpos], rB = ring[wB ? iB : rpos];
+                    st.add(rA, rB, pk(wA ? 1.f : 0.f, wB ? 1.f : 0.f), kb, kg, Bp, Bn, Jn);
                 }
-                free_at += kChunkRecs;
-            }
-            if ((b & 31) < 2 && (b >> 5) != ((b - (two ? 2 : 1)) >> 5)) {  // crossed into the next mask batch
-                mcur = mnext;
-                const int nb2 = ((b >> 5) + 1) * 32 + lane;
-                mnext = nb2 < n_blk ? __ldg(mk + nb2) : 0u;
+                seen += cnt;
+                pos += kSegHeaderCells + n;
+                rpos += kSegHeaderCells + n;
+                rpos -= rpos >= kRingCells ? kRingCells : 0;
+                if (pos >= free_at) {  // every lane is done with the oldest slot(s): refill
+                    __syncwarp();
+                    while (pos >= free_at) {
+                        if (next_issue < n_chunks) {
+                            if (lane == 0) issue();
+                            ++next_issue;
+                            issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
+                        }
+                        free_at += kChunkCells;
+                    }
+                }
             }
         }
-        if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
+        if (MODE == kWriteJ) {
+            if (p < A.pixels) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    A.J_out[3 * p + c] = seen ? Jref[c] + sum2(st.S1[c]) / sum2(st.S2[c]) : __int_as_float(0x7fc00000);
+            }
+        } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
             float Jout[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -461,6 +411,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             A.J[3 * p + 2] = Jout[2];
         }
     }
+    if (MODE == kWriteJ) return;
 
     // warp tree -> one slot per warp -> one row per CTA
     __shared__ double sm[kFitWarps][kSums];
@@ -525,37 +476,6 @@ __global__ void adam_step_kernel(const double* __restrict__ sums, AdamScalars ad
     if (i == 9 && history_row) history_row[9] = (float)sums[9];
 }
 
-// Final update_J (sucre.py:156): J = Jref + sum(D' a) / sum(a^2) for observed pixels, NaN elsewhere (0/0, sucre.py:77)
-template <bool PRECISE>
-__global__ void __launch_bounds__(kFitThreads)
-write_J_kernel(const float4* __restrict__ records, const long long* __restrict__ rec_off,
-               const long long* __restrict__ blk_off, const uint32_t* __restrict__ blk_mask, int n_tiles,
-               long long pixels, const float* __restrict__ params, const float* __restrict__ Jref_in,
-               float* __restrict__ Jout) {
-    const Coef q = load_coef(params);
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * kFitWarps + (threadIdx.x >> 5);
-    if (tile >= n_tiles) return;
-    const long long p = (long long)tile * kTile + lane;
-    const long long b0 = blk_off[tile];
-    const int nb = (int)(blk_off[tile + 1] - b0);
-    float Jref[3] = {0.f, 0.f, 0.f};
-    if (Jref_in && p < pixels && nb > 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float j = Jref_in[3 * p + c];
-            Jref[c] = j == j ? j : 0.f;  // a NaN reference (never observed so far) is no reference
-        }
-    }
-    PixelStats<kWriteJ, PRECISE> st;
-    st.clear();
-    const int seen = nb > 0 ? sweep_tile(records, blk_mask, rec_off[tile], b0, nb, lane, q, Jref, st) : 0;
-    if (p < pixels) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Jout[3 * p + c] = seen ? Jref[c] + st.S1[c] / st.S2[c] : __int_as_float(0x7fc00000);
-    }
-}
-
 // first tile of every global warp: tiles are split so that every warp gets the same weight sum(blocks + 2)
 __global__ void partition_kernel(const long long* __restrict__ blk_off, int n_tiles, int n_warps, int* __restrict__ partition) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,16 +499,24 @@ static bool precise_exp() {
     return v == 1;
 }
 
+template <int MODE, bool PRECISE>
+static int occupancy() {
+    cudaFuncSetAttribute(fit_kernel<MODE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<MODE, PRECISE>, kFitThreads, kFitSmem) != cudaSuccess)
+        per_sm = 0;
+    return per_sm;
+}
+
+// persistent grid shared by every mode (the warp->tile partition is computed for it): resident CTAs of the
+// most register-hungry instantiation
 static int fit_grid() {
     static int ctas = 0;
     if (ctas == 0) {
-        int per_sm = 0;
-        cudaFuncSetAttribute(fit_kernel<kClosedForm, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
-        cudaFuncSetAttribute(fit_kernel<kClosedForm, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
-        cudaFuncSetAttribute(fit_kernel<kParamJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
-        cudaFuncSetAttribute(fit_kernel<kParamJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<kClosedForm, false>, kFitThreads, kFitSmem) != cudaSuccess || per_sm <= 0)
-            per_sm = 2;
+        int per_sm = min(min(occupancy<kClosedForm, false>(), occupancy<kClosedForm, true>()),
+                         min(min(occupancy<kParamJ, false>(), occupancy<kParamJ, true>()),
+                             min(occupancy<kWriteJ, false>(), occupancy<kWriteJ, true>())));
+        if (per_sm <= 0) per_sm = 1;
         ctas = min(kMaxFitCtas, num_sms() * per_sm);
     }
     return ctas;
@@ -600,23 +528,22 @@ static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st) {
     else fit_kernel<MODE, false><<<ctas, kFitThreads, kFitSmem, st>>>(a);
 }
 
-static int check_store(const float* records, const int64_t* rec_off, const int64_t* blk_off, const uint32_t* blk_mask,
-                       int n_tiles, const char* who) {
-    SUCRE_REQUIRE(records && rec_off && blk_off && blk_mask, "%s: null pointer", who);
-    SUCRE_REQUIRE(n_tiles > 0, "%s: n_tiles = %d", who, n_tiles);
-    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, "%s: records must be 16-byte aligned", who);
+static int check_store(const sucre_store* s, const char* who) {
+    SUCRE_REQUIRE(s != nullptr, "%s: null store", who);
+    SUCRE_REQUIRE(s->cells && s->rec_off && s->blk_off && s->seg_off, "%s: null pointer in store", who);
+    SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && s->pixels <= (int64_t)s->n_tiles * kTile, "%s: bad store sizes", who);
+    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(s->cells) & 15) == 0, "%s: cells must be 16-byte aligned", who);
     return 0;
 }
 
-static FitArgs base_args(const float* records, const int64_t* rec_off, const int64_t* blk_off, const uint32_t* blk_mask,
-                         int n_tiles, int64_t pixels, void* workspace) {
+static FitArgs base_args(const sucre_store* s, void* workspace) {
     FitArgs a{};
-    a.records = reinterpret_cast<const float4*>(records);
-    a.rec_off = (const long long*)rec_off;
-    a.blk_off = (const long long*)blk_off;
-    a.blk_mask = blk_mask;
-    a.n_tiles = n_tiles;
-    a.pixels = pixels;
+    a.cells = reinterpret_cast<const float4*>(s->cells);
+    a.rec_off = (const long long*)s->rec_off;
+    a.blk_off = (const long long*)s->blk_off;
+    a.seg_off = (const long long*)s->seg_off;
+    a.n_tiles = s->n_tiles;
+    a.pixels = s->pixels;
     char* ws = (char*)workspace;
     a.partials = (double*)(ws + kWsPartials);
     a.partition = (const int*)(ws + kWsPartition);
@@ -630,27 +557,26 @@ using namespace sucre;
 
 extern "C" size_t sucre_fit_workspace_bytes(void) { return kWsBytes; }
 
-extern "C" int sucre_fit_prepare(const int64_t* blk_off, int n_tiles, void* workspace, void* stream) {
+extern "C" int sucre_fit_prepare(const sucre_store* store_host, void* workspace, void* stream) {
     clear_error();
-    SUCRE_REQUIRE(blk_off && workspace && n_tiles > 0, "sucre_fit_prepare: bad arguments");
-    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sucre_fit_prepare: workspace must be 16-byte aligned");
+    if (check_store(store_host, "sucre_fit_prepare")) return 1;
+    SUCRE_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sucre_fit_prepare: workspace must be non-null, 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_warps = fit_grid() * kFitWarps;
     char* ws = (char*)workspace;
     SUCRE_CUDA(cudaMemsetAsync(ws + kWsTicket, 0, 16, st));
-    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)blk_off, n_tiles, n_warps, (int*)(ws + kWsPartition));
+    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)store_host->blk_off, store_host->n_tiles, n_warps,
+                                                                 (int*)(ws + kWsPartition));
     return check_launch("partition_kernel");
 }
 
-extern "C" int sucre_fit_sums(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                              const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params, float* J,
-                              float* J_moments, int64_t n_obs, int t, double lr, double* sums, void* workspace,
-                              void* stream) {
+extern "C" int sucre_fit_sums(int mode, const sucre_store* store_host, const float* params, float* J, float* J_moments,
+                              int64_t n_obs, int t, double lr, double* sums, void* workspace, void* stream) {
     clear_error();
-    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit_sums")) return 1;
+    if (check_store(store_host, "sucre_fit_sums")) return 1;
     SUCRE_REQUIRE(params && J && sums && workspace, "sucre_fit_sums: null pointer");
     SUCRE_REQUIRE(mode == kClosedForm || (mode == kParamJ && J_moments && n_obs > 0 && t >= 1), "sucre_fit_sums: bad mode/arguments");
-    FitArgs a = base_args(records, rec_off, blk_off, blk_mask, n_tiles, target_pixels, workspace);
+    FitArgs a = base_args(store_host, workspace);
     a.params = const_cast<float*>(params);
     a.J = J;
     a.J_moments = J_moments;
@@ -671,16 +597,15 @@ extern "C" int sucre_adam_step(float* params, float* adam_state, const double* s
     return check_launch("adam_step_kernel");
 }
 
-extern "C" int sucre_fit(int mode, const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                         const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, int64_t n_obs, float* params,
-                         float* adam_state, float* J, float* J_moments, int first_step, int num_iter, double lr,
-                         float* history, void* workspace, void* stream) {
+extern "C" int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
+                         float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
+                         void* stream) {
     clear_error();
-    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit")) return 1;
+    if (check_store(store_host, "sucre_fit")) return 1;
     SUCRE_REQUIRE(params && adam_state && J && workspace, "sucre_fit: null pointer");
     SUCRE_REQUIRE(mode == kClosedForm || (mode == kParamJ && J_moments), "sucre_fit: bad mode %d", mode);
     SUCRE_REQUIRE(n_obs > 0 && first_step >= 1 && num_iter >= 0, "sucre_fit: bad n_obs/first_step/num_iter");
-    FitArgs a = base_args(records, rec_off, blk_off, blk_mask, n_tiles, target_pixels, workspace);
+    FitArgs a = base_args(store_host, workspace);
     a.params = params;
     a.moments = adam_state;
     a.J = J;
@@ -696,18 +621,15 @@ extern "C" int sucre_fit(int mode, const float* records, const int64_t* rec_off,
     return check_launch("sucre_fit kernels");
 }
 
-extern "C" int sucre_fit_write_J(const float* records, const int64_t* rec_off, const int64_t* blk_off,
-                                 const uint32_t* blk_mask, int n_tiles, int64_t target_pixels, const float* params,
-                                 const float* J_ref, float* J, void* stream) {
+extern "C" int sucre_fit_write_J(const sucre_store* store_host, const float* params, const float* J_ref, float* J,
+                                 void* workspace, void* stream) {
     clear_error();
-    if (check_store(records, rec_off, blk_off, blk_mask, n_tiles, "sucre_fit_write_J")) return 1;
-    SUCRE_REQUIRE(params && J && target_pixels > 0, "sucre_fit_write_J: bad arguments");
-    const int grid = (n_tiles + kFitWarps - 1) / kFitWarps;
-    if (precise_exp())
-        write_J_kernel<true><<<grid, kFitThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(records), (const long long*)rec_off,
-                                                                             (const long long*)blk_off, blk_mask, n_tiles, target_pixels, params, J_ref, J);
-    else
-        write_J_kernel<false><<<grid, kFitThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(records), (const long long*)rec_off,
-                                                                              (const long long*)blk_off, blk_mask, n_tiles, target_pixels, params, J_ref, J);
-    return check_launch("write_J_kernel");
+    if (check_store(store_host, "sucre_fit_write_J")) return 1;
+    SUCRE_REQUIRE(params && J && workspace, "sucre_fit_write_J: null pointer");
+    FitArgs a = base_args(store_host, workspace);
+    a.params = const_cast<float*>(params);
+    a.J = const_cast<float*>(J_ref);
+    a.J_out = J;
+    launch_fit<kWriteJ>(a, fit_grid(), (cudaStream_t)stream);
+    return check_launch("fit_kernel<write J>");
 }

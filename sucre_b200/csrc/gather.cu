@@ -57,6 +57,8 @@ __device__ __forceinline__ bool project(const float* Ri, const float* ti, const 
 }
 
 constexpr int kViewWords = sizeof(sucre_view) / 4;  // 48
+constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;      // blocks (source views) per segment of the observation store
+constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
 constexpr int kChunk = 32;                          // source views per CTA: lane j keeps the mask of view j
 constexpr int kWarps = 8;
 
@@ -149,10 +151,10 @@ __global__ void kept_kernel(const long long* __restrict__ view_count, int n_view
     if (v < n_views) view_kept[v] = ((double)view_count[v] / pixels > min_cover) ? 1 : 0;
 }
 
-// records and non-empty blocks per tile over kept views: one warp per tile
+// records, non-empty blocks and segments per tile over kept views: one warp per tile
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept, int n_tiles, int n_views,
-                  long long* __restrict__ rec_cnt, long long* __restrict__ blk_cnt) {
+                  long long* __restrict__ rec_cnt, long long* __restrict__ blk_cnt, long long* __restrict__ seg_cnt) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
@@ -169,57 +171,71 @@ tile_count_kernel(const uint32_t* __restrict__ masks, const uint8_t* __restrict_
     if (lane == 0) {
         rec_cnt[tile] = rec;
         blk_cnt[tile] = blk;
+        seg_cnt[tile] = (blk + kSegViews - 1) / kSegViews;
     }
 }
 
-// in-place exclusive scan of two count arrays (n entries -> n+1 offsets), one CTA
+// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA
 __global__ void __launch_bounds__(1024)
-scan_kernel(long long* __restrict__ a, long long* __restrict__ b, int n, long long* __restrict__ totals) {
-    __shared__ long long sa[1024], sb[1024];
+scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __restrict__ c, int n,
+            long long* __restrict__ totals) {
+    __shared__ long long sa[1024], sb[1024], sc[1024];
     const int t = threadIdx.x;
     const int chunk = (n + 1023) / 1024;
     const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
-    long long la = 0, lb = 0;
+    long long la = 0, lb = 0, lc = 0;
     for (int i = lo; i < hi; ++i) {
         la += a[i];
         lb += b[i];
+        lc += c[i];
     }
     sa[t] = la;
     sb[t] = lb;
+    sc[t] = lc;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
-        const long long xa = t >= off ? sa[t - off] : 0, xb = t >= off ? sb[t - off] : 0;
+        const long long xa = t >= off ? sa[t - off] : 0, xb = t >= off ? sb[t - off] : 0, xc = t >= off ? sc[t - off] : 0;
         __syncthreads();
         sa[t] += xa;
         sb[t] += xb;
+        sc[t] += xc;
         __syncthreads();
     }
-    long long pa = sa[t] - la, pb = sb[t] - lb;
+    long long pa = sa[t] - la, pb = sb[t] - lb, pc = sc[t] - lc;
     for (int i = lo; i < hi; ++i) {
-        const long long ca = a[i], cb = b[i];
+        const long long ca = a[i], cb = b[i], cc = c[i];
         a[i] = pa;
         b[i] = pb;
+        c[i] = pc;
         pa += ca;
         pb += cb;
+        pc += cc;
     }
     if (t == 1023) {
         a[n] = sa[t];
         b[n] = sb[t];
+        c[n] = sc[t];
         totals[0] = sa[t];
         totals[1] = sb[t];
+        totals[2] = sc[t];
     }
 }
 
 // ---- sample ----------------------------------------------------------------------------------------------
+// One warp per tile.  Phase A compacts the tile's non-empty kept blocks (lane mask + view index) into
+// blk_mask / blk_view.  Phase B walks them in segments of kSegViews blocks: per-lane record counts -> header
+// cells, exclusive scan over lanes -> each lane's first cell, then every matched (pixel, view) is re-projected,
+// its source depth + colour fetched, and the record stored in the lane's run (lane-major within the segment).
 __global__ void __launch_bounds__(256)
 gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                      const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
-                     const long long* __restrict__ rec_off, const long long* __restrict__ blk_off, int first_tile, int n_tiles,
-                     float4* __restrict__ records, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
-                     uint32_t* __restrict__ rec_src) {
+                     const long long* __restrict__ rec_off, const long long* __restrict__ blk_off,
+                     const long long* __restrict__ seg_off, int first_tile, int n_tiles, float4* __restrict__ cells,
+                     uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view, uint32_t* __restrict__ cell_src) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
+    const uint32_t lt = (1u << lane) - 1u;
     const int P = T.width * T.height;
     const int p = (first_tile + tile) * kTile + lane;
     float w0, w1, w2;
@@ -230,21 +246,47 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
         unproject(T.Kinv, u1, v1, d1, c0, c1, c2);
         rigid(T.R, T.t, c0, c1, c2, w0, w1, w2);
     }
-    long long rec = rec_off[tile], blk = blk_off[tile];
+    // phase A
+    const long long blk0 = blk_off[tile];
+    int nb = 0;
     for (int base = 0; base < n_views; base += 32) {
         const int view = base + lane;
         uint32_t m = 0;
         if (view < n_views && view_kept[view]) m = __ldg(masks + (size_t)tile * n_views + view);
-        unsigned nz = __ballot_sync(kFull, m != 0);
-        while (nz) {
-            const int j = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t bm = __shfl_sync(kFull, m, j);
-            const int s = base + j;
-            if (lane == 0) {
-                blk_mask[blk] = bm;
-                blk_view[blk] = s;
-            }
+        const unsigned nz = __ballot_sync(kFull, m != 0);
+        if (m != 0) {
+            const long long at = blk0 + nb + __popc(nz & lt);
+            blk_mask[at] = m;
+            blk_view[at] = view;
+        }
+        nb += __popc(nz);
+    }
+    __syncwarp();
+    // phase B
+    long long cell = rec_off[tile] + kSegHeaderCells * seg_off[tile];
+    for (int s0 = 0; s0 < nb; s0 += kSegViews) {
+        const int ns = min(kSegViews, nb - s0);
+        uint32_t bm_l = 0;
+        int bv_l = 0;
+        if (lane < ns) {
+            bm_l = __ldcg(blk_mask + blk0 + s0 + lane);
+            bv_l = __ldcg(blk_view + blk0 + s0 + lane);
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kSegViews; ++j) cnt += (__shfl_sync(kFull, bm_l, j) >> lane) & 1u;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const int n = __shfl_sync(kFull, incl, 31);
+        reinterpret_cast<uint8_t*>(cells + cell)[lane] = (uint8_t)cnt;  // header: 32 lane counts
+        long long at = cell + kSegHeaderCells + (incl - cnt);
+        for (int j = 0; j < ns; ++j) {
+            const uint32_t bm = __shfl_sync(kFull, bm_l, j);
+            const int s = __shfl_sync(kFull, bv_l, j);
             if ((bm >> lane) & 1u) {
                 const sucre_view* S = views + s;  // warp-uniform addresses: broadcast loads
                 float Ri[9], ti[3], K[9], Kinv[9];
@@ -271,13 +313,12 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
                 const float I0 = __fdiv_rn((float)__ldg(px + 0), 255.0f);       // loader.py:157, 87
                 const float I1 = __fdiv_rn((float)__ldg(px + 1), 255.0f);
                 const float I2 = __fdiv_rn((float)__ldg(px + 2), 255.0f);
-                const long long at = rec + __popc(bm & ((1u << lane) - 1u));
-                records[at] = make_float4(z, I0, I1, I2);
-                if (rec_src) rec_src[at] = (uint32_t)u2 | ((uint32_t)v2 << 16);
+                cells[at] = make_float4(z, I0, I1, I2);
+                if (cell_src) cell_src[at] = (uint32_t)u2 | ((uint32_t)v2 << 16);
+                ++at;
             }
-            rec += __popc(bm);
-            ++blk;
         }
+        cell += kSegHeaderCells + n;
     }
 }
 
@@ -328,29 +369,30 @@ extern "C" int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_view
 
 extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
                                  int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off,
-                                 int64_t* blk_off, int64_t* totals, void* stream) {
+                                 int64_t* blk_off, int64_t* seg_off, int64_t* totals, void* stream) {
     clear_error();
-    SUCRE_REQUIRE(masks && view_count && view_kept && rec_off && blk_off && totals, "sucre_gather_plan: null pointer");
+    SUCRE_REQUIRE(masks && view_count && view_kept && rec_off && blk_off && seg_off && totals, "sucre_gather_plan: null pointer");
     SUCRE_REQUIRE(n_tiles > 0 && n_views > 0 && target_pixels > 0, "sucre_gather_plan: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
     kept_kernel<<<(n_views + 127) / 128, 128, 0, st>>>((const long long*)view_count, n_views, (double)target_pixels, min_cover, view_kept);
-    tile_count_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(masks, view_kept, n_tiles, n_views, (long long*)rec_off, (long long*)blk_off);
-    scan_kernel<<<1, 1024, 0, st>>>((long long*)rec_off, (long long*)blk_off, n_tiles, (long long*)totals);
+    tile_count_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(masks, view_kept, n_tiles, n_views, (long long*)rec_off, (long long*)blk_off,
+                                                         (long long*)seg_off);
+    scan_kernel<<<1, 1024, 0, st>>>((long long*)rec_off, (long long*)blk_off, (long long*)seg_off, n_tiles, (long long*)totals);
     return check_launch("sucre_gather_plan kernels");
 }
 
 extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
                                    int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                                   const int64_t* blk_off, float* records, uint32_t* blk_mask, int32_t* blk_view,
-                                   uint32_t* rec_src, void* stream) {
+                                   const int64_t* blk_off, const int64_t* seg_off, float* cells, uint32_t* blk_mask,
+                                   int32_t* blk_view, uint32_t* cell_src, void* stream) {
     clear_error();
     if (check_view_host(target_host, "sucre_gather_sample(target)")) return 1;
-    SUCRE_REQUIRE(views && masks && view_kept && rec_off && blk_off && records && blk_mask && blk_view,
+    SUCRE_REQUIRE(views && masks && view_kept && rec_off && blk_off && seg_off && cells && blk_mask && blk_view,
                   "sucre_gather_sample: null pointer");
     if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_sample")) return 1;
-    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, "sucre_gather_sample: records must be 16-byte aligned");
+    SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(cells) & 15) == 0, "sucre_gather_sample: cells must be 16-byte aligned");
     gather_sample_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        *target_host, views, n_views, masks, view_kept, (const long long*)rec_off, (const long long*)blk_off, first_tile, n_tiles,
-        reinterpret_cast<float4*>(records), blk_mask, blk_view, rec_src);
+        *target_host, views, n_views, masks, view_kept, (const long long*)rec_off, (const long long*)blk_off,
+        (const long long*)seg_off, first_tile, n_tiles, reinterpret_cast<float4*>(cells), blk_mask, blk_view, cell_src);
     return check_launch("gather_sample_kernel");
 }

@@ -5,6 +5,7 @@ libsucre_b200.so reached through ctypes (sucre_b200/_lib.py).  There is no CPU f
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -97,21 +98,23 @@ class DeviceScene:
 # ------------------------------------------------------------------------------------------------------------
 @dataclass
 class ObservationStore:
-    """Tile-major compact observation stream (layout: include/sucre_b200.h).  Replaces the reference's HDF5
+    """Tile-major segmented observation stream (layout: include/sucre_b200.h).  Replaces the reference's HDF5
     spill file + MatchesData (loader.py:36-130)."""
     width: int
     height: int
     source_keys: tuple
-    view_count: np.ndarray        # (V,) int64 matches per listed view (host)
+    view_count: np.ndarray        # (V,) int64 matches per listed view over the WHOLE image (host)
     view_kept: np.ndarray         # (V,) bool  min_cover decision (host)
-    n_obs: int
+    n_obs: int                    # records in this store
     n_blocks: int
-    records: torch.Tensor         # (N,4) f32 {z, I_r, I_g, I_b}
+    n_segments: int
+    cells: torch.Tensor           # (n_obs + 2*n_segments, 4) f32: per segment 2 header cells + records {z, I_r, I_g, I_b}
     rec_off: torch.Tensor         # (n_tiles+1,) int64
     blk_off: torch.Tensor         # (n_tiles+1,) int64
+    seg_off: torch.Tensor         # (n_tiles+1,) int64
     blk_mask: torch.Tensor        # (n_blocks,) int32 (bit pattern of the uint32 lane mask)
     blk_view: torch.Tensor        # (n_blocks,) int32 index into source_keys
-    rec_src: torch.Tensor | None  # (N,) int32 u2 | v2 << 16
+    cell_src: torch.Tensor | None  # (n_cells,) int32 u2 | v2 << 16 at record cells
     workspace: torch.Tensor | None = None  # fit scratch, prepared on first use
     first_tile: int = 0           # band of the target this store covers (multi-GPU pixel sharding): tiles
     n_tiles: int = 0              # [first_tile, first_tile + n_tiles); 0 = the whole target (set in __post_init__)
@@ -141,33 +144,56 @@ class ObservationStore:
     def __len__(self) -> int:
         return self.n_obs
 
-    def per_record_index(self) -> tuple[torch.Tensor, torch.Tensor]:
-        """(pixel, view) of every record, in store order (device int64 tensors)."""
-        dev = self.records.device
-        nblk_tile = (self.blk_off[1:] - self.blk_off[:-1])
+    def c_struct(self) -> _lib.SucreStore:
+        return _lib.SucreStore(self.cells.data_ptr(), self.rec_off.data_ptr(), self.blk_off.data_ptr(),
+                               self.seg_off.data_ptr(), self.n_tiles, 0, self.local_pixels)
+
+    def record_index(self) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(cell, pixel, view) of every record (device int64 tensors, block-major order): decodes the segment
+        structure from the block masks.  For export / parity checks, not used by the kernels."""
+        dev = self.cells.device
+        G, HC = _lib.SEG_VIEWS, _lib.SEG_HEADER_CELLS
+        nblk_tile = self.blk_off[1:] - self.blk_off[:-1]
         blk_tile = torch.repeat_interleave(torch.arange(self.n_tiles, device=dev), nblk_tile)
+        j = torch.arange(self.n_blocks, device=dev) - self.blk_off[blk_tile]
+        seg = self.seg_off[blk_tile] + j // G                                   # segment of every block
         lanes = torch.arange(32, device=dev, dtype=torch.int64)
-        bits = ((self.blk_mask.to(torch.int64)[:, None] >> lanes[None, :]) & 1).bool()
-        blk, lane = bits.nonzero(as_tuple=True)
-        return (blk_tile[blk] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[blk]
+        bits = (self.blk_mask.to(torch.int64)[:, None] >> lanes[None, :]) & 1      # (n_blocks, 32)
+        excl = torch.cumsum(bits, dim=0) - bits                                   # records of the lane before block b
+        seg_first_blk = torch.zeros(self.n_segments, dtype=torch.int64, device=dev)
+        is_first = (j % G) == 0
+        seg_first_blk[seg[is_first]] = torch.nonzero(is_first, as_tuple=True)[0]
+        k = excl - excl[seg_first_blk[seg]]                                        # rank within the lane's run
+        cnt = torch.zeros((self.n_segments, 32), dtype=torch.int64, device=dev).index_add_(0, seg, bits)
+        lane_base = torch.cumsum(cnt, dim=1) - cnt
+        n_seg = cnt.sum(dim=1)
+        seg_cell = HC * torch.arange(self.n_segments, device=dev) + torch.cumsum(n_seg, 0) - n_seg
+        cell = seg_cell[seg][:, None] + HC + lane_base[seg] + k
+        b, lane = torch.nonzero(bits, as_tuple=True)
+        return cell[b, lane], (blk_tile[b] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[b]
+
+    def records(self) -> torch.Tensor:
+        """(n_obs, 4) the record cells (headers stripped)."""
+        return self.cells[self.record_index()[0]]
 
     def to_reference_layout(self) -> dict:
         """Per kept view (in source_keys order) the arrays the reference's MatchesFile/MatchesData hold
         (loader.py:68-76, 103-118): u1, v1, u2, v2 int16, z f32, I (3,n) f32 — rows ordered row-major over
         the target like torch.where (sfm.py:96).  Host numpy; meant for parity tests and --keep-matches."""
-        pixel, view = self.per_record_index()
+        cell, pixel, view = self.record_index()
         out = {}
         for vi, key in enumerate(self.source_keys):
             if not self.view_kept[vi]:
                 continue
             sel = (view == vi).nonzero(as_tuple=True)[0]
+            sel = sel[torch.argsort(pixel[sel])]
             p = pixel[sel]
-            rec = self.records[sel].cpu().numpy()
+            rec = self.cells[cell[sel]].cpu().numpy()
             entry = dict(u1=(p % self.width).to(torch.int16).cpu().numpy(),
                          v1=(p // self.width).to(torch.int16).cpu().numpy(),
                          z=rec[:, 0].copy(), I=np.ascontiguousarray(rec[:, 1:4].T))
-            if self.rec_src is not None:
-                src = self.rec_src[sel].cpu().numpy().view(np.uint32)
+            if self.cell_src is not None:
+                src = self.cell_src[cell[sel]].cpu().numpy().view(np.uint32)
                 entry['u2'] = (src & 0xffff).astype(np.int16)
                 entry['v2'] = (src >> 16).astype(np.int16)
             out[key] = entry
@@ -206,7 +232,8 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
         view_kept = torch.empty(V, dtype=torch.uint8, device=dev)
         rec_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
         blk_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
-        totals = torch.empty(2, dtype=torch.int64, device=dev)
+        seg_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
+        totals = torch.empty(3, dtype=torch.int64, device=dev)
         tptr = trec.ctypes.data
         _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(), st),
                    'sucre_gather_match')
@@ -215,26 +242,28 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
             reduce_counts(view_count)
         _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), P, float(min_cover),
                                        view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
-                                       totals.data_ptr(), st), 'sucre_gather_plan')
-        n_obs, n_blocks = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
-        records = torch.empty((max(n_obs, 1), 4), dtype=torch.float32, device=dev)
+                                       seg_off.data_ptr(), totals.data_ptr(), st), 'sucre_gather_plan')
+        n_obs, n_blocks, n_segments = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
+        n_cells = n_obs + _lib.SEG_HEADER_CELLS * n_segments
+        cells = torch.empty((max(n_cells, 1), 4), dtype=torch.float32, device=dev)
         blk_mask = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
         blk_view = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
-        rec_src = torch.empty(max(n_obs, 1), dtype=torch.int32, device=dev) if keep_src else None
+        cell_src = torch.empty(max(n_cells, 1), dtype=torch.int32, device=dev) if keep_src else None
         if n_obs > 0:
             missing = [k for k in source_keys if k not in scene.rgb]
             if missing:
                 raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
             _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
                                              view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
-                                             records.data_ptr(), blk_mask.data_ptr(), blk_view.data_ptr(),
-                                             0 if rec_src is None else rec_src.data_ptr(), st), 'sucre_gather_sample')
+                                             seg_off.data_ptr(), cells.data_ptr(), blk_mask.data_ptr(),
+                                             blk_view.data_ptr(), 0 if cell_src is None else cell_src.data_ptr(), st),
+                       'sucre_gather_sample')
         vc = view_count.cpu().numpy()
         vk = view_kept.cpu().numpy().astype(bool)
     return ObservationStore(width=W, height=H, source_keys=source_keys, view_count=vc, view_kept=vk, n_obs=n_obs,
-                            n_blocks=n_blocks, records=records[:n_obs], rec_off=rec_off, blk_off=blk_off,
-                            blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
-                            rec_src=None if rec_src is None else rec_src[:n_obs], first_tile=first_tile,
+                            n_blocks=n_blocks, n_segments=n_segments, cells=cells[:n_cells], rec_off=rec_off,
+                            blk_off=blk_off, seg_off=seg_off, blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
+                            cell_src=None if cell_src is None else cell_src[:n_cells], first_tile=first_tile,
                             n_tiles=n_tiles)
 
 
@@ -268,24 +297,20 @@ class FitState:
 
     def ensure_J(self, store: 'ObservationStore'):
         if self.J is None:
-            self.J = torch.zeros(store.J_shape, dtype=torch.float32, device=store.records.device)
+            self.J = torch.zeros(store.J_shape, dtype=torch.float32, device=store.cells.device)
         assert tuple(self.J.shape) == store.J_shape and self.J.is_contiguous()
 
 
 def _workspace(store: ObservationStore) -> torch.Tensor:
     """Per-store scratch buffer, partitioned for the fit on first use."""
     if store.workspace is None:
-        dev = store.records.device
+        dev = store.cells.device
         store.workspace = torch.empty(_lib.lib().sucre_fit_workspace_bytes(), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().sucre_fit_prepare(store.blk_off.data_ptr(), store.n_tiles, store.workspace.data_ptr(),
-                                                    _stream(dev)), 'sucre_fit_prepare')
+            cs = store.c_struct()
+            _lib.check(_lib.lib().sucre_fit_prepare(C.byref(cs), store.workspace.data_ptr(), _stream(dev)),
+                       'sucre_fit_prepare')
     return store.workspace
-
-
-def _store_ptrs(store: ObservationStore):
-    return (store.records.data_ptr(), store.rec_off.data_ptr(), store.blk_off.data_ptr(), store.blk_mask.data_ptr(),
-            store.n_tiles, store.local_pixels)
 
 
 def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05) -> torch.Tensor:
@@ -293,12 +318,13 @@ def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.0
     for.  Returns the (num_iter, 10) history tensor {params after each step, cost before it} (device)."""
     if store.n_obs == 0:
         raise _lib.SucreError('fit: the observation store is empty')
-    dev = store.records.device
+    dev = store.cells.device
     state.ensure_J(store)
     history = torch.empty((num_iter, 10), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
+        cs = store.c_struct()
         _lib.check(_lib.lib().sucre_fit(
-            state.mode, *_store_ptrs(store), store.n_obs, state.params.data_ptr(), state.moments.data_ptr(),
+            state.mode, C.byref(cs), store.n_obs, state.params.data_ptr(), state.moments.data_ptr(),
             state.J.data_ptr(), 0 if state.J_moments is None else state.J_moments.data_ptr(), state.step + 1, num_iter,
             float(lr), history.data_ptr(), _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit')
     state.step += num_iter
@@ -312,11 +338,12 @@ def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs
              lr: float = 0.05):
     """One objective evaluation at state.params -> sums (10 doubles, device); in J-parameter mode J takes its
     Adam step state.step+1.  Building block of the multi-GPU loop (all-reduce sums, then adam_step)."""
-    dev = store.records.device
+    dev = store.cells.device
     state.ensure_J(store)
     with torch.cuda.device(dev):
+        cs = store.c_struct()
         _lib.check(_lib.lib().sucre_fit_sums(
-            state.mode, *_store_ptrs(store), state.params.data_ptr(), state.J.data_ptr(),
+            state.mode, C.byref(cs), state.params.data_ptr(), state.J.data_ptr(),
             0 if state.J_moments is None else state.J_moments.data_ptr(),
             store.n_obs if n_obs_global is None else n_obs_global, state.step + 1, float(lr), sums.data_ptr(),
             _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit_sums')
@@ -333,12 +360,13 @@ def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, histor
 
 def closed_form_J(store: ObservationStore, params: torch.Tensor, J_ref: torch.Tensor | None = None) -> torch.Tensor:
     """update_J (sucre.py:66-77) with the given parameters: (H,W,3) f32 on the device, NaN where unobserved."""
-    dev = store.records.device
+    dev = store.cells.device
     J = torch.empty(store.J_shape, dtype=torch.float32, device=dev)
     if store.n_obs == 0:
         return J.fill_(float('nan'))
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().sucre_fit_write_J(*_store_ptrs(store), params.data_ptr(),
-                                                0 if J_ref is None else J_ref.data_ptr(), J.data_ptr(), _stream(dev)),
+        cs = store.c_struct()
+        _lib.check(_lib.lib().sucre_fit_write_J(C.byref(cs), params.data_ptr(), 0 if J_ref is None else J_ref.data_ptr(),
+                                                J.data_ptr(), _workspace(store).data_ptr(), _stream(dev)),
                    'sucre_fit_write_J')
     return J

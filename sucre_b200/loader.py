@@ -126,11 +126,12 @@ class MatchesFile:
         s = self.store
         if s.n_obs == 0:
             return
-        rec = s.records
+        rec = s.records()
         assert not bool(torch.isnan(rec).any()), f'In {self.path}, observations contain NaN(s).'
         assert bool((rec[:, 1:] >= 0).all()), f'In {self.path}, observations contain invalid colour value(s).'
         assert bool((rec[:, 0] > 0).all()), f'In {self.path}, observations contain null or negative range(s).'
-        assert int(s.rec_off[-1]) == s.n_obs and int(s.blk_off[-1]) == s.n_blocks, f'In {self.path}, corrupt offsets.'
+        assert int(s.rec_off[-1]) == s.n_obs and int(s.blk_off[-1]) == s.n_blocks and \
+            int(s.seg_off[-1]) == s.n_segments, f'In {self.path}, corrupt offsets.'
 
     def load_matches(self, pin_memory: bool = False, device=None) -> MatchesData:
         self._ensure_loaded(device)
@@ -150,9 +151,10 @@ class MatchesFile:
         s = self.store
         np.savez(self.cache_path, width=s.width, height=s.height, names=np.array(self.names),
                  source_keys=np.array(s.source_keys), view_count=s.view_count, view_kept=s.view_kept,
-                 records=s.records.cpu().numpy(), rec_off=s.rec_off.cpu().numpy(), blk_off=s.blk_off.cpu().numpy(),
-                 blk_mask=s.blk_mask.cpu().numpy(), blk_view=s.blk_view.cpu().numpy(),
-                 rec_src=np.zeros(0, np.int32) if s.rec_src is None else s.rec_src.cpu().numpy())
+                 n_obs=s.n_obs, cells=s.cells.cpu().numpy(), rec_off=s.rec_off.cpu().numpy(),
+                 blk_off=s.blk_off.cpu().numpy(), seg_off=s.seg_off.cpu().numpy(), blk_mask=s.blk_mask.cpu().numpy(),
+                 blk_view=s.blk_view.cpu().numpy(),
+                 cell_src=np.zeros(0, np.int32) if s.cell_src is None else s.cell_src.cpu().numpy())
         self.path.touch()  # the reference's file name marks "matches exist" (sucre.py:185)
 
     def unlink(self):
@@ -170,7 +172,7 @@ class MatchesFile:
         self.names = z['names'].tolist()
         self.store = ObservationStore(
             width=int(z['width']), height=int(z['height']), source_keys=tuple(z['source_keys'].tolist()),
-            view_count=z['view_count'], view_kept=z['view_kept'], n_obs=int(z['records'].shape[0]),
-            n_blocks=int(z['blk_mask'].shape[0]), records=t(z['records']), rec_off=t(z['rec_off']),
-            blk_off=t(z['blk_off']), blk_mask=t(z['blk_mask']), blk_view=t(z['blk_view']),
-            rec_src=t(z['rec_src']) if z['rec_src'].size else None)
+            view_count=z['view_count'], view_kept=z['view_kept'], n_obs=int(z['n_obs']),
+            n_blocks=int(z['blk_mask'].shape[0]), n_segments=int(z['seg_off'][-1]), cells=t(z['cells']),
+            rec_off=t(z['rec_off']), blk_off=t(z['blk_off']), seg_off=t(z['seg_off']), blk_mask=t(z['blk_mask']),
+            blk_view=t(z['blk_view']), cell_src=t(z['cell_src']) if z['cell_src'].size else None)

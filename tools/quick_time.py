@@ -41,12 +41,12 @@ masks = torch.empty((nt, V), dtype=torch.int32, device='cuda')
 mn, av, _ = timed(lambda: L.sucre_gather_match(trec.ctypes.data, table.data_ptr(), V, 0, nt, masks.data_ptr(), st))
 print(f'  match kernel: min {mn:.3f} ms avg {av:.3f}')
 vc = torch.empty(V, dtype=torch.int64, device='cuda'); vk = torch.empty(V, dtype=torch.uint8, device='cuda')
-ro = torch.empty(nt + 1, dtype=torch.int64, device='cuda'); bo = torch.empty(nt + 1, dtype=torch.int64, device='cuda'); tot = torch.empty(2, dtype=torch.int64, device='cuda')
-mn, av, _ = timed(lambda: (L.sucre_gather_count(masks.data_ptr(), nt, V, vc.data_ptr(), st), L.sucre_gather_plan(masks.data_ptr(), nt, V, vc.data_ptr(), W * H, 1e-6, vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), tot.data_ptr(), st)))
+ro, bo, so = (torch.empty(nt + 1, dtype=torch.int64, device='cuda') for _ in range(3)); tot = torch.empty(3, dtype=torch.int64, device='cuda')
+mn, av, _ = timed(lambda: (L.sucre_gather_count(masks.data_ptr(), nt, V, vc.data_ptr(), st), L.sucre_gather_plan(masks.data_ptr(), nt, V, vc.data_ptr(), W * H, 1e-6, vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), so.data_ptr(), tot.data_ptr(), st)))
 print(f'  plan kernels: min {mn:.3f} ms avg {av:.3f}')
-rec = torch.empty((store.n_obs, 4), device='cuda'); bm = torch.empty(store.n_blocks, dtype=torch.int32, device='cuda'); bv = torch.empty_like(bm)
-mn, av, _ = timed(lambda: L.sucre_gather_sample(trec.ctypes.data, table.data_ptr(), V, 0, nt, masks.data_ptr(), vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), rec.data_ptr(), bm.data_ptr(), bv.data_ptr(), 0, st))
-print(f'  sample kernel: min {mn:.3f} ms avg {av:.3f}  ({store.n_obs*16/mn/1e6:.0f} GB/s of records)')
+cells = torch.empty_like(store.cells); bm = torch.empty(store.n_blocks, dtype=torch.int32, device='cuda'); bv = torch.empty_like(bm)
+mn, av, _ = timed(lambda: L.sucre_gather_sample(trec.ctypes.data, table.data_ptr(), V, 0, nt, masks.data_ptr(), vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), so.data_ptr(), cells.data_ptr(), bm.data_ptr(), bv.data_ptr(), 0, st))
+print(f'  sample kernel: min {mn:.3f} ms avg {av:.3f}  ({store.n_obs*16/mn/1e6:.0f} GB/s of records; {store.n_segments} segments)')
 
 def fit():
     s = engine.FitState.initial('cuda')
