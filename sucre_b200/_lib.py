@@ -11,7 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
 ABI_VERSION = 2
 TILE = 32
-SEG_VIEWS, SEG_HEADER_CELLS = 8, 2
+SEG_VIEWS, SEG_HEADER_CELLS = 9, 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
 
 # numpy mirror of `struct sucre_view` (192 bytes)

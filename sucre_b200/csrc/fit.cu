@@ -94,9 +94,12 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 // range through a private shared-memory ring with cp.async.bulk (TMA 1-D copies of 4 KB, kStages slots, one
 // mbarrier per slot): HBM latency is covered by the copies in flight instead of by occupancy, and the arithmetic
 // reads 16-byte records from shared memory.
-constexpr int kChunkCells = 256;                    // cells per bulk copy (4 KB)
-constexpr int kStages = 3;                          // ring slots per warp
-constexpr int kRingCells = kChunkCells * kStages;   // 768 cells = 12 KB per warp, 96 KB per CTA, 2 CTAs per SM
+#ifndef SUCRE_FIT_CTAS
+#define SUCRE_FIT_CTAS 2                            // resident CTAs per SM the kernel is shaped for
+#endif
+constexpr int kChunkCells = SUCRE_FIT_CTAS >= 3 ? 128 : 256;  // cells per bulk copy (2 or 4 KB)
+constexpr int kStages = SUCRE_FIT_CTAS >= 3 ? 4 : 3;          // ring slots per warp
+constexpr int kRingCells = kChunkCells * kStages;   // 8 KB (12 KB) per warp, 64 KB (96 KB) per CTA with 3 (2) CTAs per SM
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingCells * sizeof(float4);
 constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
 constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
@@ -159,56 +162,46 @@ __device__ __forceinline__ u64 exp_pair(u64 x) {  // PRECISE: x holds natural-lo
     return PRECISE ? pk(expf(lo(x)), expf(hi(x))) : pk(fast_exp2(lo(x)), fast_exp2(hi(x)));
 }
 
-// Per-pixel statistics, one packed accumulator per statistic and channel: the low half sums the lane's even
-// records, the high half its odd records (two records of the same pixel are processed per step).
+// Per-pixel statistics of one channel, two per packed accumulator so that one FFMA2 updates both:
+//   S12 = (sum D'a, sum a^2)   S34 = (sum D'h, sum a h)   S56 = (sum D'za, sum a za)   S78 = (sum D'zg, sum a zg)
+//   S9  = sum D'^2             (a = e^{-beta z}, g = e^{-gamma z}, h = 1 - g, D' the shifted residual)
 template <int MODE, bool PRECISE>
-struct PairStats {
-    u64 S1[3], S2[3], S3[3], S4[3], S5[3], S6[3], S7[3], S8[3], S9[3];
+struct PixelStats {
+    u64 S12[3], S34[3], S56[3], S78[3];
+    float S9[3];
 
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) S1[c] = S2[c] = S3[c] = S4[c] = S5[c] = S6[c] = S7[c] = S8[c] = S9[c] = 0ull;
+        for (int c = 0; c < 3; ++c) {
+            S12[c] = S34[c] = S56[c] = S78[c] = 0ull;
+            S9[c] = 0.f;
+        }
     }
 
-    // rA / rB: two records of this lane's pixel; w = (1|0, 1|0) says which of the two exist
-    __device__ __forceinline__ void add(const float4 rA, const float4 rB, u64 w, const u64 kb[3], const u64 kg[3],
-                                        const u64 Bp[3], const u64 Bn[3], const u64 Jn[3]) {
-        const u64 z = pk(rA.x, rB.x);
-        const u64 I[3] = {pk(rA.y, rB.y), pk(rA.z, rB.z), pk(rA.w, rB.w)};
-        const u64 one = pk(1.f, 1.f), neg1 = pk(-1.f, -1.f);
+    // kbg[c] = (kb, kg) exponent scales, Bc / nJ = B and -Jref of the channel
+    __device__ __forceinline__ void add(const float4 r, const u64 kbg[3], const float Bc[3], const float nJ[3]) {
+        const float z = r.x;
+        const float I[3] = {r.y, r.z, r.w};
+        const u64 zz = pk(z, z);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const u64 a = exp_pair<PRECISE>(mul2(kb[c], z));    // e^{-beta z}
-            const u64 g = exp_pair<PRECISE>(mul2(kg[c], z));    // e^{-gamma z}
-            const u64 D = fma2(Bp[c], g, add2(I[c], Bn[c]));    // I - B (1 - g)
-            const u64 Dp = fma2(Jn[c], a, D);                   // shifted residual D - Jref a
-            const u64 Dw = mul2(Dp, w);
-            S1[c] = fma2(Dw, a, S1[c]);
-            if (MODE == kWriteJ) {
-                S2[c] = fma2(mul2(a, w), a, S2[c]);
-            } else if (MODE == kParamJ) {
-                const u64 h = fma2(g, neg1, one), za = mul2(z, a), zg = mul2(z, g);
-                S3[c] = fma2(Dw, h, S3[c]);
-                S5[c] = fma2(Dw, za, S5[c]);
-                S7[c] = fma2(Dw, zg, S7[c]);
-                S9[c] = fma2(Dw, Dp, S9[c]);
-            } else {
-                const u64 aw = mul2(a, w);
-                S2[c] = fma2(aw, a, S2[c]);
-                const u64 h = fma2(g, neg1, one), za = mul2(z, a), zg = mul2(z, g);
-                S3[c] = fma2(Dw, h, S3[c]);
-                S4[c] = fma2(aw, h, S4[c]);
-                S5[c] = fma2(Dw, za, S5[c]);
-                S6[c] = fma2(aw, za, S6[c]);
-                S7[c] = fma2(Dw, zg, S7[c]);
-                S8[c] = fma2(aw, zg, S8[c]);
-                S9[c] = fma2(Dw, Dp, S9[c]);
-            }
+            const u64 e = mul2(kbg[c], zz);
+            const float a = PRECISE ? expf(lo(e)) : fast_exp2(lo(e));   // e^{-beta z}
+            const float g = PRECISE ? expf(hi(e)) : fast_exp2(hi(e));   // e^{-gamma z}
+            const float D = fmaf(Bc[c], g, I[c] - Bc[c]);               // I - B (1 - g)
+            const float Dp = fmaf(nJ[c], a, D);                         // shifted residual D - Jref a
+            const u64 Da = pk(Dp, a);
+            S12[c] = fma2(Da, pk(a, a), S12[c]);
+            if (MODE == kWriteJ) continue;
+            const float h = 1.0f - g;
+            const u64 zag = mul2(zz, pk(a, g));                         // (z a, z g)
+            S34[c] = fma2(Da, pk(h, h), S34[c]);
+            S56[c] = fma2(Da, pk(lo(zag), lo(zag)), S56[c]);
+            S78[c] = fma2(Da, pk(hi(zag), hi(zag)), S78[c]);
+            S9[c] = fmaf(Dp, Dp, S9[c]);
         }
     }
 };
-
-__device__ __forceinline__ float sum2(u64 v) { return lo(v) + hi(v); }
 
 struct FitArgs {
     const float4* cells;
@@ -232,7 +225,7 @@ struct FitArgs {
 };
 
 template <int MODE, bool PRECISE>
-__global__ void __launch_bounds__(kFitThreads, 2)
+__global__ void __launch_bounds__(kFitThreads, SUCRE_FIT_CTAS)
 fit_kernel(const __grid_constant__ FitArgs A) {
     extern __shared__ __align__(128) unsigned char fit_smem[];
     __shared__ __align__(8) unsigned long long bars[kFitWarps][kStages];
@@ -249,15 +242,10 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     }
     __syncwarp();
 
-    // packed per-channel constants: exponent scales, +B, -B
-    u64 kb[3], kg[3], Bp[3], Bn[3];
+    // per-channel exponent scales packed (beta, gamma): one FMUL2 forms both exponents of a record
+    u64 kbg[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        kb[c] = PRECISE ? pk(-q.beta[c], -q.beta[c]) : pk(q.kb[c], q.kb[c]);
-        kg[c] = PRECISE ? pk(-q.gamma[c], -q.gamma[c]) : pk(q.kg[c], q.kg[c]);
-        Bp[c] = pk(q.B[c], q.B[c]);
-        Bn[c] = pk(-q.B[c], -q.B[c]);
-    }
+    for (int c = 0; c < 3; ++c) kbg[c] = PRECISE ? pk(-q.beta[c], -q.gamma[c]) : pk(q.kb[c], q.kg[c]);
 
     double acc[kSums];
 #pragma unroll
@@ -323,11 +311,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) Jref[c] = Jref[c] == Jref[c] ? Jref[c] : 0.f;  // a NaN reference is no reference
         }
-        PairStats<MODE, PRECISE> st;
+        PixelStats<MODE, PRECISE> st;
         st.clear();
         int seen = 0;
         if (nb > 0) {  // warp-uniform
-            const u64 Jn[3] = {pk(-Jref[0], -Jref[0]), pk(-Jref[1], -Jref[1]), pk(-Jref[2], -Jref[2])};
+            const float nJ[3] = {-Jref[0], -Jref[1], -Jref[2]};
             const int nseg = (nb + kSegViews - 1) / kSegViews;
 #pragma unroll 1
             for (int s = 0; s < nseg; ++s) {
@@ -342,20 +330,21 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                     incl += lane >= o ? up : 0;
                 }
                 const int n = __shfl_sync(kFull, incl, 31);
-                const int maxc = (int)__reduce_max_sync(kFull, (unsigned)cnt);
                 acquire(pos + kSegHeaderCells + n);
                 int first = rpos + kSegHeaderCells + (incl - cnt);
                 first -= first >= kRingCells ? kRingCells : 0;
+                // every lane walks its own run (divergent trip count); the next record is loaded while the
+                // current one is being accumulated
+                float4 rec = ring[cnt ? first : rpos];
 #pragma unroll 1
-                for (int k = 0; k < maxc; k += 2) {
-                    const bool wA = k < cnt, wB = k + 1 < cnt;
-                    int iA = first + k, iB = first + k + 1;
-                    iA -= iA >= kRingCells ? kRingCells : 0;
-                    iB -= iB >= kRingCells ? kRingCells : 0;
-                    // a lane without a record here reads the (finite) header cell and weighs it by zero
-                    const float4 rA = ring[wA ? iA : rpos], rB = ring[wB ? iB : rpos];
-                    st.add(rA, rB, pk(wA ? 1.f : 0.f, wB ? 1.f : 0.f), kb, kg, Bp, Bn, Jn);
+                for (int k = 1; k <= cnt; ++k) {
+                    int i = first + k;
+                    i -= i >= kRingCells ? kRingCells : 0;
+                    const float4 nxt = ring[k < cnt ? i : rpos];
+                    st.add(rec, kbg, q.B, nJ);
+                    rec = nxt;
                 }
+                __syncwarp();
                 seen += cnt;
                 pos += kSegHeaderCells + n;
                 rpos += kSegHeaderCells + n;
@@ -377,19 +366,19 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             if (p < A.pixels) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    A.J_out[3 * p + c] = seen ? Jref[c] + sum2(st.S1[c]) / sum2(st.S2[c]) : __int_as_float(0x7fc00000);
+                    A.J_out[3 * p + c] = seen ? Jref[c] + lo(st.S12[c]) / hi(st.S12[c]) : __int_as_float(0x7fc00000);
             }
         } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
             float Jout[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float S1 = sum2(st.S1[c]), S3 = sum2(st.S3[c]), S5 = sum2(st.S5[c]), S7 = sum2(st.S7[c]), S9 = sum2(st.S9[c]);
+                const float S1 = lo(st.S12[c]), S3 = lo(st.S34[c]), S5 = lo(st.S56[c]), S7 = lo(st.S78[c]), S9 = st.S9[c];
                 float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
                 if (MODE == kClosedForm) {
-                    delta = S1 / sum2(st.S2[c]);
-                    rh = fmaf(-delta, sum2(st.S4[c]), S3);
-                    rza = fmaf(-delta, sum2(st.S6[c]), S5);
-                    rzg = fmaf(-delta, sum2(st.S8[c]), S7);
+                    delta = S1 / hi(st.S12[c]);
+                    rh = fmaf(-delta, hi(st.S34[c]), S3);
+                    rza = fmaf(-delta, hi(st.S56[c]), S5);
+                    rzg = fmaf(-delta, hi(st.S78[c]), S7);
                     rr = fmaf(-delta, S1, S9);
                 }
                 Jout[c] = Jref[c] + delta;
