@@ -18,9 +18,9 @@
  * Observation store produced by the gather and consumed by the fit ("tile-major segmented stream"):
  *   `cells` is an array of 16-byte cells.  For tile k the kept source views with at least one match in the tile
  *   ("blocks", in pairing-list order; lane mask blk_mask[b], view index blk_view[b], b in blk_off[k]..blk_off[k+1])
- *   are grouped SUCRE_SEGMENT_VIEWS (9) at a time into segments (an odd run length keeps the lanes' 16-byte
+ *   are grouped SUCRE_SEGMENT_VIEWS (15) at a time into segments (an odd run length keeps the lanes' 16-byte
  *   shared-memory reads on distinct banks).  A segment is SUCRE_SEGMENT_HEADER_CELLS (2)
- *   header cells — 32 bytes, byte i = number of records of lane i's pixel in the segment (0..9) — followed by the
+ *   header cells — 32 bytes, byte i = number of records of lane i's pixel in the segment (0..15) — followed by the
  *   records LANE-MAJOR: lane 0's records (in view order), then lane 1's, ...  One record = float4
  *   {z, I_r, I_g, I_b}: z = ||cP|| the range of the observation in the source camera frame (loader.py:113 +
  *   sucre.py:53), I = source colour / 255 (loader.py:157, 87).  The first cell of tile k is
@@ -39,7 +39,9 @@ extern "C" {
 
 #define SUCRE_ABI_VERSION 2
 #define SUCRE_TILE_PIXELS 32
-#define SUCRE_SEGMENT_VIEWS 9
+#ifndef SUCRE_SEGMENT_VIEWS
+#define SUCRE_SEGMENT_VIEWS 15
+#endif
 #define SUCRE_SEGMENT_HEADER_CELLS 2
 
 /* One view (source or target).  All matrices row-major fp32, computed on the host with the reference's own
@@ -71,6 +73,7 @@ typedef struct sucre_store {
 } sucre_store;
 
 int sucre_abi_version(void);
+int sucre_segment_views(void); /* SUCRE_SEGMENT_VIEWS the library was built with */
 const char* sucre_last_error(void);
 
 /* ---- stage 1: multi-view correspondence gather ---------------------------------------------------------

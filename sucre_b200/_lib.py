@@ -11,7 +11,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
 ABI_VERSION = 2
 TILE = 32
-SEG_VIEWS, SEG_HEADER_CELLS = 9, 2
+SEG_HEADER_CELLS = 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
 
 # numpy mirror of `struct sucre_view` (192 bytes)
@@ -38,6 +38,7 @@ _lib = None
 _VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGNATURES = {
     'sucre_abi_version': (C.c_int, []),
+    'sucre_segment_views': (C.c_int, []),
     'sucre_last_error': (C.c_char_p, []),
     'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
@@ -67,6 +68,11 @@ def lib() -> C.CDLL:
             raise SucreError(f'ABI mismatch: library {L.sucre_abi_version()}, python {ABI_VERSION}')
         _lib = L
     return _lib
+
+
+def seg_views() -> int:
+    """Source views per segment of the observation store (SUCRE_SEGMENT_VIEWS of the loaded library)."""
+    return lib().sucre_segment_views()
 
 
 def check(rc: int, what: str):

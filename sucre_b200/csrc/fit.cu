@@ -102,6 +102,14 @@ constexpr int kStages = SUCRE_FIT_CTAS >= 3 ? 4 : 3;          // ring slots per 
 constexpr int kRingCells = kChunkCells * kStages;   // 8 KB (12 KB) per warp, 64 KB (96 KB) per CTA with 3 (2) CTAs per SM
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingCells * sizeof(float4);
 constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
+#ifndef SUCRE_FIT_ILP
+#define SUCRE_FIT_ILP 2
+#endif
+#ifndef SUCRE_FIT_OVERSUB
+#define SUCRE_FIT_OVERSUB 1
+#endif
+constexpr int kOversub = SUCRE_FIT_OVERSUB;           // CTAs launched per resident CTA slot (finer static partition)
+constexpr int kIlp = SUCRE_FIT_ILP;                   // records of one lane in flight per step
 constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
 static_assert(kSegHeaderCells + 32 * kSegViews <= kRingCells - kChunkCells, "a segment must fit in the ring next to one copy in flight");
 
@@ -333,16 +341,25 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                 acquire(pos + kSegHeaderCells + n);
                 int first = rpos + kSegHeaderCells + (incl - cnt);
                 first -= first >= kRingCells ? kRingCells : 0;
-                // every lane walks its own run (divergent trip count); the next record is loaded while the
-                // current one is being accumulated
-                float4 rec = ring[cnt ? first : rpos];
+                // every lane walks its own run (divergent trip count), two records per step for instruction-level
+                // parallelism (their exp / residual chains are independent until the accumulators)
+                {
+                    auto cell_at = [&](int k) {
+                        int i = first + k;
+                        i -= i >= kRingCells ? kRingCells : 0;
+                        return i;
+                    };
+                    int k = 0;
 #pragma unroll 1
-                for (int k = 1; k <= cnt; ++k) {
-                    int i = first + k;
-                    i -= i >= kRingCells ? kRingCells : 0;
-                    const float4 nxt = ring[k < cnt ? i : rpos];
-                    st.add(rec, kbg, q.B, nJ);
-                    rec = nxt;
+                    for (; k + kIlp <= cnt; k += kIlp) {
+                        float4 r[kIlp];
+#pragma unroll
+                        for (int u = 0; u < kIlp; ++u) r[u] = ring[cell_at(k + u)];
+#pragma unroll
+                        for (int u = 0; u < kIlp; ++u) st.add(r[u], kbg, q.B, nJ);
+                    }
+#pragma unroll 1
+                    for (; k < cnt; ++k) st.add(ring[cell_at(k)], kbg, q.B, nJ);
                 }
                 __syncwarp();
                 seen += cnt;
@@ -465,16 +482,23 @@ __global__ void adam_step_kernel(const double* __restrict__ sums, AdamScalars ad
     if (i == 9 && history_row) history_row[9] = (float)sums[9];
 }
 
-// first tile of every global warp: tiles are split so that every warp gets the same weight sum(blocks + 2)
-__global__ void partition_kernel(const long long* __restrict__ blk_off, int n_tiles, int n_warps, int* __restrict__ partition) {
+// first tile of every global warp: tiles are split so that every warp gets the same estimated cost.  Cost model
+// (instructions, from the ncu source view): ~55 per block (one record step of the slowest lane), ~110 per segment
+// (header, scan, ring bookkeeping), ~250 per tile (finalisation, J load/store, double accumulation).
+__device__ __forceinline__ long long cost_prefix(const long long* __restrict__ blk_off, const long long* __restrict__ seg_off, int t) {
+    return 4 * blk_off[t] + 8 * seg_off[t] + 18LL * t;
+}
+
+__global__ void partition_kernel(const long long* __restrict__ blk_off, const long long* __restrict__ seg_off, int n_tiles,
+                                 int n_warps, int* __restrict__ partition) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > n_warps) return;
-    const long long total = blk_off[n_tiles] + 2LL * n_tiles;
+    const long long total = cost_prefix(blk_off, seg_off, n_tiles);
     const long long target = (total * w + n_warps - 1) / n_warps;
-    int lo = 0, hi = n_tiles;  // smallest t with weight_prefix(t) >= target
+    int lo = 0, hi = n_tiles;  // smallest t with cost_prefix(t) >= target
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (blk_off[mid] + 2LL * mid >= target) hi = mid; else lo = mid + 1;
+        if (cost_prefix(blk_off, seg_off, mid) >= target) hi = mid; else lo = mid + 1;
     }
     partition[w] = w == n_warps ? n_tiles : lo;
 }
@@ -506,7 +530,7 @@ static int fit_grid() {
                          min(min(occupancy<kParamJ, false>(), occupancy<kParamJ, true>()),
                              min(occupancy<kWriteJ, false>(), occupancy<kWriteJ, true>())));
         if (per_sm <= 0) per_sm = 1;
-        ctas = min(kMaxFitCtas, num_sms() * per_sm);
+        ctas = min(kMaxFitCtas, num_sms() * per_sm * kOversub);
     }
     return ctas;
 }
@@ -554,8 +578,8 @@ extern "C" int sucre_fit_prepare(const sucre_store* store_host, void* workspace,
     const int n_warps = fit_grid() * kFitWarps;
     char* ws = (char*)workspace;
     SUCRE_CUDA(cudaMemsetAsync(ws + kWsTicket, 0, 16, st));
-    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)store_host->blk_off, store_host->n_tiles, n_warps,
-                                                                 (int*)(ws + kWsPartition));
+    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)store_host->blk_off, (const long long*)store_host->seg_off,
+                                                                 store_host->n_tiles, n_warps, (int*)(ws + kWsPartition));
     return check_launch("partition_kernel");
 }
 

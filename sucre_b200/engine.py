@@ -152,7 +152,7 @@ class ObservationStore:
         """(cell, pixel, view) of every record (device int64 tensors, block-major order): decodes the segment
         structure from the block masks.  For export / parity checks, not used by the kernels."""
         dev = self.cells.device
-        G, HC = _lib.SEG_VIEWS, _lib.SEG_HEADER_CELLS
+        G, HC = _lib.seg_views(), _lib.SEG_HEADER_CELLS
         nblk_tile = self.blk_off[1:] - self.blk_off[:-1]
         blk_tile = torch.repeat_interleave(torch.arange(self.n_tiles, device=dev), nblk_tile)
         j = torch.arange(self.n_blocks, device=dev) - self.blk_off[blk_tile]
