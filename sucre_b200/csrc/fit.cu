@@ -237,7 +237,10 @@ __global__ void __launch_bounds__(kFitThreads, SUCRE_FIT_CTAS)
 fit_kernel(const __grid_constant__ FitArgs A) {
     extern __shared__ __align__(128) unsigned char fit_smem[];
     __shared__ __align__(8) unsigned long long bars[kFitWarps][kStages];
-    const Coef q = load_coef(A.params);
+    // Programmatic dependent launch: let the next iteration's kernel be scheduled as soon as SM resources free up;
+    // everything up to griddepcontrol.wait below touches only data that no iteration writes (offsets, partition,
+    // cells), so this prologue overlaps the previous iteration's tail.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
     const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingCells;
@@ -249,11 +252,6 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-
-    // per-channel exponent scales packed (beta, gamma): one FMUL2 forms both exponents of a record
-    u64 kbg[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) kbg[c] = PRECISE ? pk(-q.beta[c], -q.gamma[c]) : pk(q.kb[c], q.kg[c]);
 
     double acc[kSums];
 #pragma unroll
@@ -293,6 +291,14 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         ++next_issue;
         issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
     }
+
+    // the previous iteration (parameters, J, ticket) must be complete and visible from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const Coef q = load_coef(A.params);
+    // per-channel exponent scales packed (beta, gamma): one FMUL2 forms both exponents of a record
+    u64 kbg[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) kbg[c] = PRECISE ? pk(-q.beta[c], -q.gamma[c]) : pk(q.kb[c], q.kg[c]);
 
     long long p_next = (long long)t_begin * kTile + lane;
     float Jnext[3] = {0.f, 0.f, 0.f};
@@ -535,10 +541,23 @@ static int fit_grid() {
     return ctas;
 }
 
+// pdl = true: programmatic dependent launch — only when the preceding kernel in the stream is another fit_kernel of
+// the same loop, because the prologue before griddepcontrol.wait reads cells / offsets / partition, which must not
+// have been written by the kernel just before (gather_sample, partition_kernel).
 template <int MODE>
-static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st) {
-    if (precise_exp()) fit_kernel<MODE, true><<<ctas, kFitThreads, kFitSmem, st>>>(a);
-    else fit_kernel<MODE, false><<<ctas, kFitThreads, kFitSmem, st>>>(a);
+static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st, bool pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kFitThreads);
+    cfg.dynamicSmemBytes = kFitSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // pairs with griddepcontrol.* in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (precise_exp()) cudaLaunchKernelEx(&cfg, fit_kernel<MODE, true>, a);
+    else cudaLaunchKernelEx(&cfg, fit_kernel<MODE, false>, a);
 }
 
 static int check_store(const sucre_store* s, const char* who) {
@@ -596,8 +615,8 @@ extern "C" int sucre_fit_sums(int mode, const sucre_store* store_host, const flo
     a.sums_out = sums;
     a.do_step = 0;
     if (mode == kParamJ) a.adam = adam_scalars(t, lr, n_obs);
-    if (mode == kClosedForm) launch_fit<kClosedForm>(a, fit_grid(), (cudaStream_t)stream);
-    else launch_fit<kParamJ>(a, fit_grid(), (cudaStream_t)stream);
+    if (mode == kClosedForm) launch_fit<kClosedForm>(a, fit_grid(), (cudaStream_t)stream, false);
+    else launch_fit<kParamJ>(a, fit_grid(), (cudaStream_t)stream, false);
     return check_launch("fit_kernel");
 }
 
@@ -628,8 +647,8 @@ extern "C" int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs,
     for (int it = 0; it < num_iter; ++it) {
         a.adam = adam_scalars(first_step + it, lr, n_obs);
         a.history_row = history ? history + (size_t)it * kSums : nullptr;
-        if (mode == kClosedForm) launch_fit<kClosedForm>(a, ctas, (cudaStream_t)stream);
-        else launch_fit<kParamJ>(a, ctas, (cudaStream_t)stream);
+        if (mode == kClosedForm) launch_fit<kClosedForm>(a, ctas, (cudaStream_t)stream, it > 0);
+        else launch_fit<kParamJ>(a, ctas, (cudaStream_t)stream, it > 0);
     }
     return check_launch("sucre_fit kernels");
 }
@@ -643,6 +662,6 @@ extern "C" int sucre_fit_write_J(const sucre_store* store_host, const float* par
     a.params = const_cast<float*>(params);
     a.J = const_cast<float*>(J_ref);
     a.J_out = J;
-    launch_fit<kWriteJ>(a, fit_grid(), (cudaStream_t)stream);
+    launch_fit<kWriteJ>(a, fit_grid(), (cudaStream_t)stream, false);
     return check_launch("fit_kernel<write J>");
 }
