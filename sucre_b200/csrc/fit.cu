@@ -27,7 +27,10 @@
 
 namespace sucre {
 
-constexpr int kFitThreads = 256;
+#ifndef SUCRE_FIT_THREADS
+#define SUCRE_FIT_THREADS 256
+#endif
+constexpr int kFitThreads = SUCRE_FIT_THREADS;
 constexpr int kFitWarps = kFitThreads / 32;
 constexpr int kMaxFitCtas = 2048;
 constexpr int kSums = 10;
@@ -97,8 +100,14 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 #ifndef SUCRE_FIT_CTAS
 #define SUCRE_FIT_CTAS 2                            // resident CTAs per SM the kernel is shaped for
 #endif
-constexpr int kChunkCells = SUCRE_FIT_CTAS >= 3 ? 128 : 256;  // cells per bulk copy (2 or 4 KB)
-constexpr int kStages = SUCRE_FIT_CTAS >= 3 ? 4 : 3;          // ring slots per warp
+#ifndef SUCRE_FIT_CHUNK
+#define SUCRE_FIT_CHUNK (SUCRE_FIT_CTAS >= 3 ? 128 : 256)
+#endif
+constexpr int kChunkCells = SUCRE_FIT_CHUNK;                 // cells per bulk copy (2 or 4 KB)
+#ifndef SUCRE_FIT_STAGES
+#define SUCRE_FIT_STAGES (SUCRE_FIT_CTAS >= 3 ? 4 : 3)
+#endif
+constexpr int kStages = SUCRE_FIT_STAGES;                    // ring slots per warp
 constexpr int kRingCells = kChunkCells * kStages;   // 8 KB (12 KB) per warp, 64 KB (96 KB) per CTA with 3 (2) CTAs per SM
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingCells * sizeof(float4);
 constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;

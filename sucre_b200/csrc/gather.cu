@@ -175,49 +175,55 @@ tile_count_kernel(const uint32_t* __restrict__ masks, const uint8_t* __restrict_
     }
 }
 
-// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA
+// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA: rounds of 1024 coalesced
+// elements, warp-shuffle scans, running carries
 __global__ void __launch_bounds__(1024)
 scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __restrict__ c, int n,
             long long* __restrict__ totals) {
-    __shared__ long long sa[1024], sb[1024], sc[1024];
-    const int t = threadIdx.x;
-    const int chunk = (n + 1023) / 1024;
-    const int lo = min(n, t * chunk), hi = min(n, lo + chunk);
-    long long la = 0, lb = 0, lc = 0;
-    for (int i = lo; i < hi; ++i) {
-        la += a[i];
-        lb += b[i];
-        lc += c[i];
-    }
-    sa[t] = la;
-    sb[t] = lb;
-    sc[t] = lc;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const long long xa = t >= off ? sa[t - off] : 0, xb = t >= off ? sb[t - off] : 0, xc = t >= off ? sc[t - off] : 0;
+    __shared__ long long wsum[3][32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    long long carry[3] = {0, 0, 0};
+    long long* arr[3] = {a, b, c};
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + t;
+        long long v[3], incl[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = i < n ? arr[k][i] : 0;
+            incl[k] = v[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(kFull, incl[k], o);
+                if (lane >= o) incl[k] += up;
+            }
+            if (lane == 31) wsum[k][warp] = incl[k];
+        }
         __syncthreads();
-        sa[t] += xa;
-        sb[t] += xb;
-        sc[t] += xc;
+        if (warp < 3) {  // warp k scans the 32 warp totals of array k
+            long long w = wsum[warp][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(kFull, w, o);
+                if (lane >= o) w += up;
+            }
+            wsum[warp][lane] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const long long before = carry[k] + (warp ? wsum[k][warp - 1] : 0);
+            if (i < n) arr[k][i] = before + incl[k] - v[k];
+            carry[k] += wsum[k][31];
+        }
         __syncthreads();
     }
-    long long pa = sa[t] - la, pb = sb[t] - lb, pc = sc[t] - lc;
-    for (int i = lo; i < hi; ++i) {
-        const long long ca = a[i], cb = b[i], cc = c[i];
-        a[i] = pa;
-        b[i] = pb;
-        c[i] = pc;
-        pa += ca;
-        pb += cb;
-        pc += cc;
-    }
-    if (t == 1023) {
-        a[n] = sa[t];
-        b[n] = sb[t];
-        c[n] = sc[t];
-        totals[0] = sa[t];
-        totals[1] = sb[t];
-        totals[2] = sc[t];
+    if (t == 0) {
+        a[n] = carry[0];
+        b[n] = carry[1];
+        c[n] = carry[2];
+        totals[0] = carry[0];
+        totals[1] = carry[1];
+        totals[2] = carry[2];
     }
 }
 
