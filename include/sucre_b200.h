@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 2
+#define SUCRE_ABI_VERSION 3
 #define SUCRE_TILE_PIXELS 32
 #ifndef SUCRE_SEGMENT_VIEWS
 #define SUCRE_SEGMENT_VIEWS 15
@@ -51,13 +51,20 @@ extern "C" {
  *   R, t  cam->world Pose                 sfm.py:219-222 (inverse of COLMAP's cam_from_world)
  *   Ri,ti Pose.inverse(): R.T, -R.T @ t   sfm.py:47
  * depth: u16 millimetres, height*width (loader.py:167 divides by 1000 -> metres; done in-kernel, IEEE).
- * rgb:   u8 RGB interleaved, height*width*3 (loader.py:157 divides by 255; done in-kernel, IEEE).
- * sizeof == 192, 16-byte aligned. */
+ * rgb:   rgb_format SUCRE_RGB_U8:  u8 RGB interleaved, height*width*3 (loader.py:157 divides by 255; done in-kernel,
+ *                                      IEEE) — images used at their stored size;
+ *        rgb_format SUCRE_RGB_F32: float RGB interleaved in [0,1], height*width*3 — images the host resampled with
+ *                                      --image-scale (loader.py:158-162 resamples in float, which leaves the u8 grid).
+ * sizeof == 208, 16-byte aligned. */
+#define SUCRE_RGB_U8 0
+#define SUCRE_RGB_F32 1
 typedef struct sucre_view {
     float K[9], Kinv[9], R[9], t[3], Ri[9], ti[3];
     int32_t width, height;
     const uint16_t* depth;
-    const uint8_t* rgb;
+    const void* rgb;
+    int32_t rgb_format;
+    int32_t reserved[3];
 } sucre_view;
 
 /* The observation store of one target (or of a band of its tiles), as the fit reads it.  A host struct of

@@ -44,7 +44,7 @@ GOLDEN = ROOT / 'tests' / 'golden'
 
 
 def run_reference(scene: SyntheticScene, target: str, *, closed_form: bool, num_iter: int, min_cover: float,
-                  batch_size: int, filter_names=()):
+                  batch_size: int, filter_names=(), image_scale: float = 1.0):
     """Runs reference restore_image on CPU; returns dict of captured arrays."""
     log_lines = []
     history = []
@@ -69,7 +69,8 @@ def run_reference(scene: SyntheticScene, target: str, *, closed_form: bool, num_
         ref_sucre.tqdm.write = staticmethod(write)
         torch.optim.Adam.step = step
         try:
-            model = ref_sfm.COLMAPModel(model_dir=dirs['model'], image_dir=dirs['images'], depth_dir=dirs['depth'])
+            model = ref_sfm.COLMAPModel(model_dir=dirs['model'], image_dir=dirs['images'], depth_dir=dirs['depth'],
+                                        image_scale=image_scale)
             image = model[target]
             image_list = [im for im in model.images.values() if im.name not in filter_names]
             h5py._reset()
@@ -211,7 +212,21 @@ def case_config1_param():
     print('config1_param', res['cost'][[0, -1]], res['B'].ravel(), res['beta'].ravel(), res['gamma'].ravel())
 
 
-CASES = dict(tiny6=case_tiny6, mixed8=case_mixed8, config1=case_config1, config1_param=case_config1_param)
+def case_scaled8():
+    # --image-scale 0.5: colour resampled in float (INTER_AREA), depth nearest, intrinsics scaled (sfm.py:193-199)
+    scene = SyntheticScene(8, 192, 128, seed=5)
+    target = 'image0004.png'
+    for mode, cf in (('closed', True), ('param', False)):
+        res = run_reference(scene, target, closed_form=cf, num_iter=15, min_cover=1e-6, batch_size=3, image_scale=0.5)
+        packed = pack_full(scene, target, res, dict(closed_form=cf, num_iter=15, min_cover=1e-6, seed=5, width=192,
+                                                    height=128, n_views=8, image_scale=0.5))
+        if not cf:
+            packed = {k: v for k, v in packed.items() if not k.startswith(('in_', 'm_', 'ref_'))}
+        np.savez_compressed(GOLDEN / f'scaled8_{mode}.npz', **packed)
+        print('scaled8', mode, {k: len(v['u1']) for k, v in res['views'].items()}, res['cost'][[0, -1]])
+
+
+CASES = dict(scaled8=case_scaled8, tiny6=case_tiny6, mixed8=case_mixed8, config1=case_config1, config1_param=case_config1_param)
 
 if __name__ == '__main__':
     GOLDEN.mkdir(parents=True, exist_ok=True)

@@ -9,15 +9,17 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 2
+ABI_VERSION = 3
 TILE = 32
 SEG_HEADER_CELLS = 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
 
-# numpy mirror of `struct sucre_view` (192 bytes)
+# numpy mirror of `struct sucre_view` (208 bytes)
 VIEW_DTYPE = np.dtype([('K', '<f4', 9), ('Kinv', '<f4', 9), ('R', '<f4', 9), ('t', '<f4', 3), ('Ri', '<f4', 9),
-                       ('ti', '<f4', 3), ('width', '<i4'), ('height', '<i4'), ('depth', '<u8'), ('rgb', '<u8')])
-assert VIEW_DTYPE.itemsize == 192
+                       ('ti', '<f4', 3), ('width', '<i4'), ('height', '<i4'), ('depth', '<u8'), ('rgb', '<u8'),
+                       ('rgb_format', '<i4'), ('reserved', '<i4', 3)])
+assert VIEW_DTYPE.itemsize == 208
+RGB_U8, RGB_F32 = 0, 1
 
 
 class SucreError(RuntimeError):
@@ -80,9 +82,11 @@ def check(rc: int, what: str):
         raise SucreError(f'{what}: {lib().sucre_last_error().decode()}')
 
 
-def view_record(K, Kinv, R, t, Ri, ti, width: int, height: int, depth_ptr: int = 0, rgb_ptr: int = 0) -> np.ndarray:
+def view_record(K, Kinv, R, t, Ri, ti, width: int, height: int, depth_ptr: int = 0, rgb_ptr: int = 0,
+                rgb_format: int = RGB_U8) -> np.ndarray:
     rec = np.zeros((), dtype=VIEW_DTYPE)
     for name, val in (('K', K), ('Kinv', Kinv), ('R', R), ('t', t), ('Ri', Ri), ('ti', ti)):
         rec[name] = np.asarray(val, dtype=np.float32).reshape(-1)
     rec['width'], rec['height'], rec['depth'], rec['rgb'] = width, height, depth_ptr, rgb_ptr
+    rec['rgb_format'] = rgb_format
     return rec

@@ -52,7 +52,7 @@ def restore_resident(scene: engine.DeviceScene, target_key, source_keys, *, min_
     dev = scene.device
     J0 = None
     if not use_closed_form:  # sucre.py:47-49: J starts as the target image, NaN where its depth <= 0
-        J0 = scene.rgb[target_key].to(torch.float32) / 255.0
+        J0 = scene.rgb_float(target_key)
         J0[scene.depth[target_key].view(torch.int16) == 0] = float('nan')
     state = engine.FitState.initial(dev, params=params, J0=J0)
     if store.n_obs == 0:

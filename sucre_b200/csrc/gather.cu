@@ -56,7 +56,7 @@ __device__ __forceinline__ bool project(const float* Ri, const float* ti, const 
     return in;
 }
 
-constexpr int kViewWords = sizeof(sucre_view) / 4;  // 48
+constexpr int kViewWords = sizeof(sucre_view) / 4;  // 52
 constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;      // blocks (source views) per segment of the observation store
 constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
 constexpr int kChunk = 32;                          // source views per CTA: lane j keeps the mask of view j
@@ -66,7 +66,7 @@ template <int PIX>
 __global__ void __launch_bounds__(kWarps * 32)
 gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                     uint32_t* __restrict__ masks, int first_tile, int n_tiles) {
-    __shared__ __align__(16) sucre_view sv[kChunk];
+    __shared__ __align__(16) sucre_view sv[kChunk];  // 6.5 KB
     const int vbase = blockIdx.y * kChunk;
     const int nv = min(kChunk, n_views - vbase);
     {
@@ -306,7 +306,8 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
                 for (int i = 0; i < 3; ++i) ti[i] = __ldg(&S->ti[i]);
                 const int Ws = __ldg(&S->width), Hs = __ldg(&S->height);
                 const uint16_t* depth = reinterpret_cast<const uint16_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->depth)));
-                const uint8_t* rgb = reinterpret_cast<const uint8_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->rgb)));
+                const void* rgb = reinterpret_cast<const void*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->rgb)));
+                const int rgb_format = __ldg(&S->rgb_format);
                 int u2, v2;
                 project(Ri, ti, K, Ws, Hs, w0, w1, w2, u2, v2);
                 const size_t q = (size_t)v2 * Ws + u2;
@@ -315,10 +316,18 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
                 unproject(Kinv, u2, v2, d2, c0, c1, c2);                        // loader.py:113
                 // sucre.py:53 cP.norm(dim=0): sequential squares, no fma
                 const float z = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2)));
-                const uint8_t* px = rgb + 3 * q;
-                const float I0 = __fdiv_rn((float)__ldg(px + 0), 255.0f);       // loader.py:157, 87
-                const float I1 = __fdiv_rn((float)__ldg(px + 1), 255.0f);
-                const float I2 = __fdiv_rn((float)__ldg(px + 2), 255.0f);
+                float I0, I1, I2;
+                if (rgb_format == SUCRE_RGB_F32) {  // resampled on the host in float (--image-scale), loader.py:158-163
+                    const float* px = reinterpret_cast<const float*>(rgb) + 3 * q;
+                    I0 = __ldg(px + 0);
+                    I1 = __ldg(px + 1);
+                    I2 = __ldg(px + 2);
+                } else {
+                    const uint8_t* px = reinterpret_cast<const uint8_t*>(rgb) + 3 * q;
+                    I0 = __fdiv_rn((float)__ldg(px + 0), 255.0f);               // loader.py:157, 87
+                    I1 = __fdiv_rn((float)__ldg(px + 1), 255.0f);
+                    I2 = __fdiv_rn((float)__ldg(px + 2), 255.0f);
+                }
                 cells[at] = make_float4(z, I0, I1, I2);
                 if (cell_src) cell_src[at] = (uint32_t)u2 | ((uint32_t)v2 << 16);
                 ++at;

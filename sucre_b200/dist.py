@@ -67,7 +67,7 @@ class CudaBandOps:
         if not self.use_closed_form:  # J parameter: this band of the target image, NaN where depth <= 0 (sucre.py:47-49)
             lo = self.store.first_tile * TILE
             hi = lo + self.store.local_pixels
-            J0 = (self.scene.rgb[self.target_key].reshape(-1, 3)[lo:hi].to(torch.float32) / 255.0)
+            J0 = self.scene.rgb_float(self.target_key).reshape(-1, 3)[lo:hi].clone()
             J0[self.scene.depth[self.target_key].view(torch.int16).reshape(-1)[lo:hi] == 0] = float('nan')
         self.state = engine.FitState.initial(self.device, params=params, J0=J0)
         if self.store.n_obs > 0:

@@ -36,10 +36,10 @@ class ViewGeom:
         t = torch.as_tensor(t, dtype=torch.float32).reshape(3, 1).cpu()
         return ViewGeom(K=K, Kinv=K.inverse(), R=R, t=t, Ri=R.T, ti=-R.T @ t, width=int(width), height=int(height))
 
-    def record(self, depth_ptr: int = 0, rgb_ptr: int = 0) -> np.ndarray:
+    def record(self, depth_ptr: int = 0, rgb_ptr: int = 0, rgb_format: int = _lib.RGB_U8) -> np.ndarray:
         c = lambda x: x.contiguous().numpy()  # noqa: E731
         return _lib.view_record(c(self.K), c(self.Kinv), c(self.R), c(self.t), c(self.Ri), c(self.ti),
-                                self.width, self.height, depth_ptr, rgb_ptr)
+                                self.width, self.height, depth_ptr, rgb_ptr, rgb_format)
 
 
 class DeviceScene:
@@ -64,12 +64,13 @@ class DeviceScene:
         return len(self.geom)
 
     def add_view(self, key, geom: ViewGeom, depth_u16: torch.Tensor, rgb_u8: torch.Tensor | None):
-        """depth_u16: (H,W) uint16 (or int16 bit pattern), rgb_u8: (H,W,3) uint8; host (ideally pinned) or device."""
+        """depth_u16: (H,W) uint16 (or int16 bit pattern); rgb_u8: (H,W,3) uint8, or float32 in [0,1] for images the
+        host resampled (--image-scale); host (ideally pinned) or device."""
         assert depth_u16.shape == (geom.height, geom.width), (depth_u16.shape, geom.height, geom.width)
         assert depth_u16.element_size() == 2
         self.depth[key] = depth_u16.to(self.device, non_blocking=True).contiguous()
         if rgb_u8 is not None:
-            assert rgb_u8.shape == (geom.height, geom.width, 3) and rgb_u8.dtype == torch.uint8
+            assert rgb_u8.shape == (geom.height, geom.width, 3) and rgb_u8.dtype in (torch.uint8, torch.float32)
             self.rgb[key] = rgb_u8.to(self.device, non_blocking=True).contiguous()
         self.geom[key] = geom
         self._tables.clear()
@@ -84,7 +85,13 @@ class DeviceScene:
 
     def record(self, key) -> np.ndarray:
         rgb = self.rgb.get(key)
-        return self.geom[key].record(self.depth[key].data_ptr(), 0 if rgb is None else rgb.data_ptr())
+        fmt = _lib.RGB_F32 if rgb is not None and rgb.dtype == torch.float32 else _lib.RGB_U8
+        return self.geom[key].record(self.depth[key].data_ptr(), 0 if rgb is None else rgb.data_ptr(), fmt)
+
+    def rgb_float(self, key) -> torch.Tensor:
+        """(H,W,3) float32 colour of a view as the reference's load_rgb returns it (loader.py:156-163)."""
+        rgb = self.rgb[key]
+        return rgb.clone() if rgb.dtype == torch.float32 else rgb.to(torch.float32) / 255.0
 
     def table(self, keys) -> torch.Tensor:
         """Device array of `sucre_view` for `keys` (cached)."""

@@ -28,7 +28,7 @@ def _imread(path: Path, flags=None) -> np.ndarray:
 
 def load_rgb(rgb_path: Path, width: int, height: int) -> Tensor:
     """(H,W,3) float32 in [0,1], value-for-value what loader.py:156-163 returns (kept for API parity; the hot path
-    uploads load_rgb_u8 and divides by 255 in-kernel, which is bit-identical for every u8 code)."""
+    uploads load_rgb_device_form: the raw u8 image, divided by 255 in-kernel, bit-identical for every u8 code)."""
     rgb = cv2.cvtColor(_imread(rgb_path), cv2.COLOR_BGR2RGB) / 255
     if (rgb.shape[0] != height) or (rgb.shape[1] != width):
         rgb = cv2.resize(rgb, (width, height), interpolation=cv2.INTER_AREA if width < rgb.shape[1] else cv2.INTER_CUBIC)
@@ -43,15 +43,16 @@ def load_depth_map(depth_map_path: Path, width: int, height: int) -> Tensor:
     return torch.tensor(depth_map, dtype=torch.float32)
 
 
-def load_rgb_u8(rgb_path: Path, width: int, height: int) -> Tensor:
-    """(H,W,3) uint8 RGB exactly as stored in the file."""
+def load_rgb_device_form(rgb_path: Path, width: int, height: int) -> Tensor:
+    """Colour in the form the device-resident scene keeps it: (H,W,3) uint8 exactly as stored when the file has the
+    camera's size (the /255 then happens in-kernel, bit-identical), else (H,W,3) float32 resampled exactly like
+    loader.py:157-163 (float64 /255, INTER_AREA when shrinking else INTER_CUBIC, then float32)."""
     bgr = _imread(rgb_path)
-    if (bgr.shape[0] != height) or (bgr.shape[1] != width):
-        raise NotImplementedError(
-            f'{rgb_path}: file is {bgr.shape[1]}x{bgr.shape[0]} but the camera is {width}x{height}. The reference '
-            f'resamples colour in float (loader.py:158-162), which leaves the u8 grid; --image-scale != 1 is not '
-            f'supported by the device-resident u8 scene yet.')
-    return torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1]))
+    if (bgr.shape[0] == height) and (bgr.shape[1] == width):
+        return torch.from_numpy(np.ascontiguousarray(bgr[..., ::-1]))
+    rgb = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB) / 255
+    rgb = cv2.resize(rgb, (width, height), interpolation=cv2.INTER_AREA if width < rgb.shape[1] else cv2.INTER_CUBIC)
+    return torch.tensor(rgb, dtype=torch.float32)
 
 
 def load_depth_u16(depth_map_path: Path, width: int, height: int) -> Tensor:

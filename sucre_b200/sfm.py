@@ -162,8 +162,8 @@ class Image:
     def get_depth_map(self) -> Tensor:
         return loader.load_depth_map(self.depth_map_path, width=self.camera.width, height=self.camera.height)
 
-    def get_rgb_u8(self) -> Tensor:
-        return loader.load_rgb_u8(self.rgb_path, width=self.camera.width, height=self.camera.height)
+    def get_rgb_device_form(self) -> Tensor:
+        return loader.load_rgb_device_form(self.rgb_path, width=self.camera.width, height=self.camera.height)
 
     def get_depth_u16(self) -> Tensor:
         return loader.load_depth_u16(self.depth_map_path, width=self.camera.width, height=self.camera.height)
@@ -241,7 +241,7 @@ class COLMAPModel:
                 seen.add(im.id)
         if todo:
             def decode(im):
-                return im, im.get_depth_u16(), im.get_rgb_u8()
+                return im, im.get_depth_u16(), im.get_rgb_device_form()
             if num_workers > 0 and len(todo) > 1:
                 with ThreadPoolExecutor(max_workers=num_workers) as pool:
                     decoded = list(pool.map(decode, todo))

@@ -37,7 +37,7 @@ class SUCRe:
         self.use_closed_form = use_closed_form
         J0 = None
         if not use_closed_form:
-            J0 = image.get_rgb_u8().to(torch.float32) / 255.0              # sucre.py:48 (= load_rgb, bit for bit)
+            J0 = image.get_rgb()                                          # sucre.py:48
             J0[image.get_depth_u16().to(torch.int32) <= 0] = torch.nan    # sucre.py:49
         self.state = engine.FitState.initial('cpu', J0=J0)
         self._J_closed: Tensor | None = None

@@ -22,9 +22,10 @@ def test_header_symbols_are_exported():
 def test_view_struct_layout_matches_header():
     header = (ROOT / 'include' / 'sucre_b200.h').read_text()
     assert 'float K[9], Kinv[9], R[9], t[3], Ri[9], ti[3];' in header
-    assert _lib.VIEW_DTYPE.itemsize == 192
+    assert _lib.VIEW_DTYPE.itemsize == 208
     assert [_lib.VIEW_DTYPE.fields[n][1] for n in ('K', 'Kinv', 'R', 't', 'Ri', 'ti', 'width', 'height', 'depth', 'rgb')] \
         == [0, 36, 72, 108, 120, 156, 168, 172, 176, 184]
+    assert _lib.VIEW_DTYPE.fields["rgb_format"][1] == 192
 
 
 def test_argument_errors_without_gpu():

@@ -99,3 +99,36 @@ def test_unknown_image_and_bad_camera(golden, tmp_path):
     (root / 'model' / 'cameras.txt').write_text(txt)
     with pytest.raises(AssertionError):
         sfm.COLMAPModel(root / 'model', root / 'images', root / 'depth')
+
+
+@pytest.mark.parametrize('mode', ['closed', 'param'])
+def test_image_scale_like_the_reference(golden, tmp_path, mode, capsys):
+    """--image-scale 0.5: intrinsics scaled (sfm.py:193-199), depth resampled nearest, colour resampled in float
+    (loader.py:158-169) and kept as float32 on the device."""
+    g = golden('scaled8_closed')
+    gm = golden(f'scaled8_{mode}')
+    root = _write_golden_scene(g, tmp_path)
+    model = sfm.COLMAPModel(root / 'model', root / 'images', root / 'depth', image_scale=0.5)
+    image = model[str(g['target'])]
+    assert (image.camera.width, image.camera.height) == (96, 64)
+    assert np.array_equal(image.geom.K.numpy(), g.geom_arrays(g.view_index(image.name))['K'])
+    sucre.restore_image(image, model, root / 'out', use_closed_form=(mode == 'closed'), num_iter=int(gm['num_iter']),
+                        keep_matches=True, device='cuda')
+    from sucre_b200 import loader
+    mf = loader.MatchesFile(root / 'out' / 'image0004.h5', colmap_model=model)
+    data = mf.load_matches(device='cuda')
+    got = data.store.to_reference_layout()
+    names = [n for n, k in zip(data.names, data.store.view_kept) if k]
+    assert names == g['kept'].tolist()
+    for key, name in zip(data.store.kept_keys, names):
+        ref = g.matches(name)
+        for f in ('u1', 'v1', 'u2', 'v2'):
+            assert np.array_equal(got[key][f], ref[f]), (name, f)
+        assert np.array_equal(got[key]['I'].view(np.uint32), ref['I'].view(np.uint32)), name   # float colour, bit-exact
+        assert np.array_equal(got[key]['z'].view(np.uint32), ref['z'].view(np.uint32)), name
+    saved = torch.load(root / 'out' / 'image0004.pt')
+    for k in ('B', 'beta', 'gamma'):
+        assert _rel(saved[k].numpy(), gm[k]) < 1e-4
+    J = saved['J'].numpy()
+    assert J.shape == (64, 96, 3)
+    assert np.array_equal(np.isnan(J), np.isnan(gm['J'])) and np.nanmax(np.abs(J - gm['J'])) < 1e-3
