@@ -26,6 +26,9 @@
  *   sucre.py:53), I = source colour / 255 (loader.py:157, 87).  The first cell of tile k is
  *   rec_off[k] + 2*seg_off[k]; tiles follow each other, so any run of tiles is one contiguous byte range (the fit
  *   streams it with 1-D TMA bulk copies).  Total cells = N + 2 * (number of segments).
+ *   The light model (--light-model) needs the observation's camera-frame point, not only its norm: its stores use
+ *   two cells per record, {cP_x, cP_y, cP_z, ||cP||} {I_r, I_g, I_b, 0} (record_cells = 2; first cell of tile k =
+ *   2*rec_off[k] + 2*seg_off[k]), and shorter segments.
  */
 #ifndef SUCRE_B200_H
 #define SUCRE_B200_H
@@ -37,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 3
+#define SUCRE_ABI_VERSION 4
 #define SUCRE_TILE_PIXELS 32
 #ifndef SUCRE_SEGMENT_VIEWS
 #define SUCRE_SEGMENT_VIEWS 15
@@ -68,15 +71,17 @@ typedef struct sucre_view {
 } sucre_view;
 
 /* The observation store of one target (or of a band of its tiles), as the fit reads it.  A host struct of
- * device pointers.  sizeof == 48. */
+ * device pointers.  sizeof == 56. */
 typedef struct sucre_store {
     const float* cells;      /* 16-byte cells, 16-byte aligned */
     const int64_t* rec_off;  /* [n_tiles+1] records before tile k */
     const int64_t* blk_off;  /* [n_tiles+1] blocks before tile k */
     const int64_t* seg_off;  /* [n_tiles+1] segments before tile k */
     int32_t n_tiles;
-    int32_t reserved;
+    int32_t seg_views;       /* source views per segment this store was planned with (1..15) */
     int64_t pixels;          /* target pixels covered: min(n_tiles*32, width*height - first_tile*32) */
+    int32_t record_cells;    /* cells per record: 1 = {z, I}; 2 = {cP_x, cP_y, cP_z, ||cP||}, {I_r, I_g, I_b, 0} */
+    int32_t reserved;
 } sucre_store;
 
 int sucre_abi_version(void);
@@ -107,9 +112,10 @@ int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t*
  *   view_kept[n_views]   (uint8)  1 if the view passes min_cover
  *   rec_off, blk_off, seg_off [n_tiles+1] (int64) exclusive prefix sums over the band's tiles, kept views only
  *   totals[3] (int64)    {N = observations in the band, blocks, segments}; copy to the host to size the store:
- *                        cells = N + 2*segments, blk_mask / blk_view = blocks entries */
+ *                        cells = record_cells*N + 2*segments, blk_mask / blk_view = blocks entries
+ * seg_views (1..15): source views per segment; sucre_segment_views() is the value the fit is tuned for. */
 int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
-                      int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off,
+                      int64_t target_pixels, double min_cover, int seg_views, uint8_t* view_kept, int64_t* rec_off,
                       int64_t* blk_off, int64_t* seg_off, int64_t* totals, void* stream);
 
 /* sucre_gather_sample: fills the observation store.  Replaces MatchesFile.save_matches / prepare_matches /
@@ -118,8 +124,8 @@ int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int
  * u2 | v2 << 16 at every record cell: the integer source pixel (what the reference stores as int16 u2, v2). */
 int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
                         int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                        const int64_t* blk_off, const int64_t* seg_off, float* cells, uint32_t* blk_mask,
-                        int32_t* blk_view, uint32_t* cell_src, void* stream);
+                        const int64_t* blk_off, const int64_t* seg_off, int seg_views, int record_cells, float* cells,
+                        uint32_t* blk_mask, int32_t* blk_view, uint32_t* cell_src, void* stream);
 
 /* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
  * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for
@@ -169,6 +175,27 @@ int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* par
  * sucre.py:77).  J_ref (optional): a previous J used as the reference point of the statistics. */
 int sucre_fit_write_J(const sucre_store* store_host, const float* params, const float* J_ref, float* J,
                       void* workspace, void* stream);
+
+/* ---- stage 2, light model (--light-model, sucre.py:44-46, 54-61) ---------------------------------------------
+ * l = exp(-lp^T Sigma^-1 lp / 2) with lp the perspective division of lP = R cP + t, z = ||cP|| + ||lP||,
+ * I_hat = l (J e^{-beta z} + B (1 - e^{-gamma z})).  Stores must have record_cells == 2.
+ * params24 = B[3], beta[3], gamma[3], R[9] row-major, t[3], Sinv[3] = (Sigma^-1)_00, _01, _11 — R, t =
+ * se3.exp(cam2light) (se3.py:22-27) and Sigma^-1 = (sigma^T sigma)^-1 are evaluated on the host with the reference's
+ * own torch expressions; the chain rule back to cam2light / sigma is applied on the host from sums[10..24].
+ *
+ * sucre_light_J: closed-form J (sucre.py:66-77 with the light terms) for the given parameters; NaN where unobserved. */
+int sucre_light_J(const sucre_store* store_host, const float* params24, float* J, void* stream);
+
+/* sucre_light_sums: one residual pass with J given per pixel, reduced to sums[25] (double):
+ *   [0..2] sum r l (1-e^{-gamma z})   [3..5] sum r l J z e^{-beta z}   [6..8] sum r l B z e^{-gamma z}   [9] sum r^2
+ *   [10..12] sum g_l l {x^2, x y, y^2}           (lp = (x, y);  dL/dSigma^-1 = -(2/3N) * (-1/2) * [[.,.],[.,.]])
+ *   [13..21] sum g_lP (x) cP (3x3 row-major)      (dL/dR = -(2/3N) * this)
+ *   [22..24] sum g_lP                             (dL/dt = -(2/3N) * this)
+ * with g_l = sum_c r_c (J_c a_c + B_c h_c), g_z = sum_c r_c l (-beta_c J_c a_c + gamma_c B_c g_c),
+ * g_lP = g_l dl/dlP + g_z lP/||lP||.  mode SUCRE_FIT_PARAM_J additionally applies Adam step t to J in the same pass
+ * (gradient -(2/(3 n_obs)) sum r l e^{-beta z}); in SUCRE_FIT_CLOSED_FORM mode J is read only. */
+int sucre_light_sums(int mode, const sucre_store* store_host, const float* params24, float* J, float* J_moments,
+                     int64_t n_obs, int t, double lr, double* sums, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,7 +44,7 @@ GOLDEN = ROOT / 'tests' / 'golden'
 
 
 def run_reference(scene: SyntheticScene, target: str, *, closed_form: bool, num_iter: int, min_cover: float,
-                  batch_size: int, filter_names=(), image_scale: float = 1.0):
+                  batch_size: int, filter_names=(), image_scale: float = 1.0, light_model: bool = False):
     """Runs reference restore_image on CPU; returns dict of captured arrays."""
     log_lines = []
     history = []
@@ -57,7 +57,8 @@ def run_reference(scene: SyntheticScene, target: str, *, closed_form: bool, num_
     def step(self, *a, **k):
         out = orig_step(self, *a, **k)
         ps = [p.detach().clone() for g in self.param_groups for p in g['params']]
-        history.append(torch.cat([p.flatten() for p in ps[:3]]).numpy())  # B, beta, gamma are registered first
+        # registration order: B, beta, gamma, then (light model) cam2light (6) and sigma (2x2)
+        history.append(torch.cat([p.flatten() for p in ps[:5 if light_model else 3]]).numpy())
         return out
 
     with tempfile.TemporaryDirectory() as tmp:
@@ -74,7 +75,7 @@ def run_reference(scene: SyntheticScene, target: str, *, closed_form: bool, num_
             image = model[target]
             image_list = [im for im in model.images.values() if im.name not in filter_names]
             h5py._reset()
-            ref_sucre.restore_image(image=image, colmap_model=model, output_dir=out_dir, light_model=False,
+            ref_sucre.restore_image(image=image, colmap_model=model, output_dir=out_dir, light_model=light_model,
                                     use_closed_form=closed_form, min_cover=min_cover, image_list=image_list,
                                     lr=0.05, num_iter=num_iter, batch_size=batch_size, keep_matches=True,
                                     device='cpu')
@@ -98,8 +99,12 @@ def run_reference(scene: SyntheticScene, target: str, *, closed_form: bool, num_
                                ti=im.pose.inverse().t.numpy(), wh=np.array([im.camera.width, im.camera.height]))
                  for im in model.images.values()}
     cost = [float(re.search(r'cost: ([0-9.e+-]+)', l).group(1)) for l in log_lines if l.startswith('iter:')]
-    return dict(views=views, history=np.stack(history), cost=np.array(cost), J=saved['J'].numpy(),
-                B=saved['B'].numpy(), beta=saved['beta'].numpy(), gamma=saved['gamma'].numpy(), poses=poses)
+    out = dict(views=views, history=np.stack(history), cost=np.array(cost), J=saved['J'].numpy(),
+               B=saved['B'].numpy(), beta=saved['beta'].numpy(), gamma=saved['gamma'].numpy(), poses=poses)
+    if light_model:
+        out['cam2light'] = saved['cam2light'].numpy()
+        out['sigma'] = saved['sigma'].numpy()
+    return out
 
 
 def _hash(*arrays) -> str:
@@ -128,8 +133,9 @@ def pack_full(scene: SyntheticScene, target: str, res: dict, extra: dict) -> dic
     for name, v in res['views'].items():
         for k, a in v.items():
             out[f'm_{name}_{k}'] = a
-    for k in ('history', 'cost', 'J', 'B', 'beta', 'gamma'):
-        out[k] = res[k]
+    for k in ('history', 'cost', 'J', 'B', 'beta', 'gamma', 'cam2light', 'sigma'):
+        if k in res:
+            out[k] = res[k]
     return out
 
 
@@ -226,7 +232,20 @@ def case_scaled8():
         print('scaled8', mode, {k: len(v['u1']) for k, v in res['views'].items()}, res['cost'][[0, -1]])
 
 
-CASES = dict(scaled8=case_scaled8, tiny6=case_tiny6, mixed8=case_mixed8, config1=case_config1, config1_param=case_config1_param)
+def case_light6():
+    # --light-model (sucre.py:44-46, 54-61): Gaussian light cone + two-leg path, 10 extra Adam parameters
+    scene = SyntheticScene(6, 96, 64, seed=0)
+    target = 'image0002.png'
+    for mode, cf in (('closed', True), ('param', False)):
+        res = run_reference(scene, target, closed_form=cf, num_iter=30, min_cover=1e-6, batch_size=2, light_model=True)
+        packed = pack_full(scene, target, res, dict(closed_form=cf, num_iter=30, min_cover=1e-6, seed=0, width=96,
+                                                    height=64, n_views=6, light_model=True))
+        packed = {k: v for k, v in packed.items() if not k.startswith(('in_', 'm_', 'ref_'))}  # inputs = tiny6_closed
+        np.savez_compressed(GOLDEN / f'light6_{mode}.npz', **packed)
+        print('light6', mode, res['cost'][[0, -1]], res['cam2light'], res['sigma'].ravel())
+
+
+CASES = dict(scaled8=case_scaled8, light6=case_light6, tiny6=case_tiny6, mixed8=case_mixed8, config1=case_config1, config1_param=case_config1_param)
 
 if __name__ == '__main__':
     GOLDEN.mkdir(parents=True, exist_ok=True)

@@ -9,7 +9,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 3
+ABI_VERSION = 4
 TILE = 32
 SEG_HEADER_CELLS = 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
@@ -29,10 +29,12 @@ class SucreError(RuntimeError):
 class SucreStore(C.Structure):
     """ctypes mirror of `struct sucre_store` (host struct of device pointers, 48 bytes)."""
     _fields_ = [('cells', C.c_void_p), ('rec_off', C.c_void_p), ('blk_off', C.c_void_p), ('seg_off', C.c_void_p),
-                ('n_tiles', C.c_int32), ('reserved', C.c_int32), ('pixels', C.c_int64)]
+                ('n_tiles', C.c_int32), ('seg_views', C.c_int32), ('pixels', C.c_int64),
+                ('record_cells', C.c_int32), ('reserved', C.c_int32)]
 
 
-assert C.sizeof(SucreStore) == 48
+assert C.sizeof(SucreStore) == 56
+LIGHT_SEG_VIEWS = 7   # two-cell records: 2 + 2*32*7 = 450 cells per segment at most
 
 
 _lib = None
@@ -44,14 +46,16 @@ _SIGNATURES = {
     'sucre_last_error': (C.c_char_p, []),
     'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
-    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
-    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     'sucre_fit_workspace_bytes': (C.c_size_t, []),
     'sucre_fit_prepare': (C.c_int, [_VP, _VP, _VP]),
     'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
     'sucre_adam_step': (C.c_int, [_VP, _VP, _VP, _I64, _I, _D, _VP, _VP]),
     'sucre_fit': (C.c_int, [_I, _VP, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
     'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_light_J': (C.c_int, [_VP, _VP, _VP, _VP]),
+    'sucre_light_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -226,6 +226,7 @@ struct FitArgs {
     const long long* blk_off;
     const long long* seg_off;
     int n_tiles;
+    int seg_views;
     long long pixels;
     float* params;         // 9: B, beta, gamma (read at start; written by the last CTA when do_step)
     float* moments;        // 18: Adam state of the 9 scalars
@@ -339,7 +340,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         int seen = 0;
         if (nb > 0) {  // warp-uniform
             const float nJ[3] = {-Jref[0], -Jref[1], -Jref[2]};
-            const int nseg = (nb + kSegViews - 1) / kSegViews;
+            const int nseg = (nb + A.seg_views - 1) / A.seg_views;
 #pragma unroll 1
             for (int s = 0; s < nseg; ++s) {
                 acquire(pos + kSegHeaderCells);
@@ -574,6 +575,9 @@ static int check_store(const sucre_store* s, const char* who) {
     SUCRE_REQUIRE(s->cells && s->rec_off && s->blk_off && s->seg_off, "%s: null pointer in store", who);
     SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && s->pixels <= (int64_t)s->n_tiles * kTile, "%s: bad store sizes", who);
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(s->cells) & 15) == 0, "%s: cells must be 16-byte aligned", who);
+    SUCRE_REQUIRE(s->record_cells == 1, "%s: this entry point reads {z, I} stores (record_cells == 1), got %d", who, s->record_cells);
+    SUCRE_REQUIRE(s->seg_views >= 1 && kSegHeaderCells + 32 * s->seg_views <= kRingCells - kChunkCells,
+                  "%s: segments of %d views do not fit the shared-memory ring", who, s->seg_views);
     return 0;
 }
 
@@ -584,6 +588,7 @@ static FitArgs base_args(const sucre_store* s, void* workspace) {
     a.blk_off = (const long long*)s->blk_off;
     a.seg_off = (const long long*)s->seg_off;
     a.n_tiles = s->n_tiles;
+    a.seg_views = s->seg_views;
     a.pixels = s->pixels;
     char* ws = (char*)workspace;
     a.partials = (double*)(ws + kWsPartials);

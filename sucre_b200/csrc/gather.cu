@@ -57,7 +57,7 @@ __device__ __forceinline__ bool project(const float* Ri, const float* ti, const 
 }
 
 constexpr int kViewWords = sizeof(sucre_view) / 4;  // 52
-constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;      // blocks (source views) per segment of the observation store
+constexpr int kSegViewsMax = 15;                    // per-lane record counts of a segment are read as small ints
 constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
 constexpr int kChunk = 32;                          // source views per CTA: lane j keeps the mask of view j
 constexpr int kWarps = 8;
@@ -154,7 +154,8 @@ __global__ void kept_kernel(const long long* __restrict__ view_count, int n_view
 // records, non-empty blocks and segments per tile over kept views: one warp per tile
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept, int n_tiles, int n_views,
-                  long long* __restrict__ rec_cnt, long long* __restrict__ blk_cnt, long long* __restrict__ seg_cnt) {
+                  int seg_views, long long* __restrict__ rec_cnt, long long* __restrict__ blk_cnt,
+                  long long* __restrict__ seg_cnt) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
@@ -171,7 +172,7 @@ tile_count_kernel(const uint32_t* __restrict__ masks, const uint8_t* __restrict_
     if (lane == 0) {
         rec_cnt[tile] = rec;
         blk_cnt[tile] = blk;
-        seg_cnt[tile] = (blk + kSegViews - 1) / kSegViews;
+        seg_cnt[tile] = (blk + seg_views - 1) / seg_views;
     }
 }
 
@@ -229,15 +230,16 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
 
 // ---- sample ----------------------------------------------------------------------------------------------
 // One warp per tile.  Phase A compacts the tile's non-empty kept blocks (lane mask + view index) into
-// blk_mask / blk_view.  Phase B walks them in segments of kSegViews blocks: per-lane record counts -> header
+// blk_mask / blk_view.  Phase B walks them in segments of seg_views blocks: per-lane record counts -> header
 // cells, exclusive scan over lanes -> each lane's first cell, then every matched (pixel, view) is re-projected,
 // its source depth + colour fetched, and the record stored in the lane's run (lane-major within the segment).
 __global__ void __launch_bounds__(256)
 gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                      const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
                      const long long* __restrict__ rec_off, const long long* __restrict__ blk_off,
-                     const long long* __restrict__ seg_off, int first_tile, int n_tiles, float4* __restrict__ cells,
-                     uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view, uint32_t* __restrict__ cell_src) {
+                     const long long* __restrict__ seg_off, int first_tile, int n_tiles, int seg_views, int record_cells,
+                     float4* __restrict__ cells, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
+                     uint32_t* __restrict__ cell_src) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
@@ -269,9 +271,9 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
     }
     __syncwarp();
     // phase B
-    long long cell = rec_off[tile] + kSegHeaderCells * seg_off[tile];
-    for (int s0 = 0; s0 < nb; s0 += kSegViews) {
-        const int ns = min(kSegViews, nb - s0);
+    long long cell = record_cells * rec_off[tile] + kSegHeaderCells * seg_off[tile];
+    for (int s0 = 0; s0 < nb; s0 += seg_views) {
+        const int ns = min(seg_views, nb - s0);
         uint32_t bm_l = 0;
         int bv_l = 0;
         if (lane < ns) {
@@ -280,7 +282,7 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
         }
         int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < kSegViews; ++j) cnt += (__shfl_sync(kFull, bm_l, j) >> lane) & 1u;
+        for (int j = 0; j < kSegViewsMax; ++j) cnt += (__shfl_sync(kFull, bm_l, j) >> lane) & 1u;  // bm_l = 0 for j >= ns
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -289,7 +291,7 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
         }
         const int n = __shfl_sync(kFull, incl, 31);
         reinterpret_cast<uint8_t*>(cells + cell)[lane] = (uint8_t)cnt;  // header: 32 lane counts
-        long long at = cell + kSegHeaderCells + (incl - cnt);
+        long long at = cell + kSegHeaderCells + (long long)record_cells * (incl - cnt);
         for (int j = 0; j < ns; ++j) {
             const uint32_t bm = __shfl_sync(kFull, bm_l, j);
             const int s = __shfl_sync(kFull, bv_l, j);
@@ -328,12 +330,17 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
                     I1 = __fdiv_rn((float)__ldg(px + 1), 255.0f);
                     I2 = __fdiv_rn((float)__ldg(px + 2), 255.0f);
                 }
-                cells[at] = make_float4(z, I0, I1, I2);
+                if (record_cells == 1) {
+                    cells[at] = make_float4(z, I0, I1, I2);
+                } else {  // light model: the camera-frame point itself is needed (sucre.py:57)
+                    cells[at] = make_float4(c0, c1, c2, z);
+                    cells[at + 1] = make_float4(I0, I1, I2, 0.f);
+                }
                 if (cell_src) cell_src[at] = (uint32_t)u2 | ((uint32_t)v2 << 16);
-                ++at;
+                at += record_cells;
             }
         }
-        cell += kSegHeaderCells + n;
+        cell += kSegHeaderCells + (long long)record_cells * n;
     }
 }
 
@@ -383,31 +390,35 @@ extern "C" int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_view
 }
 
 extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
-                                 int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off,
+                                 int64_t target_pixels, double min_cover, int seg_views, uint8_t* view_kept, int64_t* rec_off,
                                  int64_t* blk_off, int64_t* seg_off, int64_t* totals, void* stream) {
     clear_error();
     SUCRE_REQUIRE(masks && view_count && view_kept && rec_off && blk_off && seg_off && totals, "sucre_gather_plan: null pointer");
     SUCRE_REQUIRE(n_tiles > 0 && n_views > 0 && target_pixels > 0, "sucre_gather_plan: bad sizes");
+    SUCRE_REQUIRE(seg_views >= 1 && seg_views <= kSegViewsMax, "sucre_gather_plan: seg_views %d outside [1, %d]", seg_views, kSegViewsMax);
     cudaStream_t st = (cudaStream_t)stream;
     kept_kernel<<<(n_views + 127) / 128, 128, 0, st>>>((const long long*)view_count, n_views, (double)target_pixels, min_cover, view_kept);
-    tile_count_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(masks, view_kept, n_tiles, n_views, (long long*)rec_off, (long long*)blk_off,
-                                                         (long long*)seg_off);
+    tile_count_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(masks, view_kept, n_tiles, n_views, seg_views, (long long*)rec_off,
+                                                         (long long*)blk_off, (long long*)seg_off);
     scan_kernel<<<1, 1024, 0, st>>>((long long*)rec_off, (long long*)blk_off, (long long*)seg_off, n_tiles, (long long*)totals);
     return check_launch("sucre_gather_plan kernels");
 }
 
 extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
                                    int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                                   const int64_t* blk_off, const int64_t* seg_off, float* cells, uint32_t* blk_mask,
-                                   int32_t* blk_view, uint32_t* cell_src, void* stream) {
+                                   const int64_t* blk_off, const int64_t* seg_off, int seg_views, int record_cells,
+                                   float* cells, uint32_t* blk_mask, int32_t* blk_view, uint32_t* cell_src, void* stream) {
     clear_error();
     if (check_view_host(target_host, "sucre_gather_sample(target)")) return 1;
     SUCRE_REQUIRE(views && masks && view_kept && rec_off && blk_off && seg_off && cells && blk_mask && blk_view,
                   "sucre_gather_sample: null pointer");
     if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_sample")) return 1;
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(cells) & 15) == 0, "sucre_gather_sample: cells must be 16-byte aligned");
+    SUCRE_REQUIRE(seg_views >= 1 && seg_views <= kSegViewsMax && (record_cells == 1 || record_cells == 2),
+                  "sucre_gather_sample: seg_views %d / record_cells %d not supported", seg_views, record_cells);
     gather_sample_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
         *target_host, views, n_views, masks, view_kept, (const long long*)rec_off, (const long long*)blk_off,
-        (const long long*)seg_off, first_tile, n_tiles, reinterpret_cast<float4*>(cells), blk_mask, blk_view, cell_src);
+        (const long long*)seg_off, first_tile, n_tiles, seg_views, record_cells, reinterpret_cast<float4*>(cells), blk_mask,
+        blk_view, cell_src);
     return check_launch("gather_sample_kernel");
 }

@@ -125,11 +125,15 @@ class ObservationStore:
     workspace: torch.Tensor | None = None  # fit scratch, prepared on first use
     first_tile: int = 0           # band of the target this store covers (multi-GPU pixel sharding): tiles
     n_tiles: int = 0              # [first_tile, first_tile + n_tiles); 0 = the whole target (set in __post_init__)
+    seg_views: int = 0            # source views per segment (0 = the library default, set in __post_init__)
+    record_cells: int = 1         # 1: {z, I}; 2: {cP, ||cP||}, {I, 0} (light model)
     stats: dict = field(default_factory=dict)
 
     def __post_init__(self):
         if self.n_tiles == 0:
             self.n_tiles = (self.width * self.height + TILE - 1) // TILE
+        if self.seg_views == 0:
+            self.seg_views = _lib.seg_views()
 
     @property
     def is_band(self) -> bool:
@@ -153,13 +157,14 @@ class ObservationStore:
 
     def c_struct(self) -> _lib.SucreStore:
         return _lib.SucreStore(self.cells.data_ptr(), self.rec_off.data_ptr(), self.blk_off.data_ptr(),
-                               self.seg_off.data_ptr(), self.n_tiles, 0, self.local_pixels)
+                               self.seg_off.data_ptr(), self.n_tiles, self.seg_views, self.local_pixels,
+                               self.record_cells, 0)
 
     def record_index(self) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """(cell, pixel, view) of every record (device int64 tensors, block-major order): decodes the segment
         structure from the block masks.  For export / parity checks, not used by the kernels."""
         dev = self.cells.device
-        G, HC = _lib.seg_views(), _lib.SEG_HEADER_CELLS
+        G, HC, RC = self.seg_views, _lib.SEG_HEADER_CELLS, self.record_cells
         nblk_tile = self.blk_off[1:] - self.blk_off[:-1]
         blk_tile = torch.repeat_interleave(torch.arange(self.n_tiles, device=dev), nblk_tile)
         j = torch.arange(self.n_blocks, device=dev) - self.blk_off[blk_tile]
@@ -174,14 +179,17 @@ class ObservationStore:
         cnt = torch.zeros((self.n_segments, 32), dtype=torch.int64, device=dev).index_add_(0, seg, bits)
         lane_base = torch.cumsum(cnt, dim=1) - cnt
         n_seg = cnt.sum(dim=1)
-        seg_cell = HC * torch.arange(self.n_segments, device=dev) + torch.cumsum(n_seg, 0) - n_seg
-        cell = seg_cell[seg][:, None] + HC + lane_base[seg] + k
+        seg_cell = HC * torch.arange(self.n_segments, device=dev) + RC * (torch.cumsum(n_seg, 0) - n_seg)
+        cell = seg_cell[seg][:, None] + HC + RC * (lane_base[seg] + k)
         b, lane = torch.nonzero(bits, as_tuple=True)
         return cell[b, lane], (blk_tile[b] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[b]
 
     def records(self) -> torch.Tensor:
-        """(n_obs, 4) the record cells (headers stripped)."""
-        return self.cells[self.record_index()[0]]
+        """(n_obs, 4) {z, I_r, I_g, I_b} of every record (headers stripped)."""
+        cell = self.record_index()[0]
+        if self.record_cells == 1:
+            return self.cells[cell]
+        return torch.cat([self.cells[cell][:, 3:4], self.cells[cell + 1][:, :3]], dim=1)
 
     def to_reference_layout(self) -> dict:
         """Per kept view (in source_keys order) the arrays the reference's MatchesFile/MatchesData hold
@@ -197,8 +205,12 @@ class ObservationStore:
             p = pixel[sel]
             rec = self.cells[cell[sel]].cpu().numpy()
             entry = dict(u1=(p % self.width).to(torch.int16).cpu().numpy(),
-                         v1=(p // self.width).to(torch.int16).cpu().numpy(),
-                         z=rec[:, 0].copy(), I=np.ascontiguousarray(rec[:, 1:4].T))
+                         v1=(p // self.width).to(torch.int16).cpu().numpy())
+            if self.record_cells == 1:
+                entry.update(z=rec[:, 0].copy(), I=np.ascontiguousarray(rec[:, 1:4].T))
+            else:
+                rec2 = self.cells[cell[sel] + 1].cpu().numpy()
+                entry.update(z=rec[:, 3].copy(), cP=np.ascontiguousarray(rec[:, :3].T), I=np.ascontiguousarray(rec2[:, :3].T))
             if self.cell_src is not None:
                 src = self.cell_src[cell[sel]].cpu().numpy().view(np.uint32)
                 entry['u2'] = (src & 0xffff).astype(np.int16)
@@ -213,15 +225,18 @@ def _stream(device) -> int:
 
 def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
            target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
-           reduce_counts=None) -> ObservationStore:
+           reduce_counts=None, with_points: bool = False) -> ObservationStore:
     """Stage 1 on the device: match -> count -> plan -> (one 16-byte D2H to size the store) -> sample.
     Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
     (sfm.py:127-138, loader.py:78-87, 103-118).
 
     tile_range = (first_tile, n_tiles) restricts the call to a band of the target (multi-GPU pixel sharding);
     reduce_counts(view_count) then sums the per-view match counts over all bands in place (an all-reduce), because
-    min_cover is a whole-image criterion (sfm.py:136)."""
+    min_cover is a whole-image criterion (sfm.py:136).
+    with_points: keep the camera-frame point cP of every observation (two-cell records), which the light model
+    needs (sucre.py:57); the default store keeps only its norm."""
     L = _lib.lib()
+    record_cells, seg_views = (2, _lib.LIGHT_SEG_VIEWS) if with_points else (1, _lib.seg_views())
     dev = scene.device
     source_keys = tuple(source_keys)
     V = len(source_keys)
@@ -248,10 +263,10 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
         if reduce_counts is not None:
             reduce_counts(view_count)
         _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), P, float(min_cover),
-                                       view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
+                                       seg_views, view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
                                        seg_off.data_ptr(), totals.data_ptr(), st), 'sucre_gather_plan')
         n_obs, n_blocks, n_segments = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
-        n_cells = n_obs + _lib.SEG_HEADER_CELLS * n_segments
+        n_cells = record_cells * n_obs + _lib.SEG_HEADER_CELLS * n_segments
         cells = torch.empty((max(n_cells, 1), 4), dtype=torch.float32, device=dev)
         blk_mask = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
         blk_view = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
@@ -262,7 +277,8 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
                 raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
             _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
                                              view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
-                                             seg_off.data_ptr(), cells.data_ptr(), blk_mask.data_ptr(),
+                                             seg_off.data_ptr(), seg_views, record_cells, cells.data_ptr(),
+                                             blk_mask.data_ptr(),
                                              blk_view.data_ptr(), 0 if cell_src is None else cell_src.data_ptr(), st),
                        'sucre_gather_sample')
         vc = view_count.cpu().numpy()
@@ -271,7 +287,7 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
                             n_blocks=n_blocks, n_segments=n_segments, cells=cells[:n_cells], rec_off=rec_off,
                             blk_off=blk_off, seg_off=seg_off, blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
                             cell_src=None if cell_src is None else cell_src[:n_cells], first_tile=first_tile,
-                            n_tiles=n_tiles)
+                            n_tiles=n_tiles, seg_views=seg_views, record_cells=record_cells)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -377,3 +393,30 @@ def closed_form_J(store: ObservationStore, params: torch.Tensor, J_ref: torch.Te
                                                 J.data_ptr(), _workspace(store).data_ptr(), _stream(dev)),
                    'sucre_fit_write_J')
     return J
+
+
+# ---- light model (sucre.py:44-46, 54-61) ----------------------------------------------------------------------
+def light_J(store: ObservationStore, params24: torch.Tensor) -> torch.Tensor:
+    """Closed-form J with the light terms for the 24 derived parameters (B, beta, gamma, R, t, Sigma^-1)."""
+    dev = store.cells.device
+    J = torch.empty(store.J_shape, dtype=torch.float32, device=dev)
+    if store.n_obs == 0:
+        return J.fill_(float('nan'))
+    with torch.cuda.device(dev):
+        cs = store.c_struct()
+        _lib.check(_lib.lib().sucre_light_J(C.byref(cs), params24.data_ptr(), J.data_ptr(), _stream(dev)), 'sucre_light_J')
+    return J
+
+
+def light_sums(store: ObservationStore, params24: torch.Tensor, J: torch.Tensor, sums: torch.Tensor,
+               J_moments: torch.Tensor | None = None, n_obs: int = 0, step: int = 0, lr: float = 0.05):
+    """One residual pass -> sums (25 doubles, device).  With J_moments, J takes its Adam step `step` in the same pass."""
+    dev = store.cells.device
+    if store.workspace is None:
+        store.workspace = torch.empty(_lib.lib().sucre_fit_workspace_bytes(), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cs = store.c_struct()
+        _lib.check(_lib.lib().sucre_light_sums(
+            _lib.FIT_PARAM_J if J_moments is not None else _lib.FIT_CLOSED_FORM, C.byref(cs), params24.data_ptr(),
+            J.data_ptr(), 0 if J_moments is None else J_moments.data_ptr(), n_obs, step, float(lr), sums.data_ptr(),
+            store.workspace.data_ptr(), _stream(dev)), 'sucre_light_sums')

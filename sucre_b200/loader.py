@@ -155,7 +155,8 @@ class MatchesFile:
                  n_obs=s.n_obs, cells=s.cells.cpu().numpy(), rec_off=s.rec_off.cpu().numpy(),
                  blk_off=s.blk_off.cpu().numpy(), seg_off=s.seg_off.cpu().numpy(), blk_mask=s.blk_mask.cpu().numpy(),
                  blk_view=s.blk_view.cpu().numpy(),
-                 cell_src=np.zeros(0, np.int32) if s.cell_src is None else s.cell_src.cpu().numpy())
+                 cell_src=np.zeros(0, np.int32) if s.cell_src is None else s.cell_src.cpu().numpy(),
+                 seg_views=s.seg_views, record_cells=s.record_cells)
         self.path.touch()  # the reference's file name marks "matches exist" (sucre.py:185)
 
     def unlink(self):
@@ -176,4 +177,5 @@ class MatchesFile:
             view_count=z['view_count'], view_kept=z['view_kept'], n_obs=int(z['n_obs']),
             n_blocks=int(z['blk_mask'].shape[0]), n_segments=int(z['seg_off'][-1]), cells=t(z['cells']),
             rec_off=t(z['rec_off']), blk_off=t(z['blk_off']), seg_off=t(z['seg_off']), blk_mask=t(z['blk_mask']),
-            blk_view=t(z['blk_view']), cell_src=t(z['cell_src']) if z['cell_src'].size else None)
+            blk_view=t(z['blk_view']), cell_src=t(z['cell_src']) if z['cell_src'].size else None,
+            seg_views=int(z['seg_views']), record_cells=int(z['record_cells']))

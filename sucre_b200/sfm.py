@@ -178,7 +178,8 @@ class Image:
         (loader.py:63-66, 106)."""
         scene = self.model.scene(device, [self] + list(image_list), num_workers=num_workers)
         ordered = sorted(image_list, key=lambda im: im.name)
-        store = gather(scene, self.id, [im.id for im in ordered], min_cover=min_cover, keep_src=True)
+        store = gather(scene, self.id, [im.id for im in ordered], min_cover=min_cover, keep_src=True,
+                       with_points=getattr(matches_file, 'with_points', False))
         matches_file.set_store(store, [im.name for im in ordered])
 
     def __repr__(self) -> str:

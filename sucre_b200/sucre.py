@@ -6,7 +6,7 @@ the gather and the fit as sm_100a CUDA kernels.
 Same flags, defaults and output files as the reference (sucre.py:264-307, 212-215).  Differences a user can see:
   * `--device` must be a CUDA device (there is no CPU path);
   * the matches file kept by `--keep-matches` is `<stem>.matches.npz` (+ an empty `<stem>.h5` marker), not HDF5;
-  * `--light-model` is not implemented and raises;
+  * with `--light-model` the ten light parameters are stepped on the host (one device->host read per iteration);
   * the per-iteration log lines are printed when the device loop returns, not while it runs.
 """
 from __future__ import annotations
@@ -20,7 +20,7 @@ from PIL import Image
 from torch import Tensor
 from tqdm import tqdm
 
-from . import engine, loader, sfm
+from . import engine, light, loader, se3, sfm
 
 
 class SUCRe:
@@ -30,8 +30,6 @@ class SUCRe:
     buffer); J is (H,W,3)."""
 
     def __init__(self, image: sfm.Image, light_model: bool = False, use_closed_form: bool = False):
-        if light_model:
-            raise NotImplementedError('--light-model (sucre.py:44-46, 54-61) is outside the CUDA hot path built so far')
         self.image = image
         self.light_model = light_model
         self.use_closed_form = use_closed_form
@@ -42,6 +40,9 @@ class SUCRe:
         self.state = engine.FitState.initial('cpu', J0=J0)
         self._J_closed: Tensor | None = None
         self.history: Tensor | None = None
+        if light_model:  # sucre.py:44-46; these ten scalars live on the host (see light.py)
+            self.cam2light = torch.zeros(6)
+            self.sigma = torch.eye(2)
 
     # -- parameters -------------------------------------------------------------------------------------------
     @property
@@ -81,6 +82,9 @@ class SUCRe:
 
     def state_dict(self) -> dict:
         sd = {'B': self.B.detach().clone(), 'beta': self.beta.detach().clone(), 'gamma': self.gamma.detach().clone()}
+        if self.light_model:
+            sd['cam2light'] = self.cam2light.detach().clone()
+            sd['sigma'] = self.sigma.detach().clone()
         if not self.use_closed_form:
             sd['J'] = self.J.detach().clone()
         return sd
@@ -92,17 +96,38 @@ class SUCRe:
                 self.state.params[known[key]:known[key] + 3] = torch.as_tensor(value, dtype=torch.float32).reshape(3).to(self.device)
             elif key == 'J' and not self.use_closed_form:
                 self.state.J = torch.as_tensor(value, dtype=torch.float32).to(self.device).contiguous()
+            elif key in ('cam2light', 'sigma') and self.light_model:
+                setattr(self, key, torch.as_tensor(value, dtype=torch.float32).cpu().clone())
             elif strict:
                 raise KeyError(f'unexpected key {key!r} in state_dict')
 
     # -- model ------------------------------------------------------------------------------------------------
-    def compute_l_z(self, cP: Tensor) -> tuple[float, Tensor]:
-        return 1.0, cP.norm(dim=0)  # sucre.py:53,63 without the light model
+    def compute_l_z(self, cP: Tensor) -> tuple[float | Tensor, Tensor]:
+        """sucre.py:52-64 (torch ops; used by the plots, the fit evaluates this inside its kernels)."""
+        z = cP.norm(dim=0)
+        if not self.light_model:
+            return 1.0, z
+        R, t = se3.exp(self.cam2light)
+        Sigma = self.sigma.T @ self.sigma
+        lP = R.to(cP.device) @ cP + t.to(cP.device)
+        lp = (lP[:2] / lP[2]).T.unsqueeze(dim=2)
+        l = torch.exp(-torch.flatten(lp.transpose(1, 2) @ Sigma.inverse().to(cP.device) @ lp) / 2)
+        return l, z + lP.norm(dim=0)
+
+    def _light_params24(self) -> Tensor:
+        return light.derive(self.B.cpu(), self.beta.cpu(), self.gamma.cpu(), self.cam2light, self.sigma).to(self.device)
 
     @torch.no_grad()
     def update_J(self, matches_data: loader.MatchesData, force_update: bool = False):
         """Closed-form J from the current B, beta, gamma (sucre.py:66-77) — one CUDA kernel over the store."""
-        if self.use_closed_form:
+        if self.light_model:
+            if self.use_closed_form or force_update:
+                J = engine.light_J(matches_data.store, self._light_params24())
+                if self.use_closed_form:
+                    self._J_closed = J
+                else:
+                    self.state.J = J
+        elif self.use_closed_form:
             self._J_closed = engine.closed_form_J(matches_data.store, self.state.params, self.state.J)
         elif force_update:
             self.state.J = engine.closed_form_J(matches_data.store, self.state.params, None)
@@ -140,11 +165,43 @@ class SUCRe:
         I_rec[v, u] = self(u=u, v=v, cP=cP).clip(0, 1).T
         return Image.fromarray(np.uint8(I_rec.cpu().numpy() * 255))
 
+    @torch.no_grad()
+    def plot_l(self) -> Image.Image:
+        """Vignetting map of the light model, jet-coloured (sucre.py:96-104)."""
+        dev = self.device
+        depth = (self.image.get_depth_u16().to(torch.int32).to(dev).to(torch.float32) / 1000.0)
+        v, u = torch.where(depth > 0)
+        cp = torch.stack([u + 0.5, v + 0.5, torch.ones_like(u)])
+        cP = self.image.geom.Kinv.to(dev) @ (depth[v, u] * cp)
+        l, _ = self.compute_l_z(cP)
+        l_map = torch.zeros((self.image.camera.height, self.image.camera.width), device=dev)
+        l_map[v, u] = l
+        return Image.fromarray(np.uint8(_jet(l_map.cpu().numpy())[:, :, :3] * 255))
+
     def save_plots(self, save_dir: Path, iteration: int = None):
         save_path = (save_dir / self.image.name).with_suffix('.png')
         suffix = '' if iteration is None else f'_{iteration:04d}'
         self.plot_J().save(save_path.with_stem(f'{save_path.stem}_rgb{suffix}'))
         self.plot_reconstruction().save(save_path.with_stem(f'{save_path.stem}_reconstruction{suffix}'))
+        if self.light_model:
+            self.plot_l().save(save_path.with_stem(f'{save_path.stem}_vignetting{suffix}'))
+
+
+def _jet(x: np.ndarray) -> np.ndarray:
+    """RGBA of matplotlib's 'jet' colormap (256-entry table from its published anchor points); matplotlib itself is
+    used when it is installed."""
+    try:
+        import matplotlib.pyplot as plt
+        return plt.colormaps['jet'](x)
+    except ImportError:
+        pass
+    anchors = {'r': [(0, 0), (0.35, 0), (0.66, 1), (0.89, 1), (1, 0.5)],
+               'g': [(0, 0), (0.125, 0), (0.375, 1), (0.64, 1), (0.91, 0), (1, 0)],
+               'b': [(0, 0.5), (0.11, 1), (0.34, 1), (0.65, 0), (1, 0)]}
+    grid = np.linspace(0, 1, 256)
+    lut = np.stack([np.interp(grid, *zip(*anchors[c])) for c in 'rgb'] + [np.ones(256)], axis=1)
+    idx = np.clip((np.nan_to_num(np.asarray(x, dtype=np.float64)) * 256).astype(np.int64), 0, 255)
+    return lut[idx]
 
 
 def _log_history(history: np.ndarray, first_iteration: int):
@@ -169,6 +226,8 @@ def adam(
     optimizer.step()), so it has no effect here: every iteration streams the whole store once."""
     print(f'Solve least squares with Adam optimizer ({num_iter} iterations).')
     store = matches_data.store
+    if sucre.light_model:
+        return _adam_light(sucre, matches_data, lr, num_iter, save_dir, save_interval)
     # iterations after whose step the reference saves intermediate plots (sucre.py:153-154): it % save_interval == 0
     plot_its = list(range(0, num_iter, save_interval)) if save_dir is not None and save_interval else []
     histories = []
@@ -190,6 +249,49 @@ def adam(
     if sucre.history is not None:
         _log_history(sucre.history.cpu().numpy(), 0)
     sucre.update_J(matches_data=matches_data)  # sucre.py:156 (a no-op in the default mode, like the reference)
+    return sucre
+
+
+def _adam_light(sucre: SUCRe, matches_data: loader.MatchesData, lr: float, num_iter: int, save_dir, save_interval):
+    """adam() with the light model: kernels for everything per-pixel, torch.optim.Adam on the 19 host scalars."""
+    store = matches_data.store
+    if store.record_cells != 2:
+        raise engine._lib.SucreError('the light model needs matches computed with camera-frame points; rerun with '
+                                     '--force-compute-matches')
+    dev = sucre.device
+    names = ('B', 'beta', 'gamma', 'cam2light', 'sigma')
+    params = {'B': sucre.B.cpu().clone(), 'beta': sucre.beta.cpu().clone(), 'gamma': sucre.gamma.cpu().clone(),
+              'cam2light': sucre.cam2light.clone(), 'sigma': sucre.sigma.clone()}
+    for p in params.values():
+        p.requires_grad_(True)
+    optimizer = torch.optim.Adam([params[k] for k in names], lr=lr)
+
+    def sync_back():
+        with torch.no_grad():
+            sucre.state.params.copy_(torch.cat([params[k].flatten() for k in names[:3]]).to(dev))
+            sucre.cam2light, sucre.sigma = params['cam2light'].detach().clone(), params['sigma'].detach().clone()
+
+    plot_its = list(range(0, num_iter, save_interval)) if save_dir is not None and save_interval else []
+    histories, done = [], 0
+    J = None if sucre.use_closed_form else sucre.state.J
+    for it in plot_its + [None]:
+        end = num_iter if it is None else it + 1
+        if end > done:
+            h, J = light.fit(store, params, J, None if sucre.use_closed_form else sucre.state.J_moments, end - done, lr,
+                             optimizer, first_step=done + 1)
+            histories.append(h)
+            done = end
+        sync_back()
+        if sucre.use_closed_form:
+            sucre._J_closed = J
+        if it is not None:
+            sucre.save_plots(save_dir=save_dir, iteration=it)
+    sucre.history = torch.cat(histories) if histories else None
+    if sucre.history is not None:
+        for k, row in enumerate(sucre.history.numpy()):
+            with np.printoptions(precision=4):
+                tqdm.write(f'iter: {k:04d}, cost: {row[19]:.4e}, B: {row[0:3]}, beta: {row[3:6]}, gamma: {row[6:9]}')
+    sucre.update_J(matches_data=matches_data)  # sucre.py:156
     return sucre
 
 
@@ -219,6 +321,7 @@ def restore_image(
     if image_list is None:
         image_list = list(colmap_model.images.values())
 
+    matches_file.with_points = light_model  # the light model needs cP, not only its norm (sucre.py:57)
     if force_compute_matches or not matches_file.exists():
         print(f'Compute {image.name} matches.')
         image.match_images(image_list=image_list, matches_file=matches_file, min_cover=min_cover,

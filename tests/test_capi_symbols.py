@@ -30,7 +30,7 @@ def test_view_struct_layout_matches_header():
 
 def test_argument_errors_without_gpu():
     L = _lib.lib()
-    assert L.sucre_gather_plan(0, 1, 1, 0, 1, 0.0, 0, 0, 0, 0, 0, 0) != 0
+    assert L.sucre_gather_plan(0, 1, 1, 0, 1, 0.0, 15, 0, 0, 0, 0, 0, 0) != 0
     assert b'null' in L.sucre_last_error()
     assert L.sucre_adam_step(0, 0, 0, 1, 1, 0.05, 0, 0) != 0
 

@@ -42,10 +42,10 @@ mn, av, _ = timed(lambda: L.sucre_gather_match(trec.ctypes.data, table.data_ptr(
 print(f'  match kernel: min {mn:.3f} ms avg {av:.3f}')
 vc = torch.empty(V, dtype=torch.int64, device='cuda'); vk = torch.empty(V, dtype=torch.uint8, device='cuda')
 ro, bo, so = (torch.empty(nt + 1, dtype=torch.int64, device='cuda') for _ in range(3)); tot = torch.empty(3, dtype=torch.int64, device='cuda')
-mn, av, _ = timed(lambda: (L.sucre_gather_count(masks.data_ptr(), nt, V, vc.data_ptr(), st), L.sucre_gather_plan(masks.data_ptr(), nt, V, vc.data_ptr(), W * H, 1e-6, vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), so.data_ptr(), tot.data_ptr(), st)))
+mn, av, _ = timed(lambda: (L.sucre_gather_count(masks.data_ptr(), nt, V, vc.data_ptr(), st), L.sucre_gather_plan(masks.data_ptr(), nt, V, vc.data_ptr(), W * H, 1e-6, store.seg_views, vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), so.data_ptr(), tot.data_ptr(), st)))
 print(f'  plan kernels: min {mn:.3f} ms avg {av:.3f}')
 cells = torch.empty_like(store.cells); bm = torch.empty(store.n_blocks, dtype=torch.int32, device='cuda'); bv = torch.empty_like(bm)
-mn, av, _ = timed(lambda: L.sucre_gather_sample(trec.ctypes.data, table.data_ptr(), V, 0, nt, masks.data_ptr(), vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), so.data_ptr(), cells.data_ptr(), bm.data_ptr(), bv.data_ptr(), 0, st))
+mn, av, _ = timed(lambda: L.sucre_gather_sample(trec.ctypes.data, table.data_ptr(), V, 0, nt, masks.data_ptr(), vk.data_ptr(), ro.data_ptr(), bo.data_ptr(), so.data_ptr(), store.seg_views, 1, cells.data_ptr(), bm.data_ptr(), bv.data_ptr(), 0, st))
 print(f'  sample kernel: min {mn:.3f} ms avg {av:.3f}  ({store.n_obs*16/mn/1e6:.0f} GB/s of records; {store.n_segments} segments)')
 
 def fit():
