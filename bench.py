@@ -41,6 +41,9 @@ def parse():
     ap.add_argument('--cpu-sample-views', type=int, default=4)
     ap.add_argument('--cpu-sample-iters', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='targets', choices=['targets', 'pixels', 'pixels-nccl'],
+                    help='N > 1: one target per rank (weak scaling, default) or ONE target sharded by pixel band over all '
+                         'ranks (strong scaling; all-reduce fused into the fit kernel over NVLink, or through NCCL)')
     return ap.parse_args()
 
 
@@ -255,6 +258,9 @@ def ours(args):
     def step_host(_):
         return api.restore_from_host(host, target, keys, device=dev, **kw)
 
+    if args.shard != 'targets' and world > 1:
+        return ours_pixel_sharded(args, resident, keys, dev, world, rank, local, run_steps, host)
+
     run_steps(step_resident, max(3, args.warmup))
     sampler = ClockSampler(local) if rank == 0 else None
     fit_events = []
@@ -301,6 +307,41 @@ def ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ours_pixel_sharded(args, resident, keys, dev, world, rank, local, run_steps, host):
+    """Strong scaling: every step restores ONE target whose pixel bands are spread over all ranks (config 4 style)."""
+    import torch
+    import torch.distributed as dist
+    from sucre_b200 import dist as sdist
+    target = default_target(args)
+    peers = sdist.PeerExchange(dev) if args.shard == 'pixels' else None
+
+    def step(_):
+        ops = sdist.CudaBandOps(resident, target, keys, use_closed_form=True)
+        return sdist.restore_band_sharded(ops, min_cover=1e-6, num_iter=args.num_iter, lr=0.05, peers=peers)
+
+    run_steps(step, max(3, args.warmup))
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, res = run_steps(step, args.steps)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        V, W, H = args.views, args.width, args.height
+        print(json.dumps({
+            'metric': METRIC, 'value': V * W * H / (ms / args.steps / 1e3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {**workload(args), 'parallelism': f'one target, pixel bands over {world} ranks, scene replicated; '
+                       + ('all-reduce fused into fit_kernel over NVLink peer memory' if peers else 'NCCL all-reduce per iteration'),
+                       'observations': res.n_obs},
+            's_per_restored_image': ms / args.steps / 1e3, 'gpu_launches': args.steps * (api_launches(args) if peers else 0),
+            'clocks': clocks}))
+    dist.destroy_process_group()
+
+
+def api_launches(args):
+    from sucre_b200 import api
+    return api.LAUNCHES_FIXED + args.num_iter
 
 
 if __name__ == '__main__':

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 4
+#define SUCRE_ABI_VERSION 5
 #define SUCRE_TILE_PIXELS 32
 #ifndef SUCRE_SEGMENT_VIEWS
 #define SUCRE_SEGMENT_VIEWS 15
@@ -170,6 +170,20 @@ int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_
 int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
               float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
               void* stream);
+
+/* The same loop for ONE target whose tiles are sharded over `world` GPUs (store_host = this rank's band, n_obs_global
+ * = observations of all bands): the all-reduce of the 10 sums is fused into the kernel — the last CTA of every rank
+ * stores its sums into every peer's exchange buffer over NVLink (peers_host[p] = device address of rank p's buffer,
+ * SUCRE_PEER_BUFFER_BYTES each, zeroed once, mapped into this process, e.g. torch symmetric memory), waits for all
+ * ranks' tags and adds the rows in rank order, so every rank applies the identical Adam step with no host or NCCL
+ * round trip.  first_epoch: a tag >= 1 for the first iteration, identical on all ranks, and increasing by num_iter
+ * from one call on the same buffers to the next.  All ranks must make the same sequence of calls. */
+#define SUCRE_MAX_PEERS 16
+#define SUCRE_PEER_BUFFER_BYTES 3072
+int sucre_fit_sharded(int mode, const sucre_store* store_host, int64_t n_obs_global, float* params, float* adam_state,
+                      float* J, float* J_moments, int first_step, int num_iter, double lr, float* history,
+                      void* workspace, const uint64_t* peers_host, int rank, int world, uint32_t first_epoch,
+                      void* stream);
 
 /* Closed-form J for the current params written to J[pixels*3]; NaN where a pixel has no observation (0/0 like
  * sucre.py:77).  J_ref (optional): a previous J used as the reference point of the statistics. */

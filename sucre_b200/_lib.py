@@ -9,7 +9,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 4
+ABI_VERSION = 5
 TILE = 32
 SEG_HEADER_CELLS = 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
@@ -34,6 +34,7 @@ class SucreStore(C.Structure):
 
 
 assert C.sizeof(SucreStore) == 56
+MAX_PEERS, PEER_BUFFER_BYTES = 16, 3072
 LIGHT_SEG_VIEWS = 7   # two-cell records: 2 + 2*32*7 = 450 cells per segment at most
 
 
@@ -53,6 +54,7 @@ _SIGNATURES = {
     'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
     'sucre_adam_step': (C.c_int, [_VP, _VP, _VP, _I64, _I, _D, _VP, _VP]),
     'sucre_fit': (C.c_int, [_I, _VP, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
+    'sucre_fit_sharded': (C.c_int, [_I, _VP, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP, _I, _I, C.c_uint32, _VP]),
     'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     'sucre_light_J': (C.c_int, [_VP, _VP, _VP, _VP]),
     'sucre_light_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),

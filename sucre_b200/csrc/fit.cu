@@ -240,7 +240,29 @@ struct FitArgs {
     float* history_row;    // if non-null: params after the step + cost
     int do_step;           // apply Adam to the 9 scalars in the last CTA
     AdamScalars adam;
+    // pixel-band sharding over several GPUs: one-shot all-reduce of the 10 sums over NVLink peer memory, fused
+    // into the last CTA (world == 1: single GPU, nothing exchanged)
+    int rank, world;
+    unsigned epoch;                           // unique, increasing tag of this launch on every rank
+    unsigned long long peer[SUCRE_MAX_PEERS]; // peer[p] = address of rank p's exchange buffer (PeerSlot[2][SUCRE_MAX_PEERS])
 };
+
+// what rank r leaves in every peer's buffer at [epoch & 1][r]
+struct PeerSlot {
+    double sums[kSums];
+    unsigned flag;
+    unsigned pad[3];
+};
+static_assert(sizeof(PeerSlot) == 96 && sizeof(PeerSlot) * 2 * SUCRE_MAX_PEERS == SUCRE_PEER_BUFFER_BYTES, "peer buffer layout");
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int MODE, bool PRECISE>
 __global__ void __launch_bounds__(kFitThreads, SUCRE_FIT_CTAS)
@@ -466,6 +488,33 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         if (lane == 0) tot[col] = v;
     }
     __syncthreads();
+    if (A.world > 1) {
+        // One-shot all-reduce over NVLink: every rank stores its 10 sums into every peer's buffer (slot [epoch&1]
+        // [rank]), publishes them with a system-scope release of the epoch tag, waits for the tags of all ranks in
+        // its own buffer, and adds the rows in rank order — the same order on every rank, so all ranks take the
+        // identical Adam step without any host or NCCL round trip.  Two parities: a rank can be at most one
+        // launch ahead of the slowest reader of its previous message.
+        const unsigned par = A.epoch & 1u;
+        if (threadIdx.x < A.world * kSums) {
+            const int p = threadIdx.x / kSums, i = threadIdx.x % kSums;
+            PeerSlot* dst = reinterpret_cast<PeerSlot*>(A.peer[p]) + par * SUCRE_MAX_PEERS + A.rank;
+            dst->sums[i] = tot[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        PeerSlot* mine = reinterpret_cast<PeerSlot*>(A.peer[A.rank]) + par * SUCRE_MAX_PEERS;
+        if (threadIdx.x < A.world) {
+            st_release_sys(&(reinterpret_cast<PeerSlot*>(A.peer[threadIdx.x]) + par * SUCRE_MAX_PEERS + A.rank)->flag, A.epoch);
+            while (ld_acquire_sys(&mine[threadIdx.x].flag) != A.epoch) __nanosleep(64);
+        }
+        __syncthreads();
+        if (threadIdx.x < kSums) {
+            double v = 0.0;
+            for (int p = 0; p < A.world; ++p) v += *reinterpret_cast<volatile double*>(&mine[p].sums[threadIdx.x]);
+            tot[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x < kSums && A.sums_out) A.sums_out[threadIdx.x] = tot[threadIdx.x];
     if (A.do_step && threadIdx.x < 9) {
         const int i = threadIdx.x;
@@ -594,6 +643,8 @@ static FitArgs base_args(const sucre_store* s, void* workspace) {
     a.partials = (double*)(ws + kWsPartials);
     a.partition = (const int*)(ws + kWsPartition);
     a.ticket = (unsigned*)(ws + kWsTicket);
+    a.rank = 0;
+    a.world = 1;
     return a;
 }
 
@@ -643,28 +694,54 @@ extern "C" int sucre_adam_step(float* params, float* adam_state, const double* s
     return check_launch("adam_step_kernel");
 }
 
-extern "C" int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
-                         float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
-                         void* stream) {
+static int fit_loop(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
+                    float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
+                    const uint64_t* peers_host, int rank, int world, uint32_t first_epoch, void* stream, const char* who) {
     clear_error();
-    if (check_store(store_host, "sucre_fit")) return 1;
-    SUCRE_REQUIRE(params && adam_state && J && workspace, "sucre_fit: null pointer");
-    SUCRE_REQUIRE(mode == kClosedForm || (mode == kParamJ && J_moments), "sucre_fit: bad mode %d", mode);
-    SUCRE_REQUIRE(n_obs > 0 && first_step >= 1 && num_iter >= 0, "sucre_fit: bad n_obs/first_step/num_iter");
+    if (check_store(store_host, who)) return 1;
+    SUCRE_REQUIRE(params && adam_state && J && workspace, "%s: null pointer", who);
+    SUCRE_REQUIRE(mode == kClosedForm || (mode == kParamJ && J_moments), "%s: bad mode %d", who, mode);
+    SUCRE_REQUIRE(n_obs > 0 && first_step >= 1 && num_iter >= 0, "%s: bad n_obs/first_step/num_iter", who);
     FitArgs a = base_args(store_host, workspace);
     a.params = params;
     a.moments = adam_state;
     a.J = J;
     a.J_moments = J_moments;
     a.do_step = 1;
+    if (world > 1) {
+        SUCRE_REQUIRE(peers_host && world <= SUCRE_MAX_PEERS && rank >= 0 && rank < world, "%s: bad peer arguments", who);
+        a.rank = rank;
+        a.world = world;
+        for (int p = 0; p < world; ++p) {
+            SUCRE_REQUIRE(peers_host[p] != 0 && (peers_host[p] & 15) == 0, "%s: peer buffer %d null or misaligned", who, p);
+            a.peer[p] = peers_host[p];
+        }
+    }
     const int ctas = fit_grid();
     for (int it = 0; it < num_iter; ++it) {
         a.adam = adam_scalars(first_step + it, lr, n_obs);
         a.history_row = history ? history + (size_t)it * kSums : nullptr;
+        a.epoch = first_epoch + (uint32_t)it;
         if (mode == kClosedForm) launch_fit<kClosedForm>(a, ctas, (cudaStream_t)stream, it > 0);
         else launch_fit<kParamJ>(a, ctas, (cudaStream_t)stream, it > 0);
     }
-    return check_launch("sucre_fit kernels");
+    return check_launch(who);
+}
+
+extern "C" int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
+                         float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
+                         void* stream) {
+    return fit_loop(mode, store_host, n_obs, params, adam_state, J, J_moments, first_step, num_iter, lr, history, workspace,
+                    nullptr, 0, 1, 0, stream, "sucre_fit");
+}
+
+extern "C" int sucre_fit_sharded(int mode, const sucre_store* store_host, int64_t n_obs_global, float* params,
+                                 float* adam_state, float* J, float* J_moments, int first_step, int num_iter, double lr,
+                                 float* history, void* workspace, const uint64_t* peers_host, int rank, int world,
+                                 uint32_t first_epoch, void* stream) {
+    SUCRE_REQUIRE(first_epoch != 0, "sucre_fit_sharded: epochs start at 1 (0 is the cleared state of a peer buffer)");
+    return fit_loop(mode, store_host, n_obs_global, params, adam_state, J, J_moments, first_step, num_iter, lr, history,
+                    workspace, peers_host, rank, world, first_epoch, stream, "sucre_fit_sharded");
 }
 
 extern "C" int sucre_fit_write_J(const sucre_store* store_host, const float* params, const float* J_ref, float* J,

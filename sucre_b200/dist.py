@@ -20,7 +20,7 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
-from . import engine
+from . import _lib, engine
 from ._lib import TILE
 
 
@@ -34,6 +34,33 @@ def tile_band(n_tiles_total: int, rank: int, world: int) -> tuple[int, int]:
     lo = n_tiles_total * rank // world
     hi = n_tiles_total * (rank + 1) // world
     return lo, hi - lo
+
+
+class PeerExchange:
+    """Exchange buffers for the in-kernel all-reduce of sucre_fit_sharded: one SUCRE_PEER_BUFFER_BYTES buffer per rank
+    in torch symmetric memory, so that every rank holds a device pointer to every peer's buffer (NVLink / NVSwitch
+    peer access).  Also hands out the epoch tags, which must advance identically on all ranks."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.buffer = symm_mem.empty(_lib.PEER_BUFFER_BYTES // 4, dtype=torch.int32, device=device)
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, group)
+        self.rank, self.world = self.handle.rank, self.handle.world_size
+        if self.world > _lib.MAX_PEERS:
+            raise engine._lib.SucreError(f'at most {_lib.MAX_PEERS} ranks per sharded target')
+        self.buffer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._epoch = 1
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every buffer is zeroed before anybody writes into a peer
+
+    def take_epochs(self, n: int) -> int:
+        first = self._epoch
+        self._epoch += n
+        if self._epoch >= 2 ** 32:
+            raise engine._lib.SucreError('epoch counter exhausted; create a new PeerExchange')
+        return first
 
 
 @dataclass
@@ -87,6 +114,10 @@ class CudaBandOps:
     def adam_step(self, sums, n_obs_global, lr, history_row):
         engine.adam_step(self.state, sums, n_obs_global, lr, history_row)
 
+    def fused_fit(self, peers: 'PeerExchange', n_obs_global: int, num_iter: int, lr: float):
+        """The whole Adam loop as one kernel per iteration with the all-reduce fused in (sucre_fit_sharded)."""
+        return engine.fit(self.store, self.state, num_iter, lr, peers=peers, n_obs_global=n_obs_global)
+
     def new_history(self, num_iter):
         return torch.empty((num_iter, 10), dtype=torch.float32, device=self.device)
 
@@ -101,9 +132,11 @@ class CudaBandOps:
 
 
 def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, lr: float = 0.05, params=None,
-                         group=None) -> BandResult:
+                         group=None, peers: PeerExchange | None = None) -> BandResult:
     """One target restored by all ranks of `group`, each owning a band of its pixels.  Every rank returns the same
-    parameters and the full J.  `ops` is a CudaBandOps (or a stand-in with the same methods)."""
+    parameters and the full J.  `ops` is a CudaBandOps (or a stand-in with the same methods).
+    With `peers` (and a CudaBandOps) the per-iteration all-reduce runs inside the fit kernel over NVLink peer memory;
+    without, it is an NCCL / gloo all-reduce between a sums kernel and a step kernel."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     P = ops.width * ops.height
@@ -124,12 +157,15 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
 
     # 2. Adam loop: local sums -> all-reduce(10 doubles) -> identical step on every rank
     ops.init_state(params)
-    sums = ops.new_sums()
-    history = ops.new_history(num_iter)
-    for it in range(num_iter):
-        ops.fit_sums(sums, n_obs, lr)
-        all_reduce(sums)
-        ops.adam_step(sums, n_obs, lr, history[it])
+    if peers is not None and world > 1 and hasattr(ops, 'fused_fit'):
+        history = ops.fused_fit(peers, n_obs, num_iter, lr)
+    else:
+        sums = ops.new_sums()
+        history = ops.new_history(num_iter)
+        for it in range(num_iter):
+            ops.fit_sums(sums, n_obs, lr)
+            all_reduce(sums)
+            ops.adam_step(sums, n_obs, lr, history[it])
 
     # 3. assemble J: bands differ by at most one tile, pad to the longest
     local = ops.band_J()

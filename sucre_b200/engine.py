@@ -336,20 +336,32 @@ def _workspace(store: ObservationStore) -> torch.Tensor:
     return store.workspace
 
 
-def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05) -> torch.Tensor:
+def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.05, peers=None,
+        n_obs_global: int | None = None) -> torch.Tensor:
     """num_iter iterations of adam() (sucre.py:138-148) entirely on the device, in the mode `state` was created
-    for.  Returns the (num_iter, 10) history tensor {params after each step, cost before it} (device)."""
-    if store.n_obs == 0:
+    for.  Returns the (num_iter, 10) history tensor {params after each step, cost before it} (device).
+    peers (a dist.PeerExchange): `store` is this rank's band of a target sharded over several GPUs; the all-reduce
+    of the sums is then fused into the kernel over NVLink peer memory and n_obs_global is the all-band count."""
+    if store.n_obs == 0 and peers is None:
         raise _lib.SucreError('fit: the observation store is empty')
     dev = store.cells.device
     state.ensure_J(store)
     history = torch.empty((num_iter, 10), dtype=torch.float32, device=dev)
+    jm = 0 if state.J_moments is None else state.J_moments.data_ptr()
     with torch.cuda.device(dev):
         cs = store.c_struct()
-        _lib.check(_lib.lib().sucre_fit(
-            state.mode, C.byref(cs), store.n_obs, state.params.data_ptr(), state.moments.data_ptr(),
-            state.J.data_ptr(), 0 if state.J_moments is None else state.J_moments.data_ptr(), state.step + 1, num_iter,
-            float(lr), history.data_ptr(), _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit')
+        if peers is None:
+            _lib.check(_lib.lib().sucre_fit(
+                state.mode, C.byref(cs), store.n_obs, state.params.data_ptr(), state.moments.data_ptr(),
+                state.J.data_ptr(), jm, state.step + 1, num_iter, float(lr), history.data_ptr(),
+                _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit')
+        else:
+            ptrs = (C.c_uint64 * peers.world)(*peers.buffer_ptrs)
+            _lib.check(_lib.lib().sucre_fit_sharded(
+                state.mode, C.byref(cs), int(n_obs_global), state.params.data_ptr(), state.moments.data_ptr(),
+                state.J.data_ptr(), jm, state.step + 1, num_iter, float(lr), history.data_ptr(),
+                _workspace(store).data_ptr(), ptrs, peers.rank, peers.world, peers.take_epochs(num_iter), _stream(dev)),
+                'sucre_fit_sharded')
     state.step += num_iter
     return history
 

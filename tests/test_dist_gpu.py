@@ -62,7 +62,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, closed_form, out_path):
+def _nccl_worker(rank, world, port, closed_form, out_path, fused=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -70,7 +70,12 @@ def _nccl_worker(rank, world, port, closed_form, out_path):
         scene = SyntheticScene(8, 320, 240, seed=11)
         ds, _ = helpers.build_device_scene(scene, range(8), device=f'cuda:{rank}')
         ops = sdist.CudaBandOps(ds, 4, list(range(8)), use_closed_form=closed_form)
-        res = sdist.restore_band_sharded(ops, num_iter=25)
+        peers = sdist.PeerExchange(ds.device) if fused else None
+        res = sdist.restore_band_sharded(ops, num_iter=25, peers=peers)
+        if fused:  # a second target on the same exchange buffers: epochs keep advancing
+            ops2 = sdist.CudaBandOps(ds, 3, list(range(8)), use_closed_form=closed_form)
+            res2 = sdist.restore_band_sharded(ops2, num_iter=5, peers=peers)
+            assert torch.isfinite(res2.params).all()
         if rank == 0:
             np.savez(out_path, J=res.J.cpu().numpy(), params=res.params.cpu().numpy(), history=res.history.cpu().numpy(),
                      n_obs=res.n_obs)
@@ -79,12 +84,14 @@ def _nccl_worker(rank, world, port, closed_form, out_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-@pytest.mark.parametrize('closed_form', [True, False])
-def test_band_sharded_nccl_matches_single_gpu(closed_form):
+@pytest.mark.parametrize('closed_form,fused', [(True, False), (False, False), (True, True), (False, True)])
+def test_band_sharded_matches_single_gpu(closed_form, fused):
+    """fused=False: NCCL all-reduce between kernels; fused=True: all-reduce inside the fit kernel over NVLink peer
+    memory (sucre_fit_sharded)."""
     world = min(4, torch.cuda.device_count())
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, 'res.npz')
-        mp.spawn(_nccl_worker, args=(world, _free_port(), closed_form, out), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, _free_port(), closed_form, out, fused), nprocs=world, join=True)
         z = np.load(out)
     scene = SyntheticScene(8, 320, 240, seed=11)
     ds, _ = helpers.build_device_scene(scene, range(8))
