@@ -265,10 +265,10 @@ def ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     fit_events = []
     ms_res, res = run_steps(step_resident, args.steps, fit_events)
-    clocks = sampler.stop() if sampler else None
     fit_ms = [a.elapsed_time(b) for a, b in fit_events]
     run_steps(step_host, 1)
     ms_e2e, res_h = run_steps(step_host, args.steps)
+    clocks = sampler.stop() if sampler else None          # sampled across both timed regions (resident + end to end)
 
     pv_per_step = V * W * H * world                      # pixel-views all ranks process per step
     n_obs = res.n_obs
