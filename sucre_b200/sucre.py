@@ -11,7 +11,6 @@ Same flags, defaults and output files as the reference (sucre.py:264-307, 212-21
 """
 from __future__ import annotations
 
-import argparse
 from pathlib import Path
 
 import numpy as np
@@ -356,76 +355,7 @@ def restore_image(
     return None
 
 
-def parse_args(args: argparse.Namespace):
-    print('Loading COLMAP model.')
-    colmap_model = sfm.COLMAPModel(model_dir=args.model_dir, image_dir=args.image_dir, depth_dir=args.depth_dir,
-                                   image_scale=args.image_scale)
-
-    if args.image_name is not None:
-        images = [colmap_model[args.image_name]]
-    elif args.image_list is not None:
-        images = [colmap_model[image_name] for image_name in args.image_list.read_text().splitlines()]
-    else:
-        images = [colmap_model.images[image_id] for image_id in range(*args.image_ids)
-                  if image_id in colmap_model.images]
-
-    # Filter images that should not be used for pairing (sucre.py:237-239)
-    filter_image_names = args.filter_images_path.read_text().splitlines() if args.filter_images_path else []
-    image_list = [im for im in colmap_model.images.values() if im.name not in filter_image_names]
-
-    args.output_dir.mkdir(parents=True, exist_ok=True)
-
-    for image in images:
-        restore_image(
-            image=image, colmap_model=colmap_model, output_dir=args.output_dir, light_model=args.light_model,
-            use_closed_form=args.use_closed_form, min_cover=args.min_cover, image_list=image_list,
-            lr=args.learning_rate, num_iter=args.num_iter, batch_size=args.batch_size,
-            save_interval=args.save_interval, params_path=args.params_path,
-            force_compute_matches=args.force_compute_matches, keep_matches=args.keep_matches,
-            num_workers=args.num_workers, device=args.device)
-
-
-def build_parser() -> argparse.ArgumentParser:
-    """Flag-for-flag the reference's parser (sucre.py:265-305)."""
-    parser = argparse.ArgumentParser(description='SUCRe.', formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    parser.add_argument('--image-dir', required=True, type=Path, help='path to images directory.')
-    parser.add_argument('--depth-dir', required=True, type=Path, help='path to depth maps directory.')
-    parser.add_argument('--model-dir', required=True, type=Path, help='path to undistorted COLMAP model directory.')
-    parser.add_argument('--output-dir', required=True, type=Path, help='path to output directory.')
-    parser_images = parser.add_mutually_exclusive_group(required=True)
-    parser_images.add_argument('--image-name', type=str, help='name of image to restore.')
-    parser_images.add_argument('--image-list', type=Path,
-                               help='path to .txt file with names of images to restore, one name per line.')
-    parser_images.add_argument('--image-ids', type=int, nargs=2, metavar=('MIN_ID', 'MAX_ID'),
-                               help='range of ids of images to restore in the COLMAP model [min, max).')
-    parser.add_argument('--light-model', action='store_true', help='model artificial lights.')
-    parser.add_argument('--use-closed-form', action='store_true',
-                        help='use the partial closed-form solution for computing the restored image from '
-                             'absorption, backscatter and light parameters.')
-    parser.add_argument('--min-cover', type=float, default=0.000001,
-                        help='minimum percentile of shared observations to keep the pairs of an image.')
-    parser.add_argument('--image-scale', type=float, default=1.0, help='rescale all images by this factor.')
-    parser.add_argument('--filter-images-path', type=Path,
-                        help='path to a .txt file with names of images to discard when computing matches, '
-                             'one name per line.')
-    parser.add_argument('--learning-rate', type=float, default=0.05, help='learning rate for Adam optimizer.')
-    parser.add_argument('--num-iter', type=int, default=200, help='number of optimization steps.')
-    parser.add_argument('--batch-size', type=int, default=5,
-                        help='batch size for adam optimization (kept for compatibility: the CUDA fit streams all '
-                             'observations every iteration).')
-    parser.add_argument('--save-interval', type=int, help='save restored image every given optimization step.')
-    parser.add_argument('--params-path', type=Path,
-                        help='load underwater image formation model parameters from .pt file.')
-    parser.add_argument('--force-compute-matches', action='store_true',
-                        help='if matches file already exists, erase it and recompute matches.')
-    parser.add_argument('--keep-matches', action='store_true', help='keep matches file (can take a lot a space).')
-    parser.add_argument('--num-workers', type=int, default=0, help='number of decode threads, 0 is the main thread.')
-    parser.add_argument('--device', type=str, default='cuda', help='CUDA device for the computation.')
-    return parser
-
-
-def main(argv=None):
-    parse_args(build_parser().parse_args(argv))
+from .cli import build_parser, main, parse_args  # noqa: E402,F401  (the CLI lives in cli.py; re-exported here)
 
 
 if __name__ == '__main__':
