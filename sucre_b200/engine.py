@@ -56,6 +56,8 @@ class DeviceScene:
         self.depth: dict = {}
         self.rgb: dict = {}
         self._tables: dict = {}
+        self._ranges: dict = {}
+        self._cull_tables: dict = {}
 
     def __contains__(self, key):
         return key in self.geom
@@ -74,6 +76,8 @@ class DeviceScene:
             self.rgb[key] = rgb_u8.to(self.device, non_blocking=True).contiguous()
         self.geom[key] = geom
         self._tables.clear()
+        self._cull_tables.clear()
+        self._ranges.pop(key, None)
 
     def add_views(self, keys, geoms, depth_u16: torch.Tensor, rgb_u8: torch.Tensor):
         """Bulk form: stacked (V,H,W) / (V,H,W,3) tensors moved with one copy each."""
@@ -81,7 +85,50 @@ class DeviceScene:
         c = rgb_u8.to(self.device, non_blocking=True)
         for i, (k, g) in enumerate(zip(keys, geoms)):
             self.geom[k], self.depth[k], self.rgb[k] = g, d[i], c[i]
+            self._ranges.pop(k, None)
         self._tables.clear()
+        self._cull_tables.clear()
+
+    def depth_range(self, key) -> tuple[float, float]:
+        """(smallest non-zero depth, largest depth) of a view in metres (cached; one small device reduction)."""
+        if key not in self._ranges:
+            d = self.depth[key].view(torch.int16).to(torch.int32) & 0xffff
+            lo = torch.where(d > 0, d, torch.full_like(d, 1 << 16)).min()
+            lo, hi = (int(x) for x in torch.stack([lo, d.max()]).cpu())
+            self._ranges[key] = (lo / 1000.0, hi / 1000.0)
+        return self._ranges[key]
+
+    def possibly_overlapping(self, target_key, source_keys) -> np.ndarray:
+        """Conservative frustum pre-test (float64, host): False only for source views in which NO target pixel can land.
+        The target's back-projected pixels all lie in the convex slab spanned by its four image corners at its
+        smallest and largest depth; if the eight slab corners are in front of a source camera and their projections
+        all fall off the same side of its image (2-pixel margin), no forward projection is in bounds, so the view
+        has zero matches whatever its depth map says.  Such views are skipped by the gather and reported in
+        ObservationStore.stats['views_culled']."""
+        g = self.geom[target_key]
+        dmin, dmax = self.depth_range(target_key)
+        keep = np.ones(len(source_keys), dtype=bool)
+        if dmax <= 0 or dmin > dmax:
+            return keep
+        Kinv, R, t = (x.double().numpy() for x in (g.Kinv, g.R, g.t))
+        uv1 = np.array([[0, 0, 1], [g.width, 0, 1], [0, g.height, 1], [g.width, g.height, 1]], dtype=np.float64).T
+        rays = Kinv @ uv1                                                     # (3,4)
+        slab = np.concatenate([rays * (dmin * 0.999), rays * (dmax * 1.001)], axis=1)   # (3,8) camera frame
+        world = R @ slab + t
+        keys = tuple(source_keys)
+        if keys not in self._cull_tables:  # stacked float64 constants of the listed views, built once
+            gs = [self.geom[k] for k in keys]
+            self._cull_tables[keys] = (np.stack([x.Ri.double().numpy() for x in gs]), np.stack([x.ti.double().numpy() for x in gs]),
+                                       np.stack([x.K.double().numpy() for x in gs]),
+                                       np.array([x.width for x in gs], dtype=np.float64), np.array([x.height for x in gs], dtype=np.float64))
+        Ri, ti, K, Ws, Hs = self._cull_tables[keys]
+        c = Ri @ world + ti                                                   # (V,3,8)
+        front = (c[:, 2] > 1e-6).all(axis=1)
+        p = K @ c
+        with np.errstate(divide='ignore', invalid='ignore'):
+            x, y = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+        outside = (x.max(1) < -2) | (x.min(1) > Ws + 1) | (y.max(1) < -2) | (y.min(1) > Hs + 1)
+        return ~(front & outside)
 
     def record(self, key) -> np.ndarray:
         rgb = self.rgb.get(key)
@@ -225,8 +272,39 @@ def _stream(device) -> int:
 
 def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
            target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
-           reduce_counts=None, with_points: bool = False) -> ObservationStore:
-    """Stage 1 on the device: match -> count -> plan -> (one 16-byte D2H to size the store) -> sample.
+           reduce_counts=None, with_points: bool = False, cull_views: bool | None = None) -> ObservationStore:
+    """Stage 1 (see _gather_listed) behind a conservative view-level frustum pre-test: source views in which no target
+    pixel can land (DeviceScene.possibly_overlapping) are not handed to the kernels at all — on a 1000-view survey a
+    target overlaps a few dozen views.  Results are identical with or without it: a culled view has zero matches
+    and is reported as not kept; the number of culled views is in stats['views_culled'].  cull_views=None applies
+    the test to pairing lists of 128 views or more (below that its host cost exceeds what it can save)."""
+    source_keys = tuple(source_keys)
+    if cull_views is None:
+        cull_views = len(source_keys) >= 128
+    kw = dict(min_cover=min_cover, keep_src=keep_src, target_record=target_record, tile_range=tile_range,
+              reduce_counts=reduce_counts, with_points=with_points)
+    if not cull_views or len(source_keys) < 2 or target_record is not None or target_key not in scene.geom:
+        return _gather_listed(scene, target_key, source_keys, **kw)
+    keep = scene.possibly_overlapping(target_key, source_keys)
+    if keep.all():
+        return _gather_listed(scene, target_key, source_keys, **kw)
+    if not keep.any():
+        keep[0] = True  # the kernels need a non-empty list; this view yields zero matches
+    idx = np.flatnonzero(keep)
+    store = _gather_listed(scene, target_key, [source_keys[i] for i in idx], **kw)
+    view_count = np.zeros(len(source_keys), dtype=store.view_count.dtype)
+    view_kept = np.zeros(len(source_keys), dtype=bool)
+    view_count[idx], view_kept[idx] = store.view_count, store.view_kept
+    store.blk_view = torch.from_numpy(idx.astype(np.int32)).to(store.blk_view.device)[store.blk_view.long()]
+    store.source_keys, store.view_count, store.view_kept = source_keys, view_count, view_kept
+    store.stats['views_culled'] = int(len(source_keys) - len(idx))
+    return store
+
+
+def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
+                   target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
+                   reduce_counts=None, with_points: bool = False) -> ObservationStore:
+    """Stage 1 on the device: match -> count -> plan -> (one 24-byte D2H to size the store) -> sample.
     Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
     (sfm.py:127-138, loader.py:78-87, 103-118).
 

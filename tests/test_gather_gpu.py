@@ -76,3 +76,19 @@ def test_gather_api_errors():
         engine.DeviceScene('cpu')
     L = engine._lib.lib()
     assert L.sucre_gather_match(0, 0, 1, 0, 1, 0, 0) != 0 and b'null' in L.sucre_last_error()
+
+
+def test_view_culling_changes_nothing():
+    """The conservative frustum pre-test skips views that cannot overlap; the store is the same with and without it."""
+    scene = SyntheticScene(49, 96, 64, seed=8)          # 7x7 grid: a corner target sees only its neighbourhood
+    ds, host = helpers.build_device_scene(scene, range(49))
+    keys = list(range(49))
+    a = engine.gather(ds, 0, keys, keep_src=True, cull_views=True)
+    b = engine.gather(ds, 0, keys, keep_src=True, cull_views=False)
+    assert a.stats['views_culled'] >= 8 and 'views_culled' not in b.stats
+    assert np.array_equal(a.view_count, b.view_count) and np.array_equal(a.view_kept, b.view_kept) and a.n_obs == b.n_obs
+    assert torch.equal(a.cells, b.cells) and torch.equal(a.blk_view, b.blk_view) and torch.equal(a.blk_mask, b.blk_mask)
+    keep = ds.possibly_overlapping(0, keys)
+    assert b.view_count[~keep].sum() == 0              # conservative: nothing with matches was culled
+    kept, stats = helpers.oracle_gather(host, 0, keys)
+    assert helpers.compare_store_with_oracle(a, kept) == dict(idx=0, z=0, I=0, n=a.n_obs)
