@@ -28,7 +28,7 @@
 namespace sucre {
 
 #ifndef SUCRE_FIT_THREADS
-#define SUCRE_FIT_THREADS 256
+#define SUCRE_FIT_THREADS 512
 #endif
 constexpr int kFitThreads = SUCRE_FIT_THREADS;
 constexpr int kFitWarps = kFitThreads / 32;
@@ -98,17 +98,17 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 // mbarrier per slot): HBM latency is covered by the copies in flight instead of by occupancy, and the arithmetic
 // reads 16-byte records from shared memory.
 #ifndef SUCRE_FIT_CTAS
-#define SUCRE_FIT_CTAS 2                            // resident CTAs per SM the kernel is shaped for
+#define SUCRE_FIT_CTAS 1                            // resident CTAs per SM the kernel is shaped for
 #endif
 #ifndef SUCRE_FIT_CHUNK
-#define SUCRE_FIT_CHUNK (SUCRE_FIT_CTAS >= 3 ? 128 : 256)
+#define SUCRE_FIT_CHUNK 256
 #endif
 constexpr int kChunkCells = SUCRE_FIT_CHUNK;                 // cells per bulk copy (2 or 4 KB)
 #ifndef SUCRE_FIT_STAGES
-#define SUCRE_FIT_STAGES (SUCRE_FIT_CTAS >= 3 ? 4 : 3)
+#define SUCRE_FIT_STAGES 3
 #endif
 constexpr int kStages = SUCRE_FIT_STAGES;                    // ring slots per warp
-constexpr int kRingCells = kChunkCells * kStages;   // 8 KB (12 KB) per warp, 64 KB (96 KB) per CTA with 3 (2) CTAs per SM
+constexpr int kRingCells = kChunkCells * kStages;   // 12 KB per warp: 192 KB for the one 16-warp CTA of an SM
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingCells * sizeof(float4);
 constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
 #ifndef SUCRE_FIT_ILP
