@@ -92,3 +92,26 @@ def test_view_culling_changes_nothing():
     assert b.view_count[~keep].sum() == 0              # conservative: nothing with matches was culled
     kept, stats = helpers.oracle_gather(host, 0, keys)
     assert helpers.compare_store_with_oracle(a, kept) == dict(idx=0, z=0, I=0, n=a.n_obs)
+
+
+def test_degenerate_inputs_follow_the_reference_rules():
+    """NaN pose -> every comparison false -> no match (the reference's .long() of NaN is INT64_MIN, rejected);
+    a target without any valid depth -> nothing to restore; oversized images are refused (int16 indices)."""
+    scene = SyntheticScene(3, 64, 48, seed=3)
+    ds, host = helpers.build_device_scene(scene, range(3))
+    g = ds.geom[1]
+    bad = engine.ViewGeom(K=g.K, Kinv=g.Kinv, R=g.R, t=g.t, Ri=g.Ri.clone(), ti=g.ti.clone(), width=g.width, height=g.height)
+    bad.Ri[0, 0] = float('nan')
+    ds.add_view('nan', bad, ds.depth[1], ds.rgb[1])
+    store = engine.gather(ds, 0, [0, 'nan', 2])
+    assert store.view_count[1] == 0 and not store.view_kept[1] and store.view_kept[0]
+    ds.add_view('blind', ds.geom[0], torch.zeros((48, 64), dtype=torch.uint16), ds.rgb[0])
+    empty = engine.gather(ds, 'blind', [0, 1, 2])
+    assert empty.n_obs == 0
+    from sucre_b200 import api
+    with pytest.raises(engine._lib.SucreError):
+        api.restore_resident(ds, 'blind', [0, 1, 2], num_iter=2)
+    huge = engine.ViewGeom(K=g.K, Kinv=g.Kinv, R=g.R, t=g.t, Ri=g.Ri, ti=g.ti, width=40000, height=1)
+    ds.geom['huge'], ds.depth['huge'], ds.rgb['huge'] = huge, torch.zeros(40000, dtype=torch.int16, device='cuda'), None
+    with pytest.raises(engine._lib.SucreError, match='32767'):
+        engine.gather(ds, 'huge', [0])
