@@ -228,6 +228,60 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
     }
 }
 
+// One (target pixel, source view) observation in two steps, so that two of them can overlap their memory
+// latency: issue() projects the pixel into the view and starts the gathers at the source pixel it lands on,
+// finish() turns the fetched depth / colour into the record.
+struct Probe {
+    int u2, v2, fmt;
+    unsigned d16;
+    float raw0, raw1, raw2;
+    float Kinv[9];
+
+    __device__ __forceinline__ void issue(const sucre_view* S, float w0, float w1, float w2) {  // S: warp-uniform => broadcast loads
+        float Ri[9], ti[3], K[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            Ri[i] = __ldg(&S->Ri[i]);
+            K[i] = __ldg(&S->K[i]);
+            Kinv[i] = __ldg(&S->Kinv[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ti[i] = __ldg(&S->ti[i]);
+        const int Ws = __ldg(&S->width), Hs = __ldg(&S->height);
+        const uint16_t* depth = reinterpret_cast<const uint16_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->depth)));
+        const void* rgb = reinterpret_cast<const void*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->rgb)));
+        fmt = __ldg(&S->rgb_format);
+        project(Ri, ti, K, Ws, Hs, w0, w1, w2, u2, v2);
+        const size_t q = (size_t)v2 * Ws + u2;
+        d16 = __ldg(depth + q);                                                // sfm.py:137
+        if (fmt == SUCRE_RGB_F32) {  // resampled on the host in float (--image-scale), loader.py:158-163
+            const float* px = reinterpret_cast<const float*>(rgb) + 3 * q;
+            raw0 = __ldg(px + 0), raw1 = __ldg(px + 1), raw2 = __ldg(px + 2);
+        } else {
+            const uint8_t* px = reinterpret_cast<const uint8_t*>(rgb) + 3 * q;
+            raw0 = (float)__ldg(px + 0), raw1 = (float)__ldg(px + 1), raw2 = (float)__ldg(px + 2);
+        }
+    }
+
+    __device__ __forceinline__ void finish(float4* out, uint32_t* src_out, int record_cells) const {
+        const float d2 = __fdiv_rn((float)d16, 1000.0f);
+        float c0, c1, c2;
+        unproject(Kinv, u2, v2, d2, c0, c1, c2);                               // loader.py:113
+        // sucre.py:53 cP.norm(dim=0): sequential squares, no fma
+        const float z = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2)));
+        const bool f32 = fmt == SUCRE_RGB_F32;                                 // else loader.py:157, 87: u8 / 255
+        const float I0 = f32 ? raw0 : __fdiv_rn(raw0, 255.0f), I1 = f32 ? raw1 : __fdiv_rn(raw1, 255.0f),
+                    I2 = f32 ? raw2 : __fdiv_rn(raw2, 255.0f);
+        if (record_cells == 1) {
+            out[0] = make_float4(z, I0, I1, I2);
+        } else {  // light model: the camera-frame point itself is needed (sucre.py:57)
+            out[0] = make_float4(c0, c1, c2, z);
+            out[1] = make_float4(I0, I1, I2, 0.f);
+        }
+        if (src_out) *src_out = (uint32_t)u2 | ((uint32_t)v2 << 16);
+    }
+};
+
 // ---- sample ----------------------------------------------------------------------------------------------
 // One warp per tile.  Phase A compacts the tile's non-empty kept blocks (lane mask + view index) into
 // blk_mask / blk_view.  Phase B walks them in segments of seg_views blocks: per-lane record counts -> header
@@ -292,51 +346,20 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
         const int n = __shfl_sync(kFull, incl, 31);
         reinterpret_cast<uint8_t*>(cells + cell)[lane] = (uint8_t)cnt;  // header: 32 lane counts
         long long at = cell + kSegHeaderCells + (long long)record_cells * (incl - cnt);
-        for (int j = 0; j < ns; ++j) {
-            const uint32_t bm = __shfl_sync(kFull, bm_l, j);
-            const int s = __shfl_sync(kFull, bv_l, j);
-            if ((bm >> lane) & 1u) {
-                const sucre_view* S = views + s;  // warp-uniform addresses: broadcast loads
-                float Ri[9], ti[3], K[9], Kinv[9];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    Ri[i] = __ldg(&S->Ri[i]);
-                    K[i] = __ldg(&S->K[i]);
-                    Kinv[i] = __ldg(&S->Kinv[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) ti[i] = __ldg(&S->ti[i]);
-                const int Ws = __ldg(&S->width), Hs = __ldg(&S->height);
-                const uint16_t* depth = reinterpret_cast<const uint16_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->depth)));
-                const void* rgb = reinterpret_cast<const void*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->rgb)));
-                const int rgb_format = __ldg(&S->rgb_format);
-                int u2, v2;
-                project(Ri, ti, K, Ws, Hs, w0, w1, w2, u2, v2);
-                const size_t q = (size_t)v2 * Ws + u2;
-                const float d2 = __fdiv_rn((float)__ldg(depth + q), 1000.0f);  // sfm.py:137
-                float c0, c1, c2;
-                unproject(Kinv, u2, v2, d2, c0, c1, c2);                        // loader.py:113
-                // sucre.py:53 cP.norm(dim=0): sequential squares, no fma
-                const float z = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2)));
-                float I0, I1, I2;
-                if (rgb_format == SUCRE_RGB_F32) {  // resampled on the host in float (--image-scale), loader.py:158-163
-                    const float* px = reinterpret_cast<const float*>(rgb) + 3 * q;
-                    I0 = __ldg(px + 0);
-                    I1 = __ldg(px + 1);
-                    I2 = __ldg(px + 2);
-                } else {
-                    const uint8_t* px = reinterpret_cast<const uint8_t*>(rgb) + 3 * q;
-                    I0 = __fdiv_rn((float)__ldg(px + 0), 255.0f);               // loader.py:157, 87
-                    I1 = __fdiv_rn((float)__ldg(px + 1), 255.0f);
-                    I2 = __fdiv_rn((float)__ldg(px + 2), 255.0f);
-                }
-                if (record_cells == 1) {
-                    cells[at] = make_float4(z, I0, I1, I2);
-                } else {  // light model: the camera-frame point itself is needed (sucre.py:57)
-                    cells[at] = make_float4(c0, c1, c2, z);
-                    cells[at + 1] = make_float4(I0, I1, I2, 0.f);
-                }
-                if (cell_src) cell_src[at] = (uint32_t)u2 | ((uint32_t)v2 << 16);
+        // two blocks per step: the gathers of the second are in flight while the first is finished
+        for (int j = 0; j < ns; j += 2) {
+            const uint32_t bm0 = __shfl_sync(kFull, bm_l, j), bm1 = __shfl_sync(kFull, bm_l, j + 1);  // bm_l = 0 beyond ns
+            const int s0v = __shfl_sync(kFull, bv_l, j), s1v = __shfl_sync(kFull, bv_l, j + 1);
+            const bool a0 = (bm0 >> lane) & 1u, a1 = (bm1 >> lane) & 1u;
+            Probe p0, p1;
+            if (a0) p0.issue(views + s0v, w0, w1, w2);
+            if (a1) p1.issue(views + s1v, w0, w1, w2);
+            if (a0) {
+                p0.finish(cells + at, cell_src ? cell_src + at : nullptr, record_cells);
+                at += record_cells;
+            }
+            if (a1) {
+                p1.finish(cells + at, cell_src ? cell_src + at : nullptr, record_cells);
                 at += record_cells;
             }
         }
