@@ -1,7 +1,7 @@
 // Stage 2 — per-pixel fit of the underwater image formation model for sm_100a.
 //
 // One warp owns one tile (32 consecutive target pixels), one lane one pixel.  The observation store is a stream
-// of 16-byte cells, tile after tile; within a tile, segments of 8 source views: 2 header cells (32 per-lane
+// of 16-byte cells, tile after tile; within a tile, segments of up to 15 source views: 2 header cells (32 per-lane
 // record counts) then the records {z, I_r, I_g, I_b} LANE-MAJOR, so every lane walks its own contiguous run and
 // the inner loop carries no mask / popcount / shuffle addressing at all.
 //
@@ -21,8 +21,10 @@
 // Global sums: per-pixel values are promoted to double per thread, reduced by warp shuffles, one double row per
 // CTA; the last CTA to finish (ticket counter) reduces the rows in a fixed order and applies torch.optim.Adam's
 // update to the 9 scalars, so an iteration is ONE kernel and 200 iterations need no host round trip.
-// Tiles are statically partitioned over the resident warps by block count (sucre_fit_prepare), so the summation
-// order — and therefore every bit of the result — is reproducible run to run.
+// Tiles are statically partitioned over the resident warps by an instruction-cost model (sucre_fit_prepare), so the
+// summation order — and therefore every bit of the result — is reproducible run to run.  Inside the Adam loop the
+// launches are chained with programmatic dependent launch, and for a target sharded over several GPUs the all-reduce
+// of the sums runs inside the last CTA over NVLink peer memory (sucre_fit_sharded).
 #include "common.cuh"
 
 namespace sucre {

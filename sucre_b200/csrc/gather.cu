@@ -7,9 +7,10 @@
 //           views whose constants sit in shared memory; the backward projection is evaluated only at the
 //           source pixel the forward projection lands on (one 2-byte gather), and the per-(tile, view)
 //           result is a 32-bit ballot mask.
-//   plan    per-view counts -> min_cover decision -> per-tile record/block counts -> exclusive scan.
+//   plan    per-view counts -> min_cover decision -> per-tile record/block/segment counts -> exclusive scan.
 //   sample  one warp per tile re-projects only the matched pixels, fetches depth + colour of the source
-//           pixel and appends {z, I} records to the tile-major compact stream (include/sucre_b200.h).
+//           pixel and writes {z, I} records into the tile-major segmented stream (include/sucre_b200.h),
+//           lane-major within each segment of up to 15 views.
 //
 // Arithmetic contract (SURVEY.md §8a', pinned by tests against the reference's own outputs): every fp32
 // operation below is a single correctly rounded IEEE op written with an explicit intrinsic, in the order the
