@@ -255,8 +255,10 @@ def ours(args):
         fit_ms.append((f0, f1))
         return api.RestoreResult(J=J, params=state.params, history=history, n_obs=store.n_obs, view_kept=store.view_kept)
 
+    J_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+
     def step_host(_):
-        return api.restore_from_host(host, target, keys, device=dev, **kw)
+        return api.restore_from_host(host, target, keys, device=dev, out_J=J_host, **kw)
 
     if args.shard != 'targets' and world > 1:
         return ours_pixel_sharded(args, resident, keys, dev, world, rank, local, run_steps, host)

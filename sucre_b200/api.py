@@ -63,8 +63,10 @@ def restore_resident(scene: engine.DeviceScene, target_key, source_keys, *, min_
                          store=store, state=state)
 
 
-def restore_from_host(host: HostScene, target: int, sources=None, *, device='cuda', **kw) -> RestoreResult:
-    """End to end from host buffers: H2D of every listed view, restore, D2H of J, parameters and history."""
+def restore_from_host(host: HostScene, target: int, sources=None, *, device='cuda', out_J: torch.Tensor | None = None,
+                      **kw) -> RestoreResult:
+    """End to end from host buffers: H2D of every listed view, restore, D2H of J, parameters and history.
+    out_J: optional (H,W,3) float32 host tensor (ideally pinned) that receives J; otherwise a new pageable tensor."""
     sources = list(range(len(host.geoms))) if sources is None else list(sources)
     needed = sorted(set(sources) | {target})
     scene = engine.DeviceScene(device)
@@ -74,9 +76,12 @@ def restore_from_host(host: HostScene, target: int, sources=None, *, device='cud
         for i in needed:
             scene.add_view(i, host.geoms[i], host.depth[i], host.rgb[i])
     res = restore_resident(scene, target, sources, **kw)
-    out = RestoreResult(J=res.J.cpu(), params=res.params.cpu(), history=res.history.cpu(), n_obs=res.n_obs,
-                        view_kept=res.view_kept)
-    return out
+    if out_J is None:
+        J = res.J.cpu()
+    else:
+        J = out_J.copy_(res.J, non_blocking=True)
+    params, history = res.params.cpu(), res.history.cpu()  # synchronises the stream: J has landed too
+    return RestoreResult(J=J, params=params, history=history, n_obs=res.n_obs, view_kept=res.view_kept)
 
 
 def h2d_bytes(host: HostScene, target: int, sources=None) -> int:
