@@ -54,7 +54,7 @@ def build_parser() -> argparse.ArgumentParser:
 
 def parse_args(args: argparse.Namespace):
     """Builds the model, resolves targets and pairing list (sucre.py:222-261) and restores every target."""
-    from . import sfm, sucre
+    from . import loader, sfm, sucre
     print('Loading COLMAP model.')
     colmap_model = sfm.COLMAPModel(model_dir=args.model_dir, image_dir=args.image_dir, depth_dir=args.depth_dir,
                                    image_scale=args.image_scale)
@@ -69,14 +69,16 @@ def parse_args(args: argparse.Namespace):
     pairing = [im for im in colmap_model.images.values() if im.name not in excluded]
 
     args.output_dir.mkdir(parents=True, exist_ok=True)
-    for image in targets:
-        sucre.restore_image(
-            image=image, colmap_model=colmap_model, output_dir=args.output_dir, light_model=args.light_model,
-            use_closed_form=args.use_closed_form, min_cover=args.min_cover, image_list=pairing,
-            lr=args.learning_rate, num_iter=args.num_iter, batch_size=args.batch_size,
-            save_interval=args.save_interval, params_path=args.params_path,
-            force_compute_matches=args.force_compute_matches, keep_matches=args.keep_matches,
-            num_workers=args.num_workers, device=args.device)
+    # several targets: their output files are written by background threads while the next target is restored
+    with loader.AsyncWriter() as writer:
+        for image in targets:
+            sucre.restore_image(
+                image=image, colmap_model=colmap_model, output_dir=args.output_dir, light_model=args.light_model,
+                use_closed_form=args.use_closed_form, min_cover=args.min_cover, image_list=pairing,
+                lr=args.learning_rate, num_iter=args.num_iter, batch_size=args.batch_size,
+                save_interval=args.save_interval, params_path=args.params_path,
+                force_compute_matches=args.force_compute_matches, keep_matches=args.keep_matches,
+                num_workers=args.num_workers, device=args.device, **({'writer': writer} if len(targets) > 1 else {}))
 
 
 def main(argv=None):

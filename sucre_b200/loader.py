@@ -66,6 +66,37 @@ def load_depth_u16(depth_map_path: Path, width: int, height: int) -> Tensor:
     return torch.from_numpy(np.ascontiguousarray(depth))
 
 
+# ---- output ---------------------------------------------------------------------------------------------------
+class AsyncWriter:
+    """A few threads that encode PNGs / dump .pt files while the GPU works on the next target (PNG encoding and
+    torch.save release the GIL).  Once the kernels take milliseconds, writing the reference's per-target files
+    (sucre.py:116-121, 213-215) is what bounds a multi-target run.  close() waits for every job and re-raises the
+    first failure."""
+
+    def __init__(self, num_threads: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=num_threads, thread_name_prefix='sucre-writer')
+        self._jobs = []
+
+    def submit(self, fn, *args):
+        self._jobs.append(self._pool.submit(fn, *args))
+
+    def close(self):
+        try:
+            for job in self._jobs:
+                job.result()
+        finally:
+            self._jobs.clear()
+            self._pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
 # ---- matches ----------------------------------------------------------------------------------------------------
 class MatchesData:
     """What adam() consumes (reference: loader.py:36-53, a list of per-view samples).  Here: a handle on the

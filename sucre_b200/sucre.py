@@ -143,15 +143,19 @@ class SUCRe:
     # -- outputs (sucre.py:84-121), host side, once per image ----------------------------------------------------
     @torch.no_grad()
     def plot_J(self) -> Image.Image:
-        J = self.J.cpu().numpy().copy()
-        valid = np.all(~np.isnan(J), axis=2)
-        J_valid = J[valid]
-        J_valid = np.clip(J_valid, np.percentile(J_valid, 1, axis=0), np.percentile(J_valid, 99, axis=0))
-        J_valid = J_valid - np.min(J_valid, axis=0)
-        J_valid = J_valid / np.max(J_valid, axis=0)
-        J[~valid] = 0.0
-        J[valid] = J_valid
-        return Image.fromarray(np.uint8(J * 255))
+        """Per-channel 1-99 percentile stretch of the valid pixels of J (sucre.py:84-94), evaluated on J's device
+        (torch.quantile's linear interpolation is numpy.percentile's default): only the uint8 image crosses to the host."""
+        J = self.J
+        valid = ~torch.isnan(J).any(dim=2)
+        Jv = J[valid]                                                        # (n, 3)
+        lo = torch.stack([torch.quantile(Jv[:, c], 0.01) for c in range(3)])  # per channel: quantile() caps its input size
+        hi = torch.stack([torch.quantile(Jv[:, c], 0.99) for c in range(3)])
+        Jv = torch.clamp(Jv, lo, hi)
+        Jv = Jv - Jv.min(dim=0).values
+        Jv = Jv / Jv.max(dim=0).values
+        out = torch.zeros_like(J)
+        out[valid] = Jv
+        return Image.fromarray((out * 255).to(torch.uint8).cpu().numpy())
 
     @torch.no_grad()
     def plot_reconstruction(self) -> Image.Image:
@@ -177,13 +181,20 @@ class SUCRe:
         l_map[v, u] = l
         return Image.fromarray(np.uint8(_jet(l_map.cpu().numpy())[:, :, :3] * 255))
 
-    def save_plots(self, save_dir: Path, iteration: int = None):
+    def save_plots(self, save_dir: Path, iteration: int = None, writer: loader.AsyncWriter | None = None):
+        """Same files as sucre.py:115-121.  The images are rendered now (on the device); with `writer` their PNG
+        encoding happens on its threads."""
         save_path = (save_dir / self.image.name).with_suffix('.png')
         suffix = '' if iteration is None else f'_{iteration:04d}'
-        self.plot_J().save(save_path.with_stem(f'{save_path.stem}_rgb{suffix}'))
-        self.plot_reconstruction().save(save_path.with_stem(f'{save_path.stem}_reconstruction{suffix}'))
+        jobs = [(self.plot_J(), save_path.with_stem(f'{save_path.stem}_rgb{suffix}')),
+                (self.plot_reconstruction(), save_path.with_stem(f'{save_path.stem}_reconstruction{suffix}'))]
         if self.light_model:
-            self.plot_l().save(save_path.with_stem(f'{save_path.stem}_vignetting{suffix}'))
+            jobs.append((self.plot_l(), save_path.with_stem(f'{save_path.stem}_vignetting{suffix}')))
+        for img, path in jobs:
+            if writer is None:
+                img.save(path)
+            else:
+                writer.submit(img.save, path)
 
 
 def _jet(x: np.ndarray) -> np.ndarray:
@@ -310,9 +321,13 @@ def restore_image(
         force_compute_matches: bool = False,
         keep_matches: bool = False,
         num_workers: int = 0,
-        device: str = 'cuda'
+        device: str = 'cuda',
+        *,
+        writer: loader.AsyncWriter | None = None
 ):
-    """Drop-in for the reference's restore_image (sucre.py:160-219): same arguments, same prints, same files."""
+    """Drop-in for the reference's restore_image (sucre.py:160-219): same arguments, same prints, same files.
+    writer (keyword-only, optional): PNG encoding and the .pt dump are handed to its threads, so that the next target
+    can start while this one's files are written; the caller closes it.  Without it every file exists on return."""
     print(f'Restore {image.name}.')
     matches_path = (output_dir / image.name).with_suffix('.h5')
     matches_file = loader.MatchesFile(matches_path, colmap_model=colmap_model, overwrite=force_compute_matches)
@@ -343,9 +358,13 @@ def restore_image(
     adam(sucre=sucre, matches_data=matches_data, lr=lr, num_iter=num_iter, batch_size=batch_size,
          save_dir=output_dir, save_interval=save_interval, device=device)
 
-    sucre.save_plots(save_dir=output_dir)
+    sucre.save_plots(save_dir=output_dir, writer=writer)
     J = sucre.J.detach().cpu()
-    torch.save({**sucre.cpu().state_dict(), 'J': J}, (output_dir / image.name).with_suffix('.pt'))
+    payload = {**sucre.cpu().state_dict(), 'J': J}
+    if writer is None:
+        torch.save(payload, (output_dir / image.name).with_suffix('.pt'))
+    else:
+        writer.submit(torch.save, payload, (output_dir / image.name).with_suffix('.pt'))
 
     if keep_matches:
         matches_file.save()

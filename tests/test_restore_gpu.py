@@ -132,3 +132,32 @@ def test_image_scale_like_the_reference(golden, tmp_path, mode, capsys):
     J = saved['J'].numpy()
     assert J.shape == (64, 96, 3)
     assert np.array_equal(np.isnan(J), np.isnan(gm['J'])) and np.nanmax(np.abs(J - gm['J'])) < 1e-3
+
+
+def test_multi_target_cli_and_device_side_plots(golden, tmp_path):
+    """--image-list: every target's files exist when the CLI returns (background writer joined); the device-side
+    percentile stretch of plot_J equals the reference's numpy version to within one grey level."""
+    g = golden('tiny6_closed')
+    root = _write_golden_scene(g, tmp_path)
+    (root / 'targets.txt').write_text('image0001.png\nimage0002.png\nimage0004.png\n')
+    sucre.main(['--image-dir', str(root / 'images'), '--depth-dir', str(root / 'depth'), '--model-dir', str(root / 'model'),
+                '--output-dir', str(root / 'out'), '--image-list', str(root / 'targets.txt'), '--use-closed-form',
+                '--num-iter', '25'])
+    for stem in ('image0001', 'image0002', 'image0004'):
+        for suffix in ('.pt', '_rgb.png', '_reconstruction.png'):
+            assert (root / 'out' / f'{stem}{suffix}').exists(), (stem, suffix)
+    saved = torch.load(root / 'out' / 'image0002.pt')
+    assert np.nanmax(np.abs(saved['J'].numpy() - g['J'])) < 1e-3
+    # reference plot_J (sucre.py:84-94) in numpy on the saved J
+    J = saved['J'].numpy().copy()
+    valid = np.all(~np.isnan(J), axis=2)
+    Jv = J[valid]
+    Jv = np.clip(Jv, np.percentile(Jv, 1, axis=0), np.percentile(Jv, 99, axis=0))
+    Jv = Jv - np.min(Jv, axis=0)
+    Jv = Jv / np.max(Jv, axis=0)
+    J[~valid] = 0.0
+    J[valid] = Jv
+    ref_png = np.uint8(J * 255)
+    from PIL import Image as PILImage
+    got_png = np.asarray(PILImage.open(root / 'out' / 'image0002_rgb.png'))
+    assert got_png.shape == ref_png.shape and np.abs(got_png.astype(int) - ref_png.astype(int)).max() <= 1
