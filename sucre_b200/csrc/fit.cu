@@ -171,16 +171,6 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-template <bool PRECISE>
-__device__ __forceinline__ u64 exp_pair(u64 x) {  // PRECISE: x holds natural-log exponents, else base-2 exponents
-    return PRECISE ? pk(expf(lo(x)), expf(hi(x))) : pk(fast_exp2(lo(x)), fast_exp2(hi(x)));
-}
-
 // Per-pixel statistics of one channel, two per packed accumulator so that one FFMA2 updates both:
 //   S12 = (sum D'a, sum a^2)   S34 = (sum D'h, sum a h)   S56 = (sum D'za, sum a za)   S78 = (sum D'zg, sum a zg)
 //   S9  = sum D'^2             (a = e^{-beta z}, g = e^{-gamma z}, h = 1 - g, D' the shifted residual)

@@ -444,9 +444,6 @@ def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.0
     return history
 
 
-fit_closed_form = fit  # the mode lives in the FitState
-
-
 def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs_global: int | None = None,
              lr: float = 0.05):
     """One objective evaluation at state.params -> sums (10 doubles, device); in J-parameter mode J takes its

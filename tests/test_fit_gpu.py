@@ -28,7 +28,7 @@ def test_closed_form_fit_vs_reference_golden(golden, case):
     order = sorted((names[i] for i in g.pairing_list()))
     store = engine.gather(ds, str(g['target']), order, min_cover=float(g['min_cover']))
     state = engine.FitState.initial(ds.device)
-    hist = engine.fit_closed_form(store, state, int(g['num_iter'])).cpu().numpy()
+    hist = engine.fit(store, state, int(g['num_iter'])).cpu().numpy()
     J = engine.closed_form_J(store, state.params).cpu().numpy()
     ref_p = np.concatenate([g['B'].ravel(), g['beta'].ravel(), g['gamma'].ravel()])
     assert _rel(state.params.cpu().numpy(), ref_p) < P_RTOL
@@ -46,7 +46,7 @@ def test_closed_form_fit_vs_oracle_config1():
     kept, _ = helpers.oracle_gather(host, 8, list(range(20)))
     ref = oracle.fit([o for _, o in kept], 640, 480, closed_form=True, num_iter=40)
     state = engine.FitState.initial(ds.device)
-    hist = engine.fit_closed_form(store, state, 40).cpu().numpy()
+    hist = engine.fit(store, state, 40).cpu().numpy()
     J = engine.closed_form_J(store, state.params).cpu().numpy()
     assert _rel(state.params.cpu().numpy(), ref['params']) < P_RTOL
     assert _rel(hist[:, :9], ref['history'], floor=0.05) < P_RTOL
@@ -104,7 +104,7 @@ def test_fit_building_blocks_match_fused_loop(golden):
     ds, _ = helpers.golden_device_scene(g)
     store = engine.gather(ds, str(g['target']), sorted(g['names'].tolist()))
     a = engine.FitState.initial(ds.device)
-    ha = engine.fit_closed_form(store, a, 12)
+    ha = engine.fit(store, a, 12)
     b = engine.FitState.initial(ds.device)
     sums = torch.zeros(10, dtype=torch.float64, device=ds.device)
     rows = torch.zeros((12, 10), dtype=torch.float32, device=ds.device)
@@ -113,7 +113,7 @@ def test_fit_building_blocks_match_fused_loop(golden):
         engine.adam_step(b, sums, store.n_obs, 0.05, rows[it])
     assert torch.equal(a.params, b.params) and torch.equal(ha, rows) and a.step == b.step == 12
     c = engine.FitState.initial(ds.device)
-    hc = torch.cat([engine.fit_closed_form(store, c, 5), engine.fit_closed_form(store, c, 7)])
+    hc = torch.cat([engine.fit(store, c, 5), engine.fit(store, c, 7)])
     assert torch.equal(a.params, c.params) and torch.equal(ha, hc)
 
 
@@ -125,7 +125,7 @@ def test_fit_is_deterministic(golden):
     runs = []
     for _ in range(2):
         s = engine.FitState.initial(ds.device)
-        runs.append((engine.fit_closed_form(store, s, 10).clone(), s.params.clone()))
+        runs.append((engine.fit(store, s, 10).clone(), s.params.clone()))
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
 
 
@@ -136,7 +136,7 @@ def test_recovers_ground_truth_parameters():
     ds, _ = helpers.build_device_scene(scene, range(9))
     store = engine.gather(ds, 4, list(range(9)))
     state = engine.FitState.initial(ds.device)
-    hist = engine.fit_closed_form(store, state, 200).cpu().numpy()
+    hist = engine.fit(store, state, 200).cpu().numpy()
     assert hist[-1, 9] < hist[0, 9] / 5
     J = engine.closed_form_J(store, state.params).cpu().numpy()
     assert np.nanmin(J) > -0.5 and np.nanmax(J) < 1.5
@@ -147,5 +147,5 @@ def test_empty_store_raises():
     ds, _ = helpers.build_device_scene(scene, range(2))
     store = engine.gather(ds, 0, [0, 1], min_cover=1.0)
     with pytest.raises(engine._lib.SucreError):
-        engine.fit_closed_form(store, engine.FitState.initial(ds.device), 3)
+        engine.fit(store, engine.FitState.initial(ds.device), 3)
     assert torch.isnan(engine.closed_form_J(store, engine.FitState.initial(ds.device).params)).all()
