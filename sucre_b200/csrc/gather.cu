@@ -62,6 +62,9 @@ constexpr int kSegViewsMax = 15;                    // per-lane record counts of
 constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
 constexpr int kChunk = 32;                          // source views per CTA: lane j keeps the mask of view j
 constexpr int kWarps = 8;
+#ifndef SUCRE_MATCH_PIX
+#define SUCRE_MATCH_PIX 2  // target pixels per thread of gather_match_kernel
+#endif
 
 template <int PIX>
 __global__ void __launch_bounds__(kWarps * 32)
@@ -396,7 +399,7 @@ extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_vie
     SUCRE_REQUIRE(views && masks, "sucre_gather_match: null pointer");
     SUCRE_REQUIRE(n_views > 0, "sucre_gather_match: n_views = %d", n_views);
     if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_match")) return 1;
-    constexpr int PIX = 2;
+    constexpr int PIX = SUCRE_MATCH_PIX;
     dim3 grid((n_tiles + kWarps * PIX - 1) / (kWarps * PIX), (n_views + kChunk - 1) / kChunk);
     gather_match_kernel<PIX><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*target_host, views, n_views, masks, first_tile, n_tiles);
     return check_launch("gather_match_kernel");

@@ -98,13 +98,14 @@ class DeviceScene:
             self._ranges[key] = (lo / 1000.0, hi / 1000.0)
         return self._ranges[key]
 
-    def possibly_overlapping(self, target_key, source_keys) -> np.ndarray:
+    def possibly_overlapping(self, target_key, source_keys, source_geoms=None) -> np.ndarray:
         """Conservative frustum pre-test (float64, host): False only for source views in which NO target pixel can land.
         The target's back-projected pixels all lie in the convex slab spanned by its four image corners at its
         smallest and largest depth; if the eight slab corners are in front of a source camera and their projections
         all fall off the same side of its image (2-pixel margin), no forward projection is in bounds, so the view
         has zero matches whatever its depth map says.  Such views are skipped by the gather and reported in
-        ObservationStore.stats['views_culled']."""
+        ObservationStore.stats['views_culled'].  source_geoms (optional, one ViewGeom per key): lets the test run
+        before the source views are decoded / uploaded — only the target has to be resident."""
         g = self.geom[target_key]
         dmin, dmax = self.depth_range(target_key)
         keep = np.ones(len(source_keys), dtype=bool)
@@ -117,7 +118,7 @@ class DeviceScene:
         world = R @ slab + t
         keys = tuple(source_keys)
         if keys not in self._cull_tables:  # stacked float64 constants of the listed views, built once
-            gs = [self.geom[k] for k in keys]
+            gs = [self.geom[k] for k in keys] if source_geoms is None else list(source_geoms)
             self._cull_tables[keys] = (np.stack([x.Ri.double().numpy() for x in gs]), np.stack([x.ti.double().numpy() for x in gs]),
                                        np.stack([x.K.double().numpy() for x in gs]),
                                        np.array([x.width for x in gs], dtype=np.float64), np.array([x.height for x in gs], dtype=np.float64))
@@ -272,20 +273,23 @@ def _stream(device) -> int:
 
 def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
            target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
-           reduce_counts=None, with_points: bool = False, cull_views: bool | None = None) -> ObservationStore:
+           reduce_counts=None, with_points: bool = False, cull_views: bool | None = None,
+           keep_mask: np.ndarray | None = None) -> ObservationStore:
     """Stage 1 (see _gather_listed) behind a conservative view-level frustum pre-test: source views in which no target
     pixel can land (DeviceScene.possibly_overlapping) are not handed to the kernels at all — on a 1000-view survey a
     target overlaps a few dozen views.  Results are identical with or without it: a culled view has zero matches
     and is reported as not kept; the number of culled views is in stats['views_culled'].  cull_views=None applies
-    the test to pairing lists of 128 views or more (below that its host cost exceeds what it can save)."""
+    the test to pairing lists of 128 views or more (below that its host cost exceeds what it can save).
+    keep_mask: the result of a pre-test the caller already ran (views marked False need not even be in the scene)."""
     source_keys = tuple(source_keys)
     if cull_views is None:
         cull_views = len(source_keys) >= 128
     kw = dict(min_cover=min_cover, keep_src=keep_src, target_record=target_record, tile_range=tile_range,
               reduce_counts=reduce_counts, with_points=with_points)
-    if not cull_views or len(source_keys) < 2 or target_record is not None or target_key not in scene.geom:
+    if keep_mask is None and (not cull_views or len(source_keys) < 2 or target_record is not None
+                              or target_key not in scene.geom):
         return _gather_listed(scene, target_key, source_keys, **kw)
-    keep = scene.possibly_overlapping(target_key, source_keys)
+    keep = scene.possibly_overlapping(target_key, source_keys) if keep_mask is None else np.array(keep_mask, dtype=bool)
     if keep.all():
         return _gather_listed(scene, target_key, source_keys, **kw)
     if not keep.any():

@@ -9,6 +9,7 @@ Same names and meaning as the reference — Pose, Camera, Image, COLMAPModel, Im
 """
 from __future__ import annotations
 
+import os
 import struct
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
@@ -176,10 +177,19 @@ class Image:
         loader.MatchesFile.prepare_matches / load_matches).  The result stays on the device, in `matches_file`.
         Kept views are consumed in name-sorted order, the order the reference's HDF5 groups iterate in
         (loader.py:63-66, 106)."""
-        scene = self.model.scene(device, [self] + list(image_list), num_workers=num_workers)
         ordered = sorted(image_list, key=lambda im: im.name)
+        keep = None
+        if len(ordered) >= 128:
+            # large surveys: decode the target first, drop the views its frustum cannot reach (conservative pre-test,
+            # engine.DeviceScene.possibly_overlapping), and decode / upload only the others
+            scene = self.model.scene(device, [self], num_workers=num_workers)
+            keep = scene.possibly_overlapping(self.id, [im.id for im in ordered], [im.geom for im in ordered])
+            if not keep.any():
+                keep[0] = True
+        needed = [im for i, im in enumerate(ordered) if keep is None or keep[i]]
+        scene = self.model.scene(device, [self] + needed, num_workers=num_workers)
         store = gather(scene, self.id, [im.id for im in ordered], min_cover=min_cover, keep_src=True,
-                       with_points=getattr(matches_file, 'with_points', False))
+                       with_points=getattr(matches_file, 'with_points', False), keep_mask=keep)
         matches_file.set_store(store, [im.name for im in ordered])
 
     def __repr__(self) -> str:
@@ -243,8 +253,9 @@ class COLMAPModel:
         if todo:
             def decode(im):
                 return im, im.get_depth_u16(), im.get_rgb_device_form()
-            if num_workers > 0 and len(todo) > 1:
-                with ThreadPoolExecutor(max_workers=num_workers) as pool:
+            workers = num_workers if num_workers > 0 else min(8, os.cpu_count() or 1)  # cv2 decode releases the GIL
+            if workers > 1 and len(todo) > 1:
+                with ThreadPoolExecutor(max_workers=workers) as pool:
                     decoded = list(pool.map(decode, todo))
             else:
                 decoded = [decode(im) for im in todo]

@@ -161,3 +161,25 @@ def test_multi_target_cli_and_device_side_plots(golden, tmp_path):
     from PIL import Image as PILImage
     got_png = np.asarray(PILImage.open(root / 'out' / 'image0002_rgb.png'))
     assert got_png.shape == ref_png.shape and np.abs(got_png.astype(int) - ref_png.astype(int)).max() <= 1
+
+
+def test_large_survey_decodes_only_overlapping_views(tmp_path):
+    """>= 128 views in the pairing list: the target is decoded first, the conservative frustum pre-test drops the views
+    it cannot reach, and only the others are decoded and uploaded; the matches are those of the unculled gather."""
+    from sucre_b200 import engine, loader
+    from sucre_b200.synth import SyntheticScene
+    scene = SyntheticScene(144, 64, 48, seed=6)
+    dirs = scene.write(tmp_path)
+    model = sfm.COLMAPModel(dirs['model'], dirs['images'], dirs['depth'])
+    target = model['image0000.png']                       # a corner of the 12 x 12 survey
+    mf = loader.MatchesFile(tmp_path / 'image0000.h5', colmap_model=model)
+    target.match_images(list(model.images.values()), mf, device='cuda')
+    store = mf.store
+    resident = len(model._scenes['cuda'].geom)
+    assert store.stats['views_culled'] >= 60 and resident <= 85, (store.stats, resident)   # most views never decoded
+    assert len(store.source_keys) == 144 and store.view_kept.sum() > 3
+    full = model.scene('cuda', list(model.images.values()))               # now decode everything and gather unculled
+    ordered = sorted(model.images.values(), key=lambda im: im.name)
+    ref = engine.gather(full, target.id, [im.id for im in ordered], keep_src=True, cull_views=False)
+    assert np.array_equal(ref.view_count, store.view_count) and np.array_equal(ref.view_kept, store.view_kept)
+    assert torch.equal(ref.cells, store.cells) and torch.equal(ref.blk_view, store.blk_view)
