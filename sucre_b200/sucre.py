@@ -34,14 +34,24 @@ class SUCRe:
         self.use_closed_form = use_closed_form
         J0 = None
         if not use_closed_form:
-            J0 = image.get_rgb()                                          # sucre.py:48
-            J0[image.get_depth_u16().to(torch.int32) <= 0] = torch.nan    # sucre.py:49
-        self.state = engine.FitState.initial('cpu', J0=J0)
+            depth, rgb = self._target_arrays()
+            J0 = rgb.clone() if rgb.dtype == torch.float32 else rgb.to(torch.float32) / 255.0   # sucre.py:48
+            J0[depth.view(torch.int16) == 0] = torch.nan                                       # sucre.py:49
+        self.state = engine.FitState.initial('cpu' if J0 is None else J0.device, J0=J0)
         self._J_closed: Tensor | None = None
         self.history: Tensor | None = None
         if light_model:  # sucre.py:44-46; these ten scalars live on the host (see light.py)
             self.cam2light = torch.zeros(6)
             self.sigma = torch.eye(2)
+
+    def _target_arrays(self) -> tuple[Tensor, Tensor]:
+        """(u16 depth, colour in device form) of the target: taken from the model's device-resident scene when the
+        image has already been decoded there (the usual case: the gather ran first), decoded from disk otherwise."""
+        model = getattr(self.image, 'model', None)
+        for scene in (model._scenes.values() if model is not None else ()):
+            if self.image.id in scene and self.image.id in scene.rgb:
+                return scene.depth[self.image.id], scene.rgb[self.image.id]
+        return self.image.get_depth_u16(), self.image.get_rgb_device_form()
 
     # -- parameters -------------------------------------------------------------------------------------------
     @property
@@ -140,6 +150,10 @@ class SUCRe:
 
     __call__ = forward
 
+    def _target_depth_metres(self) -> Tensor:
+        depth = self._target_arrays()[0].to(self.device)
+        return (depth.view(torch.int16).to(torch.int32) & 0xffff).to(torch.float32) / 1000.0   # loader.py:167
+
     # -- outputs (sucre.py:84-121), host side, once per image ----------------------------------------------------
     @torch.no_grad()
     def plot_J(self) -> Image.Image:
@@ -160,7 +174,7 @@ class SUCRe:
     @torch.no_grad()
     def plot_reconstruction(self) -> Image.Image:
         dev = self.device
-        depth = (self.image.get_depth_u16().to(torch.int32).to(dev).to(torch.float32) / 1000.0)
+        depth = self._target_depth_metres()
         v, u = torch.where(depth > 0)
         cp = torch.stack([u + 0.5, v + 0.5, torch.ones_like(u)])
         cP = self.image.geom.Kinv.to(dev) @ (depth[v, u] * cp)
@@ -172,7 +186,7 @@ class SUCRe:
     def plot_l(self) -> Image.Image:
         """Vignetting map of the light model, jet-coloured (sucre.py:96-104)."""
         dev = self.device
-        depth = (self.image.get_depth_u16().to(torch.int32).to(dev).to(torch.float32) / 1000.0)
+        depth = self._target_depth_metres()
         v, u = torch.where(depth > 0)
         cp = torch.stack([u + 0.5, v + 0.5, torch.ones_like(u)])
         cP = self.image.geom.Kinv.to(dev) @ (depth[v, u] * cp)
