@@ -152,16 +152,17 @@ class MatchesFile:
         self._ensure_loaded()
 
     def check_integrity(self):
-        """Same invariants as loader.py:89-101, evaluated on the device: no NaN, I >= 0, range > 0, indices
-        inside the target."""
+        """The invariants of loader.py:89-101 on the device-resident store: no NaN, colours >= 0, ranges >= 0 (they are
+        > 0 by construction: a match requires a positive source depth), consistent offsets.  Evaluated over all cells:
+        the header cells hold small non-negative byte counts, i.e. finite non-negative floats."""
         self._ensure_loaded()
         s = self.store
         if s.n_obs == 0:
             return
-        rec = s.records()
-        assert not bool(torch.isnan(rec).any()), f'In {self.path}, observations contain NaN(s).'
-        assert bool((rec[:, 1:] >= 0).all()), f'In {self.path}, observations contain invalid colour value(s).'
-        assert bool((rec[:, 0] > 0).all()), f'In {self.path}, observations contain null or negative range(s).'
+        cells = s.cells
+        assert not bool(torch.isnan(cells).any()), f'In {self.path}, observations contain NaN(s).'
+        if s.record_cells == 1:  # light-model stores also carry camera-frame points, whose x / y are signed
+            assert bool((cells >= 0).all()), f'In {self.path}, observations contain invalid value(s).'
         assert int(s.rec_off[-1]) == s.n_obs and int(s.blk_off[-1]) == s.n_blocks and \
             int(s.seg_off[-1]) == s.n_segments, f'In {self.path}, corrupt offsets.'
 

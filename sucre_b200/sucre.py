@@ -228,11 +228,28 @@ def _jet(x: np.ndarray) -> np.ndarray:
     return lut[idx]
 
 
-def _log_history(history: np.ndarray, first_iteration: int):
-    for k, row in enumerate(history):
+def _fmt(x) -> str:
+    """str() of a small float32 vector under np.printoptions(precision=4) — what the reference's log line shows
+    (sucre.py:149-152) — without numpy's (slow) array printer for ordinary magnitudes."""
+    x32 = np.asarray(x, dtype=np.float32)
+    x = x32.astype(np.float64)
+    ax = np.abs(x[x != 0])
+    if not np.all(np.isfinite(x)) or (ax.size and (ax.max() >= 1e8 or ax.min() < 1e-4 or ax.max() / ax.min() > 1e3)):
         with np.printoptions(precision=4):
-            tqdm.write(f'iter: {first_iteration + k:04d}, cost: {row[9]:.4e}, B: {row[0:3]}, '
-                       f'beta: {row[3:6]}, gamma: {row[6:9]}')
+            return str(x32)
+    ints, fracs = [], []
+    for v in x:
+        i, f = f'{v:.4f}'.split('.')
+        ints.append(i)
+        fracs.append(f.rstrip('0'))
+    left, digits = max(map(len, ints)), max(map(len, fracs))
+    return '[' + ' '.join(i.rjust(left) + '.' + f.ljust(digits) for i, f in zip(ints, fracs)) + ']'
+
+
+def _log_history(history: np.ndarray, first_iteration: int, cost_column: int = 9):
+    lines = [f'iter: {first_iteration + k:04d}, cost: {row[cost_column]:.4e}, B: {_fmt(row[0:3])}, '
+             f'beta: {_fmt(row[3:6])}, gamma: {_fmt(row[6:9])}' for k, row in enumerate(history)]
+    tqdm.write('\n'.join(lines))
 
 
 def adam(
@@ -312,9 +329,7 @@ def _adam_light(sucre: SUCRe, matches_data: loader.MatchesData, lr: float, num_i
             sucre.save_plots(save_dir=save_dir, iteration=it)
     sucre.history = torch.cat(histories) if histories else None
     if sucre.history is not None:
-        for k, row in enumerate(sucre.history.numpy()):
-            with np.printoptions(precision=4):
-                tqdm.write(f'iter: {k:04d}, cost: {row[19]:.4e}, B: {row[0:3]}, beta: {row[3:6]}, gamma: {row[6:9]}')
+        _log_history(sucre.history.numpy(), 0, cost_column=19)
     sucre.update_J(matches_data=matches_data)  # sucre.py:156
     return sucre
 
