@@ -123,3 +123,33 @@ def test_no_cpu_path():
     from sucre_b200 import engine
     with pytest.raises(engine._lib.SucreError):
         engine.DeviceScene('cpu')
+
+
+def test_log_formatter_matches_numpy_printing():
+    """The per-iteration log line (sucre.py:149-152) prints B, beta, gamma with np.printoptions(precision=4)."""
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        x = (rng.normal(size=3) * 10.0 ** rng.integers(-6, 4)).astype(np.float32)
+        if rng.random() < 0.2:
+            x = np.round(x, 1)
+        if rng.random() < 0.05:
+            x[rng.integers(3)] = 0
+        with np.printoptions(precision=4):
+            assert sucre._fmt(x) == str(x), x
+    assert sucre._fmt([0.1198, 0.161, 0.1593]) == '[0.1198 0.161  0.1593]'
+    assert 'nan' in sucre._fmt([float('nan'), 0.1, 0.2])
+
+
+def test_async_writer_runs_jobs_and_reraises(tmp_path):
+    done = []
+    with loader.AsyncWriter(2) as w:
+        for i in range(8):
+            w.submit(lambda k: done.append(k), i)
+    assert sorted(done) == list(range(8))
+
+    def boom():
+        raise OSError('disk full')
+    w = loader.AsyncWriter(1)
+    w.submit(boom)
+    with pytest.raises(OSError):
+        w.close()
