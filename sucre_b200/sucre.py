@@ -238,10 +238,10 @@ def _fmt(x) -> str:
         with np.printoptions(precision=4):
             return str(x32)
     ints, fracs = [], []
-    for v in x:
-        i, f = f'{v:.4f}'.split('.')
+    for v in x32:  # numpy's own shortest-repr digit generation (Dragon4), element by element
+        i, _, f = np.format_float_positional(v, precision=4, unique=True, fractional=True, trim='.').partition('.')
         ints.append(i)
-        fracs.append(f.rstrip('0'))
+        fracs.append(f)
     left, digits = max(map(len, ints)), max(map(len, fracs))
     return '[' + ' '.join(i.rjust(left) + '.' + f.ljust(digits) for i, f in zip(ints, fracs)) + ']'
 
