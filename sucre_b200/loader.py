@@ -73,9 +73,11 @@ class AsyncWriter:
     (sucre.py:116-121, 213-215) is what bounds a multi-target run.  close() waits for every job and re-raises the
     first failure."""
 
-    def __init__(self, num_threads: int = 4):
+    def __init__(self, num_threads: int | None = None):
         from concurrent.futures import ThreadPoolExecutor
-        self._pool = ThreadPoolExecutor(max_workers=num_threads, thread_name_prefix='sucre-writer')
+        import os
+        num_threads = num_threads or min(8, os.cpu_count() or 1)
+        self._pool = ThreadPoolExecutor(max_workers=num_threads, thread_name_prefix="sucre-writer")
         self._jobs = []
 
     def submit(self, fn, *args):
