@@ -6,7 +6,8 @@
 
 One step = restore ONE target image of BASELINE.json configs[1] (synthetic 100-view 1368x912 scene): fused gather
 against all views + 200 closed-form Adam iterations + final J.  `value` = pixel-views/s with the scene resident in
-HBM; `e2e` = the same through api.restore_from_host (pinned host buffers, H2D + D2H inside the timed region).
+HBM; `e2e` = the same through api.restore_from_host (pinned host buffers, H2D + D2H inside the timed region; by
+default only the footprint rectangle of every source view is copied, --upload full copies whole views).
 N > 1: one process per GPU (torchrun), every rank restores a different target of its own replica of the scene
 (weak scaling, no data-path collective); time = max over ranks.
 """
@@ -41,6 +42,9 @@ def parse():
     ap.add_argument('--cpu-sample-views', type=int, default=4)
     ap.add_argument('--cpu-sample-iters', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--upload', default='footprint', choices=['footprint', 'rows', 'full'],
+                    help='what the end-to-end leg copies host -> device per step: whole views, or only the rectangle of '
+                         'each source view the target can see (identical results, api.upload_plan)')
     ap.add_argument('--shard', default='targets', choices=['targets', 'pixels', 'pixels-nccl'],
                     help='N > 1: one target per rank (weak scaling, default) or ONE target sharded by pixel band over all '
                          'ranks (strong scaling; all-reduce fused into the fit kernel over NVLink, or through NCCL)')
@@ -244,30 +248,33 @@ def ours(args):
     def step_resident(fit_ms):
         if fit_ms is None:
             return api.restore_resident(resident, target, keys, **kw)
-        # same call sequence as api.restore_resident, with events around the Adam loop (the dominant kernel)
+        # same call sequence as api.restore_resident, with events around the gather and the Adam loop (the dominant kernel)
+        g0, f0, f1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        g0.record()
         store = engine.gather(resident, target, keys, min_cover=1e-6)
         state = engine.FitState.initial(dev)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         history = engine.fit(store, state, args.num_iter, 0.05)
         f1.record()
         J = engine.closed_form_J(store, state.params, state.J)
         fit_ms.append((f0, f1))
+        gather_events.append((g0, f0))
         return api.RestoreResult(J=J, params=state.params, history=history, n_obs=store.n_obs, view_kept=store.view_kept)
 
     J_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
 
     def step_host(_):
-        return api.restore_from_host(host, target, keys, device=dev, out_J=J_host, **kw)
+        return api.restore_from_host(host, target, keys, device=dev, out_J=J_host, upload=args.upload, **kw)
 
     if args.shard != 'targets' and world > 1:
         return ours_pixel_sharded(args, resident, keys, dev, world, rank, local, run_steps, host)
 
     run_steps(step_resident, max(3, args.warmup))
     sampler = ClockSampler(local) if rank == 0 else None
-    fit_events = []
+    fit_events, gather_events = [], []
     ms_res, res = run_steps(step_resident, args.steps, fit_events)
     fit_ms = [a.elapsed_time(b) for a, b in fit_events]
+    gather_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_events)
     run_steps(step_host, 1)
     ms_e2e, res_h = run_steps(step_host, args.steps)
     clocks = sampler.stop() if sampler else None          # sampled across both timed regions (resident + end to end)
@@ -293,9 +300,14 @@ def ours(args):
                    'l2': f'inputs larger than L2: scene {host.nbytes / 1e6:.0f} MB + observation store '
                          f'{16 * n_obs / 1e6:.0f} MB streamed every iteration (L2 126 MB)'},
         's_per_restored_image': ms_res / args.steps / 1e3,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': api.h2d_bytes(host, target, keys),
+        # SURVEY.md §8d(i) also quotes the gather stage alone: P*V / t_gather (match + plan + sample, its one host sync included)
+        'gather': {'ms': gather_ms, 'pixel_views_per_s': V * W * H / (gather_ms / 1e3)},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': res_h.h2d_bytes,
                 'd2h_bytes_per_step': api.d2h_bytes(res_h), 's_per_restored_image': ms_e2e / args.steps / 1e3,
-                'api': 'sucre_b200.api.restore_from_host (pinned host u16 depth + u8 colour in, J + parameters out)'},
+                'api': 'sucre_b200.api.restore_from_host (pinned host u16 depth + u8 colour in, J + parameters out)',
+                'upload': f'{args.upload}: {res_h.h2d_bytes / 1e6:.0f} MB of the {host.nbytes / 1e6:.0f} MB host scene are copied '
+                          f'per step (the target whole, of every source view the rectangle the target can see; same '
+                          f'result bit for bit as --upload full, tests/test_upload_gpu.py)'},
         'gpu_launches': args.steps * (api.LAUNCHES_FIXED + args.num_iter),
         'roofline': {'bound': 'hbm', 'kernel': 'fit_kernel<closed form>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,

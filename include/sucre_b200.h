@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 5
+#define SUCRE_ABI_VERSION 6
 #define SUCRE_TILE_PIXELS 32
 #ifndef SUCRE_SEGMENT_VIEWS
 #define SUCRE_SEGMENT_VIEWS 15
@@ -87,6 +87,22 @@ typedef struct sucre_store {
 int sucre_abi_version(void);
 int sucre_segment_views(void); /* SUCRE_SEGMENT_VIEWS the library was built with */
 const char* sucre_last_error(void);
+
+/* ---- scene upload ---------------------------------------------------------------------------------------------
+ * Replaces the per-(target, view) decode + `.to(device)` of whole source images (sfm.py:130-133 via
+ * loader.py:156-170): copies, for n views, only the rectangle of each view that the target can see
+ * (engine.DeviceScene.footprints: a conservative bound of where target pixels can land) from a host stack of
+ * equally sized planes into the matching device stack, with cudaMemcpy2DAsync on `stream`.
+ *   dst            device stack: view i starts at dst + i*view_bytes
+ *   src_host       host stack (pinned for asynchronous copies): view src_index_host[i] starts at
+ *                  src_host + src_index_host[i]*view_bytes
+ *   width, height, pixel_bytes   plane geometry: view_bytes = height * width * pixel_bytes (2: u16 depth, 3: u8 RGB)
+ *   rects_host     int32[n][4] = {x0, y0, x1, y1} in pixels, half-open; x1 <= x0 or y1 <= y0: nothing copied
+ *   copied_bytes_host  (optional) receives the bytes enqueued
+ * Pixels outside the rectangles are left as they are (the caller zero-fills the device stack: depth 0 = invalid,
+ * sfm.py:96). */
+int sucre_scene_upload(void* dst, const void* src_host, int n, const int32_t* src_index_host, int width, int height,
+                       int pixel_bytes, const int32_t* rects_host, int64_t* copied_bytes_host, void* stream);
 
 /* ---- stage 1: multi-view correspondence gather ---------------------------------------------------------
  * Replaces Image.match_images / match_two_way / match_one_way / Matches.map / Matches.__and__

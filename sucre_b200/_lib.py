@@ -9,7 +9,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 5
+ABI_VERSION = 6
 TILE = 32
 SEG_HEADER_CELLS = 2
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
@@ -45,6 +45,7 @@ _SIGNATURES = {
     'sucre_abi_version': (C.c_int, []),
     'sucre_segment_views': (C.c_int, []),
     'sucre_last_error': (C.c_char_p, []),
+    'sucre_scene_upload': (C.c_int, [_VP, _VP, _I, _VP, _I, _I, _I, _VP, _VP, _VP]),
     'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
     'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _I, _VP, _VP, _VP, _VP, _VP, _VP]),

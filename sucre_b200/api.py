@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 
 from . import engine
@@ -43,6 +44,7 @@ class RestoreResult:
     view_kept: object        # (V,) bool
     store: engine.ObservationStore | None = None
     state: engine.FitState | None = None
+    h2d_bytes: int = 0       # bytes copied host -> device by restore_from_host
 
 
 def restore_resident(scene: engine.DeviceScene, target_key, source_keys, *, min_cover: float = 1e-6,
@@ -63,31 +65,65 @@ def restore_resident(scene: engine.DeviceScene, target_key, source_keys, *, min_
                          store=store, state=state)
 
 
+UPLOAD_MODES = ('footprint', 'rows', 'full')
+
+
+def host_depth_range(depth_u16: torch.Tensor) -> tuple[float, float]:
+    """(smallest non-zero, largest) depth in metres of a host u16 millimetre plane; (65.536, 0.0) if it has no valid pixel."""
+    a = depth_u16.numpy().view(np.uint16)
+    lo = int((a - np.uint16(1)).min()) + 1  # 0 wraps to 65535: the minimum skips invalid pixels
+    return lo / 1000.0, int(a.max()) / 1000.0
+
+
+def upload_plan(host: HostScene, target: int, sources, upload: str = 'footprint'):
+    """Which part of which host view a restoration of `target` against `sources` needs on the device:
+    (needed view indices, (n,4) int32 rectangles x0, y0, x1, y1).  'full': whole views; 'footprint': the target whole,
+    of every other view the rectangle the target can see (engine.DeviceScene.footprints); 'rows': the same widened to
+    whole rows."""
+    if upload not in UPLOAD_MODES:
+        raise ValueError(f'upload must be one of {UPLOAD_MODES}, got {upload!r}')
+    needed = sorted(set(sources) | {target})
+    geoms = [host.geoms[i] for i in needed]
+    rects = np.array([[0, 0, g.width, g.height] for g in geoms], dtype=np.int32)
+    if upload != 'full':
+        fp = engine.DeviceScene.footprints(host.geoms[target], host_depth_range(host.depth[target]), geoms,
+                                           rows_only=upload == 'rows')
+        keep_whole = np.array([i == target for i in needed])
+        rects = np.where(keep_whole[:, None], rects, fp)
+    return needed, rects
+
+
 def restore_from_host(host: HostScene, target: int, sources=None, *, device='cuda', out_J: torch.Tensor | None = None,
-                      **kw) -> RestoreResult:
-    """End to end from host buffers: H2D of every listed view, restore, D2H of J, parameters and history.
+                      upload: str = 'footprint', **kw) -> RestoreResult:
+    """End to end from host buffers: H2D of what the listed views contribute, restore, D2H of J, parameters and
+    history.  upload: see upload_plan — every mode gives the same result bit for bit, the footprint modes copy less.
     out_J: optional (H,W,3) float32 host tensor (ideally pinned) that receives J; otherwise a new pageable tensor."""
     sources = list(range(len(host.geoms))) if sources is None else list(sources)
-    needed = sorted(set(sources) | {target})
+    needed, rects = upload_plan(host, target, sources, upload)
     scene = engine.DeviceScene(device)
-    if len(needed) == len(host.geoms):
-        scene.add_views(needed, host.geoms, host.depth, host.rgb)
+    if upload == 'full':
+        if len(needed) == len(host.geoms):
+            scene.add_views(needed, host.geoms, host.depth, host.rgb)
+        else:
+            for i in needed:
+                scene.add_view(i, host.geoms[i], host.depth[i], host.rgb[i])
+        h2d = len(needed) * (host.depth[0].numel() * 2 + host.rgb[0].numel())
     else:
-        for i in needed:
-            scene.add_view(i, host.geoms[i], host.depth[i], host.rgb[i])
+        h2d = scene.add_views_footprint(needed, [host.geoms[i] for i in needed], host.depth, host.rgb, needed, rects)
     res = restore_resident(scene, target, sources, **kw)
     if out_J is None:
         J = res.J.cpu()
     else:
         J = out_J.copy_(res.J, non_blocking=True)
     params, history = res.params.cpu(), res.history.cpu()  # synchronises the stream: J has landed too
-    return RestoreResult(J=J, params=params, history=history, n_obs=res.n_obs, view_kept=res.view_kept)
+    return RestoreResult(J=J, params=params, history=history, n_obs=res.n_obs, view_kept=res.view_kept, h2d_bytes=h2d)
 
 
-def h2d_bytes(host: HostScene, target: int, sources=None) -> int:
+def h2d_bytes(host: HostScene, target: int, sources=None, upload: str = 'full') -> int:
+    """Bytes restore_from_host copies to the device for this call."""
     sources = list(range(len(host.geoms))) if sources is None else list(sources)
-    n = len(set(sources) | {target})
-    return n * (host.depth[0].numel() * 2 + host.rgb[0].numel())
+    _, rects = upload_plan(host, target, sources, upload)
+    return int(((rects[:, 2] - rects[:, 0]).astype(np.int64) * (rects[:, 3] - rects[:, 1])).sum()) * 5
 
 
 def d2h_bytes(res: RestoreResult) -> int:

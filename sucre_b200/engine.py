@@ -89,6 +89,35 @@ class DeviceScene:
         self._tables.clear()
         self._cull_tables.clear()
 
+    def add_views_footprint(self, keys, geoms, depth_u16: torch.Tensor, rgb_u8: torch.Tensor, src_index, rects) -> int:
+        """Footprint upload: for view keys[i] only the rectangle rects[i] = (x0, y0, x1, y1) of host plane src_index[i]
+        of the stacked (N,H,W) / (N,H,W,3) host tensors (pinned for asynchronous copies) is copied to the device
+        (sucre_scene_upload, cudaMemcpy2DAsync); the rest of the device planes is zero = invalid depth (sfm.py:96).
+        With rectangles from `footprints` the gather reads nothing outside them, so its results are those of a full
+        upload.  Returns the bytes copied."""
+        assert depth_u16.is_contiguous() and rgb_u8.is_contiguous() and depth_u16.element_size() == 2
+        assert rgb_u8.dtype == torch.uint8 and not depth_u16.is_cuda and not rgb_u8.is_cuda
+        H, W = (int(x) for x in depth_u16.shape[1:3])
+        assert tuple(rgb_u8.shape[1:]) == (H, W, 3) and all(g.width == W and g.height == H for g in geoms)
+        n = len(keys)
+        idx = np.ascontiguousarray(src_index, dtype=np.int32).reshape(n)
+        rc = np.ascontiguousarray(rects, dtype=np.int32).reshape(n, 4)
+        d = torch.zeros((n, H, W), dtype=depth_u16.dtype, device=self.device)
+        c = torch.zeros((n, H, W, 3), dtype=torch.uint8, device=self.device)
+        copied, total = C.c_int64(0), 0
+        with torch.cuda.device(self.device):
+            for dst, src, px in ((d, depth_u16, 2), (c, rgb_u8, 3)):
+                _lib.check(_lib.lib().sucre_scene_upload(dst.data_ptr(), src.data_ptr(), n, idx.ctypes.data, W, H, px,
+                                                         rc.ctypes.data, C.byref(copied), _stream(self.device)),
+                           'sucre_scene_upload')
+                total += copied.value
+        for i, (k, g) in enumerate(zip(keys, geoms)):
+            self.geom[k], self.depth[k], self.rgb[k] = g, d[i], c[i]
+            self._ranges.pop(k, None)
+        self._tables.clear()
+        self._cull_tables.clear()
+        return total
+
     def depth_range(self, key) -> tuple[float, float]:
         """(smallest non-zero depth, largest depth) of a view in metres (cached; one small device reduction)."""
         if key not in self._ranges:
@@ -97,6 +126,52 @@ class DeviceScene:
             lo, hi = (int(x) for x in torch.stack([lo, d.max()]).cpu())
             self._ranges[key] = (lo / 1000.0, hi / 1000.0)
         return self._ranges[key]
+
+    @staticmethod
+    def footprints(target_geom: 'ViewGeom', depth_range: tuple[float, float], source_geoms, margin: int = 2,
+                   rows_only: bool = False) -> np.ndarray:
+        """Conservative footprint of a target in each source view (float64, host): (V,4) int32 rectangles
+        (x0, y0, x1, y1), half-open, that contain every source pixel a valid target pixel can land on, hence every
+        source pixel the gather reads (the backward leg and the sampling only touch landing pixels, sfm.py:124, 137).
+        Argument of `possibly_overlapping`: the target's back-projected pixels lie in the convex slab spanned by its
+        four image-corner rays at its smallest and largest depth; when the eight slab corners are in front of the
+        source camera the slab projects inside the convex hull of their projections, so their bounding box (+ `margin`
+        pixels for the fp32 arithmetic of the kernels) bounds every landing pixel.  Otherwise the whole image is
+        returned.  An empty rectangle (x1 <= x0) means no target pixel can land in the view.
+        depth_range = (smallest non-zero, largest) target depth in metres; rows_only widens every rectangle to whole
+        image rows (one contiguous block per plane)."""
+        g = target_geom
+        dmin, dmax = depth_range
+        V = len(source_geoms)
+        Ws = np.array([x.width for x in source_geoms], dtype=np.int64)
+        Hs = np.array([x.height for x in source_geoms], dtype=np.int64)
+        full = np.stack([np.zeros(V, np.int64), np.zeros(V, np.int64), Ws, Hs], axis=1)
+        if V == 0 or dmax <= 0 or dmin > dmax:
+            return full.astype(np.int32)
+        Kinv, R, t = (x.double().numpy() for x in (g.Kinv, g.R, g.t))
+        uv1 = np.array([[0, 0, 1], [g.width, 0, 1], [0, g.height, 1], [g.width, g.height, 1]], dtype=np.float64).T
+        rays = Kinv @ uv1
+        slab = np.concatenate([rays * (dmin * 0.999), rays * (dmax * 1.001)], axis=1)   # (3,8) camera frame
+        world = R @ slab + t
+        Ri = np.stack([x.Ri.double().numpy() for x in source_geoms])
+        ti = np.stack([x.ti.double().numpy() for x in source_geoms])
+        K = np.stack([x.K.double().numpy() for x in source_geoms])
+        c = Ri @ world + ti                                                   # (V,3,8)
+        front = (c[:, 2] > 1e-6).all(axis=1)
+        p = K @ c
+        with np.errstate(divide='ignore', invalid='ignore'):
+            x, y = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2]
+        ok = front & np.isfinite(x).all(axis=1) & np.isfinite(y).all(axis=1)
+        x, y = np.where(ok[:, None], x, 0.0), np.where(ok[:, None], y, 0.0)
+        big = float(1 << 30)
+        lo = lambda a: np.floor(np.clip(a.min(axis=1), -big, big)).astype(np.int64) - margin           # noqa: E731
+        hi = lambda a: np.ceil(np.clip(a.max(axis=1), -big, big)).astype(np.int64) + margin + 1        # noqa: E731
+        rect = np.stack([np.clip(lo(x), 0, Ws), np.clip(lo(y), 0, Hs), np.clip(hi(x), 0, Ws), np.clip(hi(y), 0, Hs)], axis=1)
+        empty = (rect[:, 2] <= rect[:, 0]) | (rect[:, 3] <= rect[:, 1])
+        rect[empty] = 0
+        if rows_only:
+            rect[~empty, 0], rect[~empty, 2] = 0, Ws[~empty]
+        return np.where(ok[:, None], rect, full).astype(np.int32)
 
     def possibly_overlapping(self, target_key, source_keys, source_geoms=None) -> np.ndarray:
         """Conservative frustum pre-test (float64, host): False only for source views in which NO target pixel can land.
