@@ -102,7 +102,7 @@ class DeviceScene:
         n = len(keys)
         idx = np.ascontiguousarray(src_index, dtype=np.int32).reshape(n)
         rc = np.ascontiguousarray(rects, dtype=np.int32).reshape(n, 4)
-        d = torch.zeros((n, H, W), dtype=depth_u16.dtype, device=self.device)
+        d = torch.zeros((n, H, W), dtype=torch.int16, device=self.device).view(depth_u16.dtype)
         c = torch.zeros((n, H, W, 3), dtype=torch.uint8, device=self.device)
         copied, total = C.c_int64(0), 0
         with torch.cuda.device(self.device):
