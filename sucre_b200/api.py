@@ -8,7 +8,7 @@ kernels of libsucre_b200.so.  Replaces sfm.py:127-138 + loader.py:78-118 + sucre
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 import torch
@@ -26,6 +26,7 @@ class HostScene:
     geoms: list
     depth: torch.Tensor
     rgb: torch.Tensor
+    _stacks: tuple | None = field(default=None, repr=False, compare=False)
 
     def pin(self) -> 'HostScene':
         return HostScene(self.geoms, self.depth.pin_memory(), self.rgb.pin_memory())
@@ -33,6 +34,13 @@ class HostScene:
     @property
     def nbytes(self) -> int:
         return self.depth.numel() * 2 + self.rgb.numel()
+
+    def projection_stacks(self, views) -> tuple:
+        """engine.projection_stacks of `views` (float64 copies of the per-view constants, converted once per scene)."""
+        if self._stacks is None:
+            self._stacks = engine.projection_stacks(self.geoms)
+        idx = np.asarray(views, dtype=np.int64)
+        return tuple(a[idx] for a in self._stacks)
 
 
 @dataclass
@@ -75,33 +83,34 @@ def host_depth_range(depth_u16: torch.Tensor) -> tuple[float, float]:
     return lo / 1000.0, int(a.max()) / 1000.0
 
 
-def upload_plan(host: HostScene, target: int, sources, upload: str = 'footprint'):
+def upload_plan(host: HostScene, target: int, sources, upload: str = 'footprint', depth_range=None):
     """Which part of which host view a restoration of `target` against `sources` needs on the device:
     (needed view indices, (n,4) int32 rectangles x0, y0, x1, y1).  'full': whole views; 'footprint': the target whole,
     of every other view the rectangle the target can see (engine.DeviceScene.footprints); 'rows': the same widened to
-    whole rows."""
+    whole rows.  depth_range: (smallest non-zero, largest) target depth in metres if the caller already has it."""
     if upload not in UPLOAD_MODES:
         raise ValueError(f'upload must be one of {UPLOAD_MODES}, got {upload!r}')
     needed = sorted(set(sources) | {target})
-    geoms = [host.geoms[i] for i in needed]
-    rects = np.array([[0, 0, g.width, g.height] for g in geoms], dtype=np.int32)
+    rects = np.array([[0, 0, host.geoms[i].width, host.geoms[i].height] for i in needed], dtype=np.int32)
     if upload != 'full':
-        fp = engine.DeviceScene.footprints(host.geoms[target], host_depth_range(host.depth[target]), geoms,
-                                           rows_only=upload == 'rows')
-        keep_whole = np.array([i == target for i in needed])
-        rects = np.where(keep_whole[:, None], rects, fp)
+        rng = host_depth_range(host.depth[target]) if depth_range is None else depth_range
+        fp = engine.DeviceScene.footprints(host.geoms[target], rng, None, rows_only=upload == 'rows',
+                                           stacks=host.projection_stacks(needed))
+        fp[needed.index(target)] = rects[needed.index(target)]
+        rects = fp
     return needed, rects
 
 
 def restore_from_host(host: HostScene, target: int, sources=None, *, device='cuda', out_J: torch.Tensor | None = None,
                       upload: str = 'footprint', **kw) -> RestoreResult:
     """End to end from host buffers: H2D of what the listed views contribute, restore, D2H of J, parameters and
-    history.  upload: see upload_plan — every mode gives the same result bit for bit, the footprint modes copy less.
+    history.  upload: see upload_plan — every mode gives the same result bit for bit, the footprint modes copy less
+    (the target goes first and whole, its depth range is reduced on the device, then the rectangles follow).
     out_J: optional (H,W,3) float32 host tensor (ideally pinned) that receives J; otherwise a new pageable tensor."""
     sources = list(range(len(host.geoms))) if sources is None else list(sources)
-    needed, rects = upload_plan(host, target, sources, upload)
     scene = engine.DeviceScene(device)
     if upload == 'full':
+        needed, _ = upload_plan(host, target, sources, 'full')
         if len(needed) == len(host.geoms):
             scene.add_views(needed, host.geoms, host.depth, host.rgb)
         else:
@@ -109,7 +118,14 @@ def restore_from_host(host: HostScene, target: int, sources=None, *, device='cud
                 scene.add_view(i, host.geoms[i], host.depth[i], host.rgb[i])
         h2d = len(needed) * (host.depth[0].numel() * 2 + host.rgb[0].numel())
     else:
-        h2d = scene.add_views_footprint(needed, [host.geoms[i] for i in needed], host.depth, host.rgb, needed, rects)
+        needed = sorted(set(sources) | {target})
+        d, c = scene.allocate_views(needed, [host.geoms[i] for i in needed], host.depth.dtype)
+        t = needed.index(target)
+        g = host.geoms[target]
+        h2d = scene.upload_rects((d[t:t + 1], c[t:t + 1]), host.depth, host.rgb, [target], [[0, 0, g.width, g.height]])
+        _, rects = upload_plan(host, target, sources, upload, depth_range=scene.depth_range(target))
+        rects[t] = 0  # already there
+        h2d += scene.upload_rects((d, c), host.depth, host.rgb, needed, rects)
     res = restore_resident(scene, target, sources, **kw)
     if out_J is None:
         J = res.J.cpu()

@@ -111,7 +111,6 @@ constexpr int kChunkCells = SUCRE_FIT_CHUNK;                 // cells per bulk c
 #endif
 constexpr int kStages = SUCRE_FIT_STAGES;                    // ring slots per warp
 constexpr int kRingCells = kChunkCells * kStages;   // 12 KB per warp: 192 KB for the one 16-warp CTA of an SM
-constexpr size_t kFitSmem = (size_t)kFitWarps * kRingCells * sizeof(float4);
 constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
 #ifndef SUCRE_FIT_ILP
 #define SUCRE_FIT_ILP 2
@@ -121,6 +120,13 @@ constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
 #endif
 constexpr int kOversub = SUCRE_FIT_OVERSUB;           // CTAs launched per resident CTA slot (finer static partition)
 constexpr int kIlp = SUCRE_FIT_ILP;                   // records of one lane in flight per step
+// The first kIlp-1 cells of the ring are mirrored behind its end (a second, tiny bulk copy whenever slot 0 is
+// filled), so that the kIlp consecutive records of a step are always at p[0..kIlp-1] and only the walking pointer
+// wraps — no per-record modulo in the inner loop.
+constexpr int kMirrorCells = kIlp - 1;
+constexpr int kRingStride = kRingCells + kMirrorCells;   // cells per warp in shared memory
+constexpr size_t kFitSmem = (size_t)kFitWarps * kRingStride * sizeof(float4);
+static_assert(kMirrorCells >= 0 && kMirrorCells < kChunkCells, "mirror must be a prefix of one chunk");
 constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
 static_assert(kSegHeaderCells + 32 * kSegViews <= kRingCells - kChunkCells, "a segment must fit in the ring next to one copy in flight");
 
@@ -197,16 +203,16 @@ struct PixelStats {
             const u64 e = mul2(kbg[c], zz);
             const float a = PRECISE ? expf(lo(e)) : fast_exp2(lo(e));   // e^{-beta z}
             const float g = PRECISE ? expf(hi(e)) : fast_exp2(hi(e));   // e^{-gamma z}
-            const float D = fmaf(Bc[c], g, I[c] - Bc[c]);               // I - B (1 - g)
+            const float h = 1.0f - g;
+            const float D = fmaf(-Bc[c], h, I[c]);                      // I - B (1 - g)
             const float Dp = fmaf(nJ[c], a, D);                         // shifted residual D - Jref a
             const u64 Da = pk(Dp, a);
             S12[c] = fma2(Da, pk(a, a), S12[c]);
             if (MODE == kWriteJ) continue;
-            const float h = 1.0f - g;
-            const u64 zag = mul2(zz, pk(a, g));                         // (z a, z g)
+            const u64 Dz = mul2(Da, zz);                                // (D' z, a z): every broadcast factor below is a scalar
             S34[c] = fma2(Da, pk(h, h), S34[c]);
-            S56[c] = fma2(Da, pk(lo(zag), lo(zag)), S56[c]);
-            S78[c] = fma2(Da, pk(hi(zag), hi(zag)), S78[c]);
+            S56[c] = fma2(Dz, pk(a, a), S56[c]);
+            S78[c] = fma2(Dz, pk(g, g), S78[c]);
             S9[c] = fmaf(Dp, Dp, S9[c]);
         }
     }
@@ -267,7 +273,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
-    const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingCells;
+    const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingStride;
     const uint8_t* ring_bytes = reinterpret_cast<const uint8_t*>(ring);
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
     if (lane == 0) {
@@ -297,8 +303,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     auto issue = [&]() {  // lane 0: arm the slot's barrier and start the copy of chunk `next_issue`
         const int first = next_issue * kChunkCells;
         const uint32_t bytes = (uint32_t)min(kChunkCells, n_cells - first) * (uint32_t)sizeof(float4);
-        mbar_expect_tx(bar_s + 8 * issue_slot, bytes);
+        // slot 0 also refreshes the mirror of the ring's first cells behind its end (same barrier)
+        const uint32_t mirror = issue_slot == 0 ? min(bytes, (uint32_t)(kMirrorCells * sizeof(float4))) : 0u;
+        mbar_expect_tx(bar_s + 8 * issue_slot, bytes + mirror);
         bulk_load(ring_s + issue_slot * kChunkCells * (uint32_t)sizeof(float4), src + first, bytes, bar_s + 8 * issue_slot);
+        if (mirror) bulk_load(ring_s + kRingCells * (uint32_t)sizeof(float4), src + first, mirror, bar_s + 8 * issue_slot);
     };
     auto acquire = [&](int upto) {  // cells [0, upto) of the warp's stream have landed
         while (upto > avail) {
@@ -372,24 +381,26 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                 int first = rpos + kSegHeaderCells + (incl - cnt);
                 first -= first >= kRingCells ? kRingCells : 0;
                 // every lane walks its own run (divergent trip count), two records per step for instruction-level
-                // parallelism (their exp / residual chains are independent until the accumulators)
+                // parallelism (their exp / residual chains are independent until the accumulators); the records of a
+                // step are contiguous thanks to the mirror cells, only the walking pointer wraps
                 {
-                    auto cell_at = [&](int k) {
-                        int i = first + k;
-                        i -= i >= kRingCells ? kRingCells : 0;
-                        return i;
-                    };
+                    const float4* rp = ring + first;
                     int k = 0;
 #pragma unroll 1
                     for (; k + kIlp <= cnt; k += kIlp) {
                         float4 r[kIlp];
 #pragma unroll
-                        for (int u = 0; u < kIlp; ++u) r[u] = ring[cell_at(k + u)];
+                        for (int u = 0; u < kIlp; ++u) r[u] = rp[u];
+                        rp += kIlp;
+                        rp -= rp >= ring + kRingCells ? kRingCells : 0;
 #pragma unroll
                         for (int u = 0; u < kIlp; ++u) st.add(r[u], kbg, q.B, nJ);
                     }
 #pragma unroll 1
-                    for (; k < cnt; ++k) st.add(ring[cell_at(k)], kbg, q.B, nJ);
+                    for (; k < cnt; ++k) {  // fewer than kIlp left: they cannot reach past the mirror
+                        st.add(*rp, kbg, q.B, nJ);
+                        ++rp;
+                    }
                 }
                 __syncwarp();
                 seen += cnt;

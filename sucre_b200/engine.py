@@ -27,6 +27,8 @@ class ViewGeom:
     ti: torch.Tensor     # (3,1) Pose.inverse().t = -R.T @ t    sfm.py:47
     width: int
     height: int
+    _rec: np.ndarray | None = field(default=None, repr=False, compare=False)   # sucre_view record without pointers
+    _f64: tuple | None = field(default=None, repr=False, compare=False)        # (Ri, ti, K) as float64 numpy
 
     @staticmethod
     def from_pose(K, R, t, width: int, height: int) -> 'ViewGeom':
@@ -37,9 +39,36 @@ class ViewGeom:
         return ViewGeom(K=K, Kinv=K.inverse(), R=R, t=t, Ri=R.T, ti=-R.T @ t, width=int(width), height=int(height))
 
     def record(self, depth_ptr: int = 0, rgb_ptr: int = 0, rgb_format: int = _lib.RGB_U8) -> np.ndarray:
-        c = lambda x: x.contiguous().numpy()  # noqa: E731
-        return _lib.view_record(c(self.K), c(self.Kinv), c(self.R), c(self.t), c(self.Ri), c(self.ti),
-                                self.width, self.height, depth_ptr, rgb_ptr, rgb_format)
+        """The view's `sucre_view` record (the constants are converted once and cached; a ViewGeom is immutable
+        once it has been handed to a scene)."""
+        rec = self.constants().copy()
+        rec['depth'], rec['rgb'], rec['rgb_format'] = depth_ptr, rgb_ptr, rgb_format
+        return rec
+
+    def constants(self) -> np.ndarray:
+        """The `sucre_view` record with null pointers (cached; do not modify)."""
+        if self._rec is None:
+            c = lambda x: x.contiguous().numpy()  # noqa: E731
+            self._rec = _lib.view_record(c(self.K), c(self.Kinv), c(self.R), c(self.t), c(self.Ri), c(self.ti),
+                                         self.width, self.height)
+        return self._rec
+
+    def projection_f64(self) -> tuple:
+        """(Ri, ti, K) as float64 numpy arrays, for the host-side frustum tests (cached)."""
+        if self._f64 is None:
+            self._f64 = tuple(x.double().numpy() for x in (self.Ri, self.ti, self.K))
+        return self._f64
+
+
+def projection_stacks(geoms) -> tuple:
+    """Stacked float64 constants of a list of views for DeviceScene.footprints / possibly_overlapping:
+    (Ri (V,3,3), ti (V,3,1), K (V,3,3), widths (V,), heights (V,))."""
+    if len(geoms) == 0:
+        z = np.zeros((0, 3, 3))
+        return z, np.zeros((0, 3, 1)), z, np.zeros(0, np.int64), np.zeros(0, np.int64)
+    f = [g.projection_f64() for g in geoms]
+    return (np.stack([x[0] for x in f]), np.stack([x[1] for x in f]), np.stack([x[2] for x in f]),
+            np.array([g.width for g in geoms], dtype=np.int64), np.array([g.height for g in geoms], dtype=np.int64))
 
 
 class DeviceScene:
@@ -89,21 +118,36 @@ class DeviceScene:
         self._tables.clear()
         self._cull_tables.clear()
 
-    def add_views_footprint(self, keys, geoms, depth_u16: torch.Tensor, rgb_u8: torch.Tensor, src_index, rects) -> int:
-        """Footprint upload: for view keys[i] only the rectangle rects[i] = (x0, y0, x1, y1) of host plane src_index[i]
-        of the stacked (N,H,W) / (N,H,W,3) host tensors (pinned for asynchronous copies) is copied to the device
-        (sucre_scene_upload, cudaMemcpy2DAsync); the rest of the device planes is zero = invalid depth (sfm.py:96).
-        With rectangles from `footprints` the gather reads nothing outside them, so its results are those of a full
+    def allocate_views(self, keys, geoms, depth_dtype=torch.uint16) -> tuple[torch.Tensor, torch.Tensor]:
+        """Registers equally sized views whose pixels are still to come (upload_rects): returns the stacked device
+        planes (n,H,W) depth — zero = invalid, sfm.py:96 — and (n,H,W,3) colour, which scene.depth[k] / scene.rgb[k]
+        alias.  Colour is left uninitialised: the gather reads it only where the source depth is valid."""
+        n, W, H = len(keys), geoms[0].width, geoms[0].height
+        assert all(g.width == W and g.height == H for g in geoms)
+        d = torch.zeros((n, H, W), dtype=torch.int16, device=self.device).view(depth_dtype)
+        c = torch.empty((n, H, W, 3), dtype=torch.uint8, device=self.device)
+        for i, (k, g) in enumerate(zip(keys, geoms)):
+            self.geom[k], self.depth[k], self.rgb[k] = g, d[i], c[i]
+            self._ranges.pop(k, None)
+        self._tables.clear()
+        self._cull_tables.clear()
+        return d, c
+
+    def upload_rects(self, planes, depth_u16: torch.Tensor, rgb_u8: torch.Tensor, src_index, rects) -> int:
+        """Footprint upload into planes = (d, c) of allocate_views (or slices of them): for plane i only the rectangle
+        rects[i] = (x0, y0, x1, y1) of host view src_index[i] of the stacked (N,H,W) / (N,H,W,3) host tensors (pinned
+        for asynchronous copies) is copied (sucre_scene_upload, cudaMemcpy2DAsync on the current stream).  With
+        rectangles from `footprints` the gather reads nothing outside them, so its results are those of a full
         upload.  Returns the bytes copied."""
+        d, c = planes
+        n, H, W = (int(x) for x in d.shape)
         assert depth_u16.is_contiguous() and rgb_u8.is_contiguous() and depth_u16.element_size() == 2
         assert rgb_u8.dtype == torch.uint8 and not depth_u16.is_cuda and not rgb_u8.is_cuda
-        H, W = (int(x) for x in depth_u16.shape[1:3])
-        assert tuple(rgb_u8.shape[1:]) == (H, W, 3) and all(g.width == W and g.height == H for g in geoms)
-        n = len(keys)
+        assert tuple(depth_u16.shape[1:]) == (H, W) and tuple(rgb_u8.shape[1:]) == (H, W, 3) and c.shape[0] == n
+        assert d.is_contiguous() and c.is_contiguous()
         idx = np.ascontiguousarray(src_index, dtype=np.int32).reshape(n)
         rc = np.ascontiguousarray(rects, dtype=np.int32).reshape(n, 4)
-        d = torch.zeros((n, H, W), dtype=torch.int16, device=self.device).view(depth_u16.dtype)
-        c = torch.zeros((n, H, W, 3), dtype=torch.uint8, device=self.device)
+        assert idx.size == 0 or (idx.min() >= 0 and idx.max() < depth_u16.shape[0] == rgb_u8.shape[0])
         copied, total = C.c_int64(0), 0
         with torch.cuda.device(self.device):
             for dst, src, px in ((d, depth_u16, 2), (c, rgb_u8, 3)):
@@ -111,11 +155,6 @@ class DeviceScene:
                                                          rc.ctypes.data, C.byref(copied), _stream(self.device)),
                            'sucre_scene_upload')
                 total += copied.value
-        for i, (k, g) in enumerate(zip(keys, geoms)):
-            self.geom[k], self.depth[k], self.rgb[k] = g, d[i], c[i]
-            self._ranges.pop(k, None)
-        self._tables.clear()
-        self._cull_tables.clear()
         return total
 
     def depth_range(self, key) -> tuple[float, float]:
@@ -129,7 +168,7 @@ class DeviceScene:
 
     @staticmethod
     def footprints(target_geom: 'ViewGeom', depth_range: tuple[float, float], source_geoms, margin: int = 2,
-                   rows_only: bool = False) -> np.ndarray:
+                   rows_only: bool = False, stacks: tuple | None = None) -> np.ndarray:
         """Conservative footprint of a target in each source view (float64, host): (V,4) int32 rectangles
         (x0, y0, x1, y1), half-open, that contain every source pixel a valid target pixel can land on, hence every
         source pixel the gather reads (the backward leg and the sampling only touch landing pixels, sfm.py:124, 137).
@@ -139,12 +178,11 @@ class DeviceScene:
         pixels for the fp32 arithmetic of the kernels) bounds every landing pixel.  Otherwise the whole image is
         returned.  An empty rectangle (x1 <= x0) means no target pixel can land in the view.
         depth_range = (smallest non-zero, largest) target depth in metres; rows_only widens every rectangle to whole
-        image rows (one contiguous block per plane)."""
+        image rows (one contiguous block per plane); stacks = projection_stacks(source_geoms) if the caller keeps it."""
         g = target_geom
         dmin, dmax = depth_range
-        V = len(source_geoms)
-        Ws = np.array([x.width for x in source_geoms], dtype=np.int64)
-        Hs = np.array([x.height for x in source_geoms], dtype=np.int64)
+        Ri, ti, K, Ws, Hs = projection_stacks(source_geoms) if stacks is None else stacks
+        V = len(Ws)
         full = np.stack([np.zeros(V, np.int64), np.zeros(V, np.int64), Ws, Hs], axis=1)
         if V == 0 or dmax <= 0 or dmin > dmax:
             return full.astype(np.int32)
@@ -153,9 +191,6 @@ class DeviceScene:
         rays = Kinv @ uv1
         slab = np.concatenate([rays * (dmin * 0.999), rays * (dmax * 1.001)], axis=1)   # (3,8) camera frame
         world = R @ slab + t
-        Ri = np.stack([x.Ri.double().numpy() for x in source_geoms])
-        ti = np.stack([x.ti.double().numpy() for x in source_geoms])
-        K = np.stack([x.K.double().numpy() for x in source_geoms])
         c = Ri @ world + ti                                                   # (V,3,8)
         front = (c[:, 2] > 1e-6).all(axis=1)
         p = K @ c
@@ -193,10 +228,7 @@ class DeviceScene:
         world = R @ slab + t
         keys = tuple(source_keys)
         if keys not in self._cull_tables:  # stacked float64 constants of the listed views, built once
-            gs = [self.geom[k] for k in keys] if source_geoms is None else list(source_geoms)
-            self._cull_tables[keys] = (np.stack([x.Ri.double().numpy() for x in gs]), np.stack([x.ti.double().numpy() for x in gs]),
-                                       np.stack([x.K.double().numpy() for x in gs]),
-                                       np.array([x.width for x in gs], dtype=np.float64), np.array([x.height for x in gs], dtype=np.float64))
+            self._cull_tables[keys] = projection_stacks([self.geom[k] for k in keys] if source_geoms is None else list(source_geoms))
         Ri, ti, K, Ws, Hs = self._cull_tables[keys]
         c = Ri @ world + ti                                                   # (V,3,8)
         front = (c[:, 2] > 1e-6).all(axis=1)
@@ -220,8 +252,14 @@ class DeviceScene:
         """Device array of `sucre_view` for `keys` (cached)."""
         keys = tuple(keys)
         if keys not in self._tables:
-            host = np.stack([self.record(k) for k in keys]).view(np.uint8).reshape(len(keys), -1)
-            self._tables[keys] = torch.from_numpy(host).to(self.device)
+            host = np.empty(len(keys), dtype=_lib.VIEW_DTYPE)
+            for i, k in enumerate(keys):
+                host[i] = self.geom[k].constants()
+            rgbs = [self.rgb.get(k) for k in keys]
+            host['depth'] = [self.depth[k].data_ptr() for k in keys]
+            host['rgb'] = [0 if c is None else c.data_ptr() for c in rgbs]
+            host['rgb_format'] = [_lib.RGB_F32 if c is not None and c.dtype == torch.float32 else _lib.RGB_U8 for c in rgbs]
+            self._tables[keys] = torch.from_numpy(host.view(np.uint8).reshape(len(keys), -1)).to(self.device)
         return self._tables[keys]
 
 

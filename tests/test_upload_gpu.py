@@ -47,7 +47,9 @@ def test_scene_upload_copies_exactly_the_rectangles():
     order = [4, 2, 0, 1, 3]
     geoms = [engine.ViewGeom.from_pose(torch.eye(3), torch.eye(3), torch.zeros(3, 1), W, H)] * n
     scene = engine.DeviceScene('cuda:0')
-    copied = scene.add_views_footprint(list('abcde'), geoms, depth, src, order, rects)
+    planes = scene.allocate_views(list('abcde'), geoms, depth.dtype)
+    planes[1].zero_()  # colour planes come uninitialised
+    copied = scene.upload_rects(planes, depth, src, order, rects)
     area = (rects[:, 2] - rects[:, 0]) * (rects[:, 3] - rects[:, 1])
     assert copied == 5 * int(area.sum())
     for i, key in enumerate('abcde'):
@@ -59,4 +61,4 @@ def test_scene_upload_copies_exactly_the_rectangles():
     bad = rects.copy()
     bad[1] = [5, 7, W + 1, 30]
     with pytest.raises(engine._lib.SucreError, match='outside'):
-        scene.add_views_footprint(list('abcde'), geoms, depth, src, order, bad)
+        scene.upload_rects(planes, depth, src, order, bad)
