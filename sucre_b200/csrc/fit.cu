@@ -42,7 +42,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr size_t kWsPartials = 0;                                                   // double[kMaxFitCtas][kSums]
 constexpr size_t kWsPartition = kWsPartials + sizeof(double) * kSums * kMaxFitCtas;  // int[kMaxFitCtas*kFitWarps + 1]
 constexpr size_t kWsTicket = kWsPartition + sizeof(int) * (kMaxFitCtas * kFitWarps + 1 + 3);  // unsigned, 16-aligned
+#ifdef SUCRE_FIT_TIMING  // developer build: %globaltimer at CTA start and at the end of every warp's tile loop (tools/fit_timing.py)
+constexpr size_t kWsTiming = kWsTicket + 16;   // u64[kMaxFitCtas] CTA start, u64[kMaxFitCtas*kFitWarps] warp end, u64 last CTA end
+constexpr size_t kWsBytes = kWsTiming + 8 * (kMaxFitCtas + kMaxFitCtas * kFitWarps + 1);
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#else
 constexpr size_t kWsBytes = kWsTicket + 16;
+#endif
 
 enum FitMode { kClosedForm = 0, kParamJ = 1, kWriteJ = 2 };
 
@@ -234,6 +244,9 @@ struct FitArgs {
     const int* partition;  // per global warp: first tile; [n_warps] = n_tiles
     double* partials;      // gridDim.x rows of kSums
     unsigned* ticket;
+#ifdef SUCRE_FIT_TIMING
+    unsigned long long* timing;
+#endif
     double* sums_out;      // if non-null the last CTA stores the reduced sums here
     float* history_row;    // if non-null: params after the step + cost
     int do_step;           // apply Adam to the 9 scalars in the last CTA
@@ -273,6 +286,9 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
+#ifdef SUCRE_FIT_TIMING
+    if (threadIdx.x == 0) A.timing[blockIdx.x] = globaltimer();
+#endif
     const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingStride;
     const uint8_t* ring_bytes = reinterpret_cast<const uint8_t*>(ring);
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
@@ -459,6 +475,9 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         }
     }
     if (MODE == kWriteJ) return;
+#ifdef SUCRE_FIT_TIMING
+    if (lane == 0) A.timing[kMaxFitCtas + gw] = globaltimer();
+#endif
 
     // warp tree -> one slot per warp -> one row per CTA
     __shared__ double sm[kFitWarps][kSums];
@@ -532,6 +551,9 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     }
     if (threadIdx.x == 9 && A.history_row) A.history_row[9] = (float)tot[9];
     if (threadIdx.x == 0) *A.ticket = 0u;
+#ifdef SUCRE_FIT_TIMING
+    if (threadIdx.x == 0) A.timing[kMaxFitCtas + kMaxFitCtas * kFitWarps] = globaltimer();
+#endif
 }
 
 // Adam step of the 9 scalars from already reduced sums (multi-GPU: after the all-reduce)
@@ -553,8 +575,13 @@ __global__ void adam_step_kernel(const double* __restrict__ sums, AdamScalars ad
 // first tile of every global warp: tiles are split so that every warp gets the same estimated cost.  Cost model
 // (instructions, from the ncu source view): ~55 per block (one record step of the slowest lane), ~110 per segment
 // (header, scan, ring bookkeeping), ~250 per tile (finalisation, J load/store, double accumulation).
+#ifndef SUCRE_COST_BLOCK
+#define SUCRE_COST_BLOCK 4
+#define SUCRE_COST_SEGMENT 8
+#define SUCRE_COST_TILE 18
+#endif
 __device__ __forceinline__ long long cost_prefix(const long long* __restrict__ blk_off, const long long* __restrict__ seg_off, int t) {
-    return 4 * blk_off[t] + 8 * seg_off[t] + 18LL * t;
+    return SUCRE_COST_BLOCK * blk_off[t] + SUCRE_COST_SEGMENT * seg_off[t] + (long long)SUCRE_COST_TILE * t;
 }
 
 __global__ void partition_kernel(const long long* __restrict__ blk_off, const long long* __restrict__ seg_off, int n_tiles,
@@ -646,6 +673,9 @@ static FitArgs base_args(const sucre_store* s, void* workspace) {
     a.partials = (double*)(ws + kWsPartials);
     a.partition = (const int*)(ws + kWsPartition);
     a.ticket = (unsigned*)(ws + kWsTicket);
+#ifdef SUCRE_FIT_TIMING
+    a.timing = (unsigned long long*)(ws + kWsTiming);
+#endif
     a.rank = 0;
     a.world = 1;
     return a;
