@@ -120,3 +120,26 @@ def test_footprints_degenerate_inputs():
     lo, hi = api.host_depth_range(depth)
     a = depth.numpy().view(np.uint16)
     assert lo == a[a > 0].min() / 1000.0 and hi == a.max() / 1000.0
+
+
+def test_view_level_pre_test_agrees_with_the_oracle_and_the_footprints():
+    """DeviceScene.possibly_overlapping (the view-level cull of engine.gather) on the host only: a culled view has
+    no in-bounds forward projection in the oracle, and its footprint rectangle is empty."""
+    scene = SyntheticScene(64, 96, 64, seed=5)
+    views = list(range(64))
+    host, og = _host_scene(scene, views)
+    target = 0
+    ds = object.__new__(DeviceScene)                 # no device: geometry and the cached depth range are all it needs
+    ds.geom = dict(enumerate(host.geoms))
+    ds._ranges = {target: api.host_depth_range(host.depth[target])}
+    ds._cull_tables = {}
+    keep = ds.possibly_overlapping(target, views)
+    assert keep.dtype == bool and keep[target] and 8 <= (~keep).sum() < 64
+    assert np.array_equal(keep, ds.possibly_overlapping(target, views, source_geoms=host.geoms))   # cached tables
+    rects = DeviceScene.footprints(host.geoms[target], ds._ranges[target], host.geoms)
+    dT = host.depth[target].numpy().view(np.uint16)
+    for s in views:
+        if not keep[s]:
+            _, n, n_in = oracle.match_pair(dT, og[target], host.depth[s].numpy().view(np.uint16), og[s])
+            assert n == 0 and n_in == 0
+            assert rects[s, 2] - rects[s, 0] <= 3 or rects[s, 3] - rects[s, 1] <= 3   # at most the 2-pixel margin
