@@ -266,6 +266,9 @@ def ours(args):
     def step_host(_):
         return api.restore_from_host(host, target, keys, device=dev, out_J=J_host, upload=args.upload, **kw)
 
+    def step_host_full(_):
+        return api.restore_from_host(host, target, keys, device=dev, out_J=J_host, upload='full', **kw)
+
     if args.shard != 'targets' and world > 1:
         return ours_pixel_sharded(args, resident, keys, dev, world, rank, local, run_steps, host)
 
@@ -278,6 +281,9 @@ def ours(args):
     run_steps(step_host, 1)
     ms_e2e, res_h = run_steps(step_host, args.steps)
     clocks = sampler.stop() if sampler else None          # sampled across both timed regions (resident + end to end)
+    # for comparison, outside the sampled regions: the same call copying whole views
+    run_steps(step_host_full, 1)
+    ms_full, res_f = run_steps(step_host_full, args.steps)
 
     pv_per_step = V * W * H * world                      # pixel-views all ranks process per step
     n_obs = res.n_obs
@@ -307,7 +313,10 @@ def ours(args):
                 'api': 'sucre_b200.api.restore_from_host (pinned host u16 depth + u8 colour in, J + parameters out)',
                 'upload': f'{args.upload}: {res_h.h2d_bytes / 1e6:.0f} MB of the {host.nbytes / 1e6:.0f} MB host scene are copied '
                           f'per step (the target whole, of every source view the rectangle the target can see; same '
-                          f'result bit for bit as --upload full, tests/test_upload_gpu.py)'},
+                          f'result bit for bit as --upload full, tests/test_upload_gpu.py)',
+                'whole_view_upload': {'value': pv_per_step / (ms_full / args.steps / 1e3), 'unit': UNIT,
+                                      'h2d_bytes_per_step': res_f.h2d_bytes,
+                                      's_per_restored_image': ms_full / args.steps / 1e3}},
         'gpu_launches': args.steps * (api.LAUNCHES_FIXED + args.num_iter),
         'roofline': {'bound': 'hbm', 'kernel': 'fit_kernel<closed form>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
