@@ -285,7 +285,13 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     // cells), so this prologue overlaps the previous iteration's tail.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if defined(SUCRE_FIT_WARP_REMAP) && SUCRE_FIT_WARP_REMAP
+    // untested tuning variant (tools/fit_variants.sh): the four warps of one scheduler (warp % 4) take four CONSECUTIVE
+    // ranges of the partition, whose whole-tile rounding errors cancel pairwise, instead of ranges 4 apart
+    const int gw = blockIdx.x * kFitWarps + ((warp & 3) * (kFitWarps / 4) + (warp >> 2));
+#else
     const int gw = blockIdx.x * kFitWarps + warp;
+#endif
 #ifdef SUCRE_FIT_TIMING
     if (threadIdx.x == 0) A.timing[blockIdx.x] = globaltimer();
 #endif
