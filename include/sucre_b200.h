@@ -15,20 +15,26 @@
  *     SUCRE_TILE_PIXELS (32) consecutive flat pixels, tile k covering p in [32k, 32k+32) — one warp, one lane
  *     per pixel.
  *
- * Observation store produced by the gather and consumed by the fit ("tile-major segmented stream"):
- *   `cells` is an array of 16-byte cells.  For tile k the kept source views with at least one match in the tile
- *   ("blocks", in pairing-list order; lane mask blk_mask[b], view index blk_view[b], b in blk_off[k]..blk_off[k+1])
- *   are grouped SUCRE_SEGMENT_VIEWS (15) at a time into segments (an odd run length keeps the lanes' 16-byte
- *   shared-memory reads on distinct banks).  A segment is SUCRE_SEGMENT_HEADER_CELLS (2)
- *   header cells — 32 bytes, byte i = number of records of lane i's pixel in the segment (0..15) — followed by the
- *   records LANE-MAJOR: lane 0's records (in view order), then lane 1's, ...  One record = float4
- *   {z, I_r, I_g, I_b}: z = ||cP|| the range of the observation in the source camera frame (loader.py:113 +
- *   sucre.py:53), I = source colour / 255 (loader.py:157, 87).  The first cell of tile k is
- *   rec_off[k] + 2*seg_off[k]; tiles follow each other, so any run of tiles is one contiguous byte range (the fit
- *   streams it with 1-D TMA bulk copies).  Total cells = N + 2 * (number of segments).
- *   The light model (--light-model) needs the observation's camera-frame point, not only its norm: its stores use
- *   two cells per record, {cP_x, cP_y, cP_z, ||cP||} {I_r, I_g, I_b, 0} (record_cells = 2; first cell of tile k =
- *   2*rec_off[k] + 2*seg_off[k]), and shorter segments.
+ * Observation store produced by the gather and consumed by the fit ("tile-major ELL rows"):
+ *   `cells` is an array of ROWS of 32 records, one record per lane of a tile.  Within tile k, row j holds for lane
+ *   i the j-th observation of target pixel 32k+i (its kept source views in pairing-list order) or, when the pixel
+ *   has fewer than j+1 observations, an all-zero sentinel record (a real observation always has z > 0).  Tile k has
+ *   rows(k) = max over its 32 pixels of the observation count and starts at row row_off[k]; tiles follow each other,
+ *   so any run of rows is one contiguous byte range (the fit streams it with 1-D TMA bulk copies), a warp reads a
+ *   row as one fully coalesced, bank-conflict-free access, and there are no headers, lane offsets or segment
+ *   boundaries to decode.  Record formats (record_format):
+ *     SUCRE_REC_Z_U8   8 bytes  {float z; uint8 r, g, b, 0}      z = ||cP||, the range of the observation in the
+ *                               source camera frame (loader.py:113 + sucre.py:53); r,g,b the source pixel's u8 colour
+ *                               (the reference's I = u8 / 255, loader.py:157, 87, is formed in the fit's arithmetic)
+ *     SUCRE_REC_Z_F32  16 bytes {z, I_r, I_g, I_b} floats        scenes whose colour was resampled in float
+ *                               (--image-scale, loader.py:158-162)
+ *     SUCRE_REC_P_U8   16 bytes {cP_x, cP_y, cP_z; uint8 r, g, b, 0}   the light model (--light-model) needs the
+ *                               camera-frame point itself (sucre.py:57)
+ *     SUCRE_REC_P_F32  32 bytes {cP_x, cP_y, cP_z, ||cP||} {I_r, I_g, I_b, 0}
+ *   Bytes per row = 32 * record bytes.  Total rows = row_off[n_tiles]; fill = N / (32 * rows).
+ *   For export and parity checks the gather also lists, per tile, its non-empty kept (tile, view) blocks in
+ *   pairing-list order: blk_mask[b] = lane mask, blk_view[b] = view index, b in blk_off[k]..blk_off[k+1]; the j-th
+ *   record of lane i is the j-th block of the tile whose mask has bit i set.
  */
 #ifndef SUCRE_B200_H
 #define SUCRE_B200_H
@@ -40,12 +46,12 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 6
+#define SUCRE_ABI_VERSION 7
 #define SUCRE_TILE_PIXELS 32
-#ifndef SUCRE_SEGMENT_VIEWS
-#define SUCRE_SEGMENT_VIEWS 15
-#endif
-#define SUCRE_SEGMENT_HEADER_CELLS 2
+#define SUCRE_REC_Z_U8 0
+#define SUCRE_REC_Z_F32 1
+#define SUCRE_REC_P_U8 2
+#define SUCRE_REC_P_F32 3
 
 /* One view (source or target).  All matrices row-major fp32, computed on the host with the reference's own
  * expressions so that they are bit-identical to what the reference multiplies by:
@@ -61,31 +67,33 @@ extern "C" {
  * sizeof == 208, 16-byte aligned. */
 #define SUCRE_RGB_U8 0
 #define SUCRE_RGB_F32 1
+/* K (resp. Kinv) has the PINHOLE sparsity [[a,0,b],[0,c,d],[0,0,1]] exactly (entries 1,3,6,7 are +-0 and entry 8 is 1):
+ * the kernels then skip the multiplications by 0 and 1, which cannot change any rounded result (x*0 + y == y). */
+#define SUCRE_VIEW_K_SPARSE 1
+#define SUCRE_VIEW_KINV_SPARSE 2
 typedef struct sucre_view {
     float K[9], Kinv[9], R[9], t[3], Ri[9], ti[3];
     int32_t width, height;
     const uint16_t* depth;
     const void* rgb;
     int32_t rgb_format;
-    int32_t reserved[3];
+    int32_t flags;           /* SUCRE_VIEW_* bits, set by the host from the VALUES of K / Kinv (never assumed) */
+    int32_t reserved[2];
 } sucre_view;
 
 /* The observation store of one target (or of a band of its tiles), as the fit reads it.  A host struct of
- * device pointers.  sizeof == 56. */
+ * device pointers.  sizeof == 40. */
 typedef struct sucre_store {
-    const float* cells;      /* 16-byte cells, 16-byte aligned */
-    const int64_t* rec_off;  /* [n_tiles+1] records before tile k */
-    const int64_t* blk_off;  /* [n_tiles+1] blocks before tile k */
-    const int64_t* seg_off;  /* [n_tiles+1] segments before tile k */
+    const void* cells;       /* rows of 32 records, 16-byte aligned; may be NULL when n_rows == 0 */
+    const int64_t* row_off;  /* [n_tiles+1] rows before tile k */
     int32_t n_tiles;
-    int32_t seg_views;       /* source views per segment this store was planned with (1..15) */
+    int32_t record_format;   /* SUCRE_REC_* */
     int64_t pixels;          /* target pixels covered: min(n_tiles*32, width*height - first_tile*32) */
-    int32_t record_cells;    /* cells per record: 1 = {z, I}; 2 = {cP_x, cP_y, cP_z, ||cP||}, {I_r, I_g, I_b, 0} */
-    int32_t reserved;
+    int64_t n_rows;          /* host copy of row_off[n_tiles] */
 } sucre_store;
 
 int sucre_abi_version(void);
-int sucre_segment_views(void); /* SUCRE_SEGMENT_VIEWS the library was built with */
+int sucre_record_bytes(int record_format); /* 8, 16, 16, 32; 0 for an unknown format */
 const char* sucre_last_error(void);
 
 /* ---- scene upload ---------------------------------------------------------------------------------------------
@@ -114,9 +122,12 @@ int sucre_scene_upload(void* dst, const void* src_host, int n, const int32_t* sr
  *
  * sucre_gather_match: for every target pixel of the band and every listed view, the reference's two-way integer
  * round-trip test.  masks[k*n_views + s] receives the lane mask of local tile k against view s.
- * Bit-exact with the reference (SURVEY.md §8a'). */
+ * Bit-exact with the reference (SURVEY.md §8a').  A conservative per-(warp, view) frustum test skips views in which
+ * none of the warp's 64 target pixels can land (their mask words are written as 0, which is what the full evaluation
+ * gives).  stats (optional, may be NULL; int64[2], ACCUMULATED, zero it first): [0] += (tile, view) pairs skipped by
+ * that test, [1] += forward projections that landed inside the source image (SURVEY.md §8d's n_inbounds). */
 int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
-                       int n_tiles, uint32_t* masks, void* stream);
+                       int n_tiles, uint32_t* masks, int64_t* stats, void* stream);
 
 /* sucre_gather_count: view_count[n_views] (int64) = matches per view over the band (kept or not).
  * Multi-GPU callers all-reduce view_count before sucre_gather_plan: min_cover is a whole-image criterion. */
@@ -126,22 +137,24 @@ int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t*
  * evaluated in double like the reference's Python floats; view_count and target_pixels are WHOLE-IMAGE figures)
  * and the layout of the band's observation store.
  *   view_kept[n_views]   (uint8)  1 if the view passes min_cover
- *   rec_off, blk_off, seg_off [n_tiles+1] (int64) exclusive prefix sums over the band's tiles, kept views only
- *   totals[3] (int64)    {N = observations in the band, blocks, segments}; copy to the host to size the store:
- *                        cells = record_cells*N + 2*segments, blk_mask / blk_view = blocks entries
- * seg_views (1..15): source views per segment; sucre_segment_views() is the value the fit is tuned for. */
+ *   rec_off, blk_off, row_off [n_tiles+1] (int64) exclusive prefix sums over the band's tiles, kept views only:
+ *                        records (observations), blocks = non-empty (tile, view) pairs, rows = the largest observation
+ *                        count among the tile's 32 pixels
+ *   totals[3] (int64)    {N = observations in the band, blocks, rows}; copy to the host to size the store:
+ *                        cells = rows * 32 * sucre_record_bytes(format) bytes, blk_mask / blk_view = blocks entries */
 int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int64_t* view_count,
-                      int64_t target_pixels, double min_cover, int seg_views, uint8_t* view_kept, int64_t* rec_off,
-                      int64_t* blk_off, int64_t* seg_off, int64_t* totals, void* stream);
+                      int64_t target_pixels, double min_cover, uint8_t* view_kept, int64_t* rec_off, int64_t* blk_off,
+                      int64_t* row_off, int64_t* totals, void* stream);
 
 /* sucre_gather_sample: fills the observation store.  Replaces MatchesFile.save_matches / prepare_matches /
  * load_matches (loader.py:68-87, 103-118) and load_rgb's scaling (loader.py:156-163); the HDF5 spill file is
- * replaced by this device-resident store.  cell_src (optional, may be NULL; one uint32 per cell) receives
- * u2 | v2 << 16 at every record cell: the integer source pixel (what the reference stores as int16 u2, v2). */
+ * replaced by this device-resident store.  record_format: SUCRE_REC_*; the U8 formats require every kept view to be
+ * SUCRE_RGB_U8.  cell_src (optional, may be NULL; one uint32 per record slot, index row*32 + lane) receives
+ * u2 | v2 << 16, the integer source pixel (what the reference stores as int16 u2, v2), 0xffffffff at sentinels. */
 int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
-                        int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* rec_off,
-                        const int64_t* blk_off, const int64_t* seg_off, int seg_views, int record_cells, float* cells,
-                        uint32_t* blk_mask, int32_t* blk_view, uint32_t* cell_src, void* stream);
+                        int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
+                        const int64_t* blk_off, int record_format, void* cells, uint32_t* blk_mask, int32_t* blk_view,
+                        uint32_t* cell_src, void* stream);
 
 /* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
  * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for
@@ -154,15 +167,16 @@ int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, 
  * mode SUCRE_FIT_PARAM_J      default CLI mode: J[pixels*3] is an Adam parameter (sucre.py:47-50), initialised by
  *                             the caller to the target image with NaN where target depth <= 0; J_moments
  *                             [pixels*6] = per pixel {exp_avg[3], exp_avg_sq[3]}, zero-initialised.
- * Every iteration reads each cell exactly once. */
+ * Every iteration reads each row exactly once.  Stores must be SUCRE_REC_Z_U8 or SUCRE_REC_Z_F32. */
 #define SUCRE_FIT_CLOSED_FORM 0
 #define SUCRE_FIT_PARAM_J 1
 
 /* Size of the scratch buffer of the fit calls (16-byte aligned, one per observation store). */
 size_t sucre_fit_workspace_bytes(void);
 
-/* Once per observation store, before any other fit call on `workspace`: partitions the tiles over the
- * resident warps by block count (static => reproducible summation order). */
+/* Once per observation store, before any other fit call on `workspace`: partitions the rows over the resident
+ * warps (equal rows + per-tile overhead per warp; a tile may be split between two neighbouring warps of a CTA, which
+ * combine their per-pixel statistics through shared memory; static => reproducible summation order). */
 int sucre_fit_prepare(const sucre_store* store_host, void* workspace, void* stream);
 
 /* One evaluation of the objective at `params`, reduced to sums[10] (double):
@@ -193,13 +207,20 @@ int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* par
  * SUCRE_PEER_BUFFER_BYTES each, zeroed once, mapped into this process, e.g. torch symmetric memory), waits for all
  * ranks' tags and adds the rows in rank order, so every rank applies the identical Adam step with no host or NCCL
  * round trip.  first_epoch: a tag >= 1 for the first iteration, identical on all ranks, and increasing by num_iter
- * from one call on the same buffers to the next.  All ranks must make the same sequence of calls. */
+ * from one call on the same buffers to the next.  All ranks must make the same sequence of calls.  A rank that waits
+ * longer than SUCRE_PEER_TIMEOUT_NS for a peer stops waiting, sets bit 0 of the status word
+ * (sucre_fit_status) and carries on with what it has, so a dead peer cannot hang the node. */
 #define SUCRE_MAX_PEERS 16
 #define SUCRE_PEER_BUFFER_BYTES 3072
+#define SUCRE_PEER_TIMEOUT_NS 2000000000ull
 int sucre_fit_sharded(int mode, const sucre_store* store_host, int64_t n_obs_global, float* params, float* adam_state,
                       float* J, float* J_moments, int first_step, int num_iter, double lr, float* history,
                       void* workspace, const uint64_t* peers_host, int rank, int world, uint32_t first_epoch,
                       void* stream);
+
+/* Copies the status word of `workspace` (0 = fine; bit 0: a peer exchange timed out) to *status (device
+ * pointer, uint32) on `stream`, and clears it. */
+int sucre_fit_status(void* workspace, uint32_t* status, void* stream);
 
 /* Closed-form J for the current params written to J[pixels*3]; NaN where a pixel has no observation (0/0 like
  * sucre.py:77).  J_ref (optional): a previous J used as the reference point of the statistics. */
@@ -208,7 +229,7 @@ int sucre_fit_write_J(const sucre_store* store_host, const float* params, const 
 
 /* ---- stage 2, light model (--light-model, sucre.py:44-46, 54-61) ---------------------------------------------
  * l = exp(-lp^T Sigma^-1 lp / 2) with lp the perspective division of lP = R cP + t, z = ||cP|| + ||lP||,
- * I_hat = l (J e^{-beta z} + B (1 - e^{-gamma z})).  Stores must have record_cells == 2.
+ * I_hat = l (J e^{-beta z} + B (1 - e^{-gamma z})).  Stores must be SUCRE_REC_P_U8 or SUCRE_REC_P_F32.
  * params24 = B[3], beta[3], gamma[3], R[9] row-major, t[3], Sinv[3] = (Sigma^-1)_00, _01, _11 — R, t =
  * se3.exp(cam2light) (se3.py:22-27) and Sigma^-1 = (sigma^T sigma)^-1 are evaluated on the host with the reference's
  * own torch expressions; the chain rule back to cam2light / sigma is applied on the host from sums[10..24].

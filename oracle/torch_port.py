@@ -129,27 +129,32 @@ class FormationModel(torch.nn.Module):
         return 1.0 * (self.J[v, u].T * torch.exp(-self.beta * z) + self.B * (1 - torch.exp(-self.gamma * z)))
 
 
+def adam_iteration(model: FormationModel, views: list[dict], opt, n_obs: int, batch_size: int = 5) -> float:
+    """One iteration of adam() (sucre.py:138-148): zero_grad, update_J, view batches, step.  Returns the cost."""
+    cost = 0.0
+    opt.zero_grad()
+    if model.closed_form:
+        model.solve_J(views)
+    for i in range(0, len(views), batch_size):
+        chunk = views[i:i + batch_size]
+        u = torch.hstack([o['u'] for o in chunk]).long()
+        v = torch.hstack([o['v'] for o in chunk]).long()
+        cP = torch.hstack([o['cP'] for o in chunk])
+        I = torch.hstack([o['I'] for o in chunk])
+        loss = torch.square(I - model(u, v, cP)).sum()
+        (loss / n_obs / 3).backward()
+        cost += loss.item()
+    opt.step()
+    return cost
+
+
 def run_adam(model: FormationModel, views: list[dict], num_iter: int, lr: float = 0.05, batch_size: int = 5):
     """Returns (history (num_iter, 9), cost (num_iter,))."""
     n_obs = sum(o['u'].shape[0] for o in views)
     opt = torch.optim.Adam(model.parameters(), lr=lr)
     history, costs = [], []
     for _ in range(num_iter):
-        cost = 0.0
-        opt.zero_grad()
-        if model.closed_form:
-            model.solve_J(views)
-        for i in range(0, len(views), batch_size):
-            chunk = views[i:i + batch_size]
-            u = torch.hstack([o['u'] for o in chunk]).long()
-            v = torch.hstack([o['v'] for o in chunk]).long()
-            cP = torch.hstack([o['cP'] for o in chunk])
-            I = torch.hstack([o['I'] for o in chunk])
-            loss = torch.square(I - model(u, v, cP)).sum()
-            (loss / n_obs / 3).backward()
-            cost += loss.item()
-        opt.step()
-        costs.append(cost)
+        costs.append(adam_iteration(model, views, opt, n_obs, batch_size))
         history.append(torch.cat([model.B.detach().flatten(), model.beta.detach().flatten(),
                                   model.gamma.detach().flatten()]).clone())
     if model.closed_form:

@@ -9,17 +9,19 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 6
+ABI_VERSION = 7
 TILE = 32
-SEG_HEADER_CELLS = 2
+REC_Z_U8, REC_Z_F32, REC_P_U8, REC_P_F32 = 0, 1, 2, 3
+RECORD_BYTES = {REC_Z_U8: 8, REC_Z_F32: 16, REC_P_U8: 16, REC_P_F32: 32}
 FIT_CLOSED_FORM, FIT_PARAM_J = 0, 1
 
 # numpy mirror of `struct sucre_view` (208 bytes)
 VIEW_DTYPE = np.dtype([('K', '<f4', 9), ('Kinv', '<f4', 9), ('R', '<f4', 9), ('t', '<f4', 3), ('Ri', '<f4', 9),
                        ('ti', '<f4', 3), ('width', '<i4'), ('height', '<i4'), ('depth', '<u8'), ('rgb', '<u8'),
-                       ('rgb_format', '<i4'), ('reserved', '<i4', 3)])
+                       ('rgb_format', '<i4'), ('flags', '<i4'), ('reserved', '<i4', 2)])
 assert VIEW_DTYPE.itemsize == 208
 RGB_U8, RGB_F32 = 0, 1
+VIEW_K_SPARSE, VIEW_KINV_SPARSE = 1, 2
 
 
 class SucreError(RuntimeError):
@@ -27,15 +29,13 @@ class SucreError(RuntimeError):
 
 
 class SucreStore(C.Structure):
-    """ctypes mirror of `struct sucre_store` (host struct of device pointers, 48 bytes)."""
-    _fields_ = [('cells', C.c_void_p), ('rec_off', C.c_void_p), ('blk_off', C.c_void_p), ('seg_off', C.c_void_p),
-                ('n_tiles', C.c_int32), ('seg_views', C.c_int32), ('pixels', C.c_int64),
-                ('record_cells', C.c_int32), ('reserved', C.c_int32)]
+    """ctypes mirror of `struct sucre_store` (host struct of device pointers, 40 bytes)."""
+    _fields_ = [('cells', C.c_void_p), ('row_off', C.c_void_p), ('n_tiles', C.c_int32), ('record_format', C.c_int32),
+                ('pixels', C.c_int64), ('n_rows', C.c_int64)]
 
 
-assert C.sizeof(SucreStore) == 56
+assert C.sizeof(SucreStore) == 40
 MAX_PEERS, PEER_BUFFER_BYTES = 16, 3072
-LIGHT_SEG_VIEWS = 7   # two-cell records: 2 + 2*32*7 = 450 cells per segment at most
 
 
 _lib = None
@@ -43,19 +43,20 @@ _lib = None
 _VP, _I, _I64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_double
 _SIGNATURES = {
     'sucre_abi_version': (C.c_int, []),
-    'sucre_segment_views': (C.c_int, []),
+    'sucre_record_bytes': (C.c_int, [_I]),
     'sucre_last_error': (C.c_char_p, []),
     'sucre_scene_upload': (C.c_int, [_VP, _VP, _I, _VP, _I, _I, _I, _VP, _VP, _VP]),
-    'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
-    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
-    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
     'sucre_fit_workspace_bytes': (C.c_size_t, []),
     'sucre_fit_prepare': (C.c_int, [_VP, _VP, _VP]),
     'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
     'sucre_adam_step': (C.c_int, [_VP, _VP, _VP, _I64, _I, _D, _VP, _VP]),
     'sucre_fit': (C.c_int, [_I, _VP, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP]),
     'sucre_fit_sharded': (C.c_int, [_I, _VP, _I64, _VP, _VP, _VP, _VP, _I, _I, _D, _VP, _VP, _VP, _I, _I, C.c_uint32, _VP]),
+    'sucre_fit_status': (C.c_int, [_VP, _VP, _VP]),
     'sucre_fit_write_J': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     'sucre_light_J': (C.c_int, [_VP, _VP, _VP, _VP]),
     'sucre_light_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),
@@ -79,11 +80,6 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def seg_views() -> int:
-    """Source views per segment of the observation store (SUCRE_SEGMENT_VIEWS of the loaded library)."""
-    return lib().sucre_segment_views()
-
-
 def check(rc: int, what: str):
     if rc != 0:
         raise SucreError(f'{what}: {lib().sucre_last_error().decode()}')
@@ -96,4 +92,12 @@ def view_record(K, Kinv, R, t, Ri, ti, width: int, height: int, depth_ptr: int =
         rec[name] = np.asarray(val, dtype=np.float32).reshape(-1)
     rec['width'], rec['height'], rec['depth'], rec['rgb'] = width, height, depth_ptr, rgb_ptr
     rec['rgb_format'] = rgb_format
+    rec['flags'] = (VIEW_K_SPARSE if _pinhole_sparse(rec['K']) else 0) | (VIEW_KINV_SPARSE if _pinhole_sparse(rec['Kinv']) else 0)
     return rec
+
+
+def _pinhole_sparse(M) -> bool:
+    """True iff the 3x3 matrix is exactly [[a,0,b],[0,c,d],[0,0,1]] (decided on the values: the kernels then skip the
+    multiplications by 0 and 1, which cannot change a rounded result)."""
+    m = np.asarray(M, dtype=np.float32).reshape(9)
+    return bool(m[1] == 0 and m[3] == 0 and m[6] == 0 and m[7] == 0 and m[8] == 1 and np.isfinite(m).all())

@@ -19,7 +19,6 @@ void clear_error() { g_error.clear(); }
 }  // namespace sucre
 
 extern "C" int sucre_abi_version(void) { return SUCRE_ABI_VERSION; }
-extern "C" int sucre_segment_views(void) { return SUCRE_SEGMENT_VIEWS; }
 extern "C" const char* sucre_last_error(void) { return sucre::g_error.c_str(); }
 
 extern "C" int sucre_scene_upload(void* dst, const void* src_host, int n, const int32_t* src_index_host, int width, int height,

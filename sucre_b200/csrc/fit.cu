@@ -1,11 +1,12 @@
 // Stage 2 — per-pixel fit of the underwater image formation model for sm_100a.
 //
-// One warp owns one tile (32 consecutive target pixels), one lane one pixel.  The observation store is a stream
-// of 16-byte cells, tile after tile; within a tile, segments of up to 15 source views: 2 header cells (32 per-lane
-// record counts) then the records {z, I_r, I_g, I_b} LANE-MAJOR, so every lane walks its own contiguous run and
-// the inner loop carries no mask / popcount / shuffle addressing at all.
+// One warp owns a run of tiles (32 consecutive target pixels each), one lane one pixel.  The observation store is
+// a stream of ELL ROWS (include/sucre_b200.h): row j of a tile holds, for every lane, the j-th observation of its
+// pixel or an all-zero sentinel; a tile has as many rows as its fullest pixel has observations.  A row is one
+// coalesced, bank-conflict-free 256-byte access (8-byte records {z, u8 r, g, b}), every lane of the warp walks the
+// same rows, and there is nothing to decode: no headers, offsets or masks in the inner loop.
 //
-// Every Adam iteration reads every record exactly ONCE.  The reference makes two passes (update_J, then
+// Every Adam iteration reads every row exactly ONCE.  The reference makes two passes (update_J, then
 // forward/backward with J held constant, sucre.py:141-146); here both come out of one sweep through per-pixel
 // sufficient statistics of the SHIFTED residual D' = I - B(1 - e^{-gamma z}) - Jref e^{-beta z}, where Jref is
 // the pixel's J of the previous iteration (kept in HBM, 12 B/pixel):
@@ -17,14 +18,21 @@
 // residual scale, so the subtraction-of-sums above does not cancel (an unshifted one-sweep form loses ~3 digits).
 // In the default mode (J is itself an Adam parameter, sucre.py:47-50) Jref IS J, delta = 0, and the pixel's own
 // Adam update is applied in the same kernel.
+// With u8 colour the statistics are kept in 255-scaled units: I = u8 / 255 (loader.py:157) is linear in the byte, so
+// D' * 255 = byte - (255 B) h - (255 Jref) a needs no per-record division; the scale is divided out once per pixel
+// (J) and once per CTA (sums).
+//
+// Balance: the rows (plus a fixed per-tile overhead) are split EVENLY over the resident warps by sucre_fit_prepare.
+// A boundary may fall inside a tile; the warp that gets the tail of such a tile evaluates it first, parks the
+// tile's partial statistics in shared memory, and the neighbouring warp of the same CTA that owns the tile's head
+// adds them before finalising the pixel — so the per-warp work differs by one row at most, whatever the tile sizes,
+// and the summation order stays fixed (bit-reproducible results run to run).
 //
 // Global sums: per-pixel values are promoted to double per thread, reduced by warp shuffles, one double row per
 // CTA; the last CTA to finish (ticket counter) reduces the rows in a fixed order and applies torch.optim.Adam's
-// update to the 9 scalars, so an iteration is ONE kernel and 200 iterations need no host round trip.
-// Tiles are statically partitioned over the resident warps by an instruction-cost model (sucre_fit_prepare), so the
-// summation order — and therefore every bit of the result — is reproducible run to run.  Inside the Adam loop the
-// launches are chained with programmatic dependent launch, and for a target sharded over several GPUs the all-reduce
-// of the sums runs inside the last CTA over NVLink peer memory (sucre_fit_sharded).
+// update to the 9 scalars, so an iteration is ONE kernel and 200 iterations need no host round trip.  Inside the
+// Adam loop the launches are chained with programmatic dependent launch, and for a target sharded over several
+// GPUs the all-reduce of the sums runs inside the last CTA over NVLink peer memory (sucre_fit_sharded).
 #include "common.cuh"
 
 namespace sucre {
@@ -34,25 +42,33 @@ namespace sucre {
 #endif
 constexpr int kFitThreads = SUCRE_FIT_THREADS;
 constexpr int kFitWarps = kFitThreads / 32;
-constexpr int kMaxFitCtas = 2048;
+constexpr int kMaxFitCtas = 1024;
 constexpr int kSums = 10;
+constexpr int kStats = 27;     // per-pixel statistics: 9 per channel
 constexpr float kLog2e = 1.4426950408889634f;
+#ifndef SUCRE_FIT_TILE_COST
+#define SUCRE_FIT_TILE_COST 3  // per-tile overhead (J load/store, finalisation, double accumulation) in row-equivalents
+#endif
+constexpr int kTileCost = SUCRE_FIT_TILE_COST;
 
 // workspace layout (bytes)
-constexpr size_t kWsPartials = 0;                                                   // double[kMaxFitCtas][kSums]
-constexpr size_t kWsPartition = kWsPartials + sizeof(double) * kSums * kMaxFitCtas;  // int[kMaxFitCtas*kFitWarps + 1]
-constexpr size_t kWsTicket = kWsPartition + sizeof(int) * (kMaxFitCtas * kFitWarps + 1 + 3);  // unsigned, 16-aligned
+constexpr size_t kWsPartials = 0;                                                     // double[kMaxFitCtas][kSums]
+constexpr size_t kWsPartRow = kWsPartials + sizeof(double) * kSums * kMaxFitCtas;      // long long[kMaxFitCtas*kFitWarps + 1]
+constexpr size_t kWsPartTile = kWsPartRow + sizeof(long long) * (kMaxFitCtas * kFitWarps + 2);  // int[kMaxFitCtas*kFitWarps + 1]
+constexpr size_t kWsTicket = kWsPartTile + sizeof(int) * (kMaxFitCtas * kFitWarps + 4);  // unsigned ticket, unsigned status; 16-aligned
 #ifdef SUCRE_FIT_TIMING  // developer build: %globaltimer at CTA start and at the end of every warp's tile loop (tools/fit_timing.py)
 constexpr size_t kWsTiming = kWsTicket + 16;   // u64[kMaxFitCtas] CTA start, u64[kMaxFitCtas*kFitWarps] warp end, u64 last CTA end
 constexpr size_t kWsBytes = kWsTiming + 8 * (kMaxFitCtas + kMaxFitCtas * kFitWarps + 1);
+#else
+constexpr size_t kWsBytes = kWsTicket + 16;
+#endif
+static_assert(kWsPartRow % 8 == 0 && kWsPartTile % 8 == 0 && kWsTicket % 16 == 0, "workspace alignment");
+
 __device__ __forceinline__ unsigned long long globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#else
-constexpr size_t kWsBytes = kWsTicket + 16;
-#endif
 
 enum FitMode { kClosedForm = 0, kParamJ = 1, kWriteJ = 2 };
 
@@ -60,24 +76,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-struct Coef {
-    float B[3], kb[3], kg[3];  // kb = -beta log2(e), kg = -gamma log2(e): e^{-beta z} = 2^{kb z}
-    float beta[3], gamma[3];
-};
-
-__device__ __forceinline__ Coef load_coef(const float* __restrict__ p) {
-    Coef q;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        q.B[c] = p[c];
-        q.beta[c] = p[3 + c];
-        q.gamma[c] = p[6 + c];
-        q.kb[c] = -q.beta[c] * kLog2e;
-        q.kg[c] = -q.gamma[c] * kLog2e;
-    }
-    return q;
 }
 
 // torch.optim.Adam (single-tensor, non-capturable CPU branch the reference runs): fp32 state and params,
@@ -105,40 +103,23 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 }
 
 // ---- per-warp bulk-copy ring --------------------------------------------------------------------------------
-// The tiles of one warp are consecutive, so its cells are ONE contiguous byte range in HBM.  The warp streams that
-// range through a private shared-memory ring with cp.async.bulk (TMA 1-D copies of 4 KB, kStages slots, one
-// mbarrier per slot): HBM latency is covered by the copies in flight instead of by occupancy, and the arithmetic
-// reads 16-byte records from shared memory.
-#ifndef SUCRE_FIT_CTAS
-#define SUCRE_FIT_CTAS 1                            // resident CTAs per SM the kernel is shaped for
+// The rows of one warp are ONE contiguous byte range in HBM.  The warp streams that range through a private
+// shared-memory ring with cp.async.bulk (TMA 1-D copies of kChunkBytes, kStages slots, one mbarrier per slot): HBM
+// latency is covered by the copies in flight instead of by occupancy, and the arithmetic reads one record per lane
+// and row from shared memory.  A slot is refilled as soon as the walk has left it.
+#ifndef SUCRE_FIT_CHUNK_BYTES
+#define SUCRE_FIT_CHUNK_BYTES 2560
 #endif
-#ifndef SUCRE_FIT_CHUNK
-#define SUCRE_FIT_CHUNK 256
-#endif
-constexpr int kChunkCells = SUCRE_FIT_CHUNK;                 // cells per bulk copy (2 or 4 KB)
 #ifndef SUCRE_FIT_STAGES
-#define SUCRE_FIT_STAGES 3
+#define SUCRE_FIT_STAGES 4
 #endif
-constexpr int kStages = SUCRE_FIT_STAGES;                    // ring slots per warp
-constexpr int kRingCells = kChunkCells * kStages;   // 12 KB per warp: 192 KB for the one 16-warp CTA of an SM
-constexpr int kSegViews = SUCRE_SEGMENT_VIEWS;
-#ifndef SUCRE_FIT_ILP
-#define SUCRE_FIT_ILP 2
-#endif
-#ifndef SUCRE_FIT_OVERSUB
-#define SUCRE_FIT_OVERSUB 1
-#endif
-constexpr int kOversub = SUCRE_FIT_OVERSUB;           // CTAs launched per resident CTA slot (finer static partition)
-constexpr int kIlp = SUCRE_FIT_ILP;                   // records of one lane in flight per step
-// The first kIlp-1 cells of the ring are mirrored behind its end (a second, tiny bulk copy whenever slot 0 is
-// filled), so that the kIlp consecutive records of a step are always at p[0..kIlp-1] and only the walking pointer
-// wraps — no per-record modulo in the inner loop.
-constexpr int kMirrorCells = kIlp - 1;
-constexpr int kRingStride = kRingCells + kMirrorCells;   // cells per warp in shared memory
-constexpr size_t kFitSmem = (size_t)kFitWarps * kRingStride * sizeof(float4);
-static_assert(kMirrorCells >= 0 && kMirrorCells < kChunkCells, "mirror must be a prefix of one chunk");
-constexpr int kSegHeaderCells = SUCRE_SEGMENT_HEADER_CELLS;
-static_assert(kSegHeaderCells + 32 * kSegViews <= kRingCells - kChunkCells, "a segment must fit in the ring next to one copy in flight");
+constexpr int kChunkBytes = SUCRE_FIT_CHUNK_BYTES;   // 10 rows of 8-byte records, 5 rows of 16-byte records
+constexpr int kStages = SUCRE_FIT_STAGES;
+constexpr int kRingBytes = kChunkBytes * kStages;    // 10 KB per warp
+constexpr size_t kParkBytes = (size_t)kFitWarps * kStats * 32 * sizeof(float);   // 54 KB: parked statistics of split tiles
+constexpr size_t kFitSmem = (size_t)kFitWarps * kRingBytes + kParkBytes;
+static_assert(kChunkBytes % 512 == 0, "a chunk must hold whole rows of both record sizes");
+static_assert(kFitSmem <= 225 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -147,6 +128,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -160,7 +144,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two records per instruction ------------------
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two statistics per instruction ---------------
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) {
     u64 v;
@@ -187,6 +171,44 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// one record as the arithmetic wants it: range z and the three colour values in the store's units
+// (SUCRE_REC_Z_U8: the bytes as exact floats 0..255; SUCRE_REC_Z_F32: I in [0,1])
+struct Obs {
+    float z, x[3];
+};
+template <int REC> struct RecTraits;
+template <> struct RecTraits<SUCRE_REC_Z_U8> {
+    typedef uint2 raw;
+    static constexpr int kBytes = 8;
+    static constexpr float kScale = 255.0f;
+    static __device__ __forceinline__ float range(const raw q) { return __uint_as_float(q.x); }
+    static __device__ __forceinline__ Obs unpack(const raw q) {
+        Obs o;
+        o.z = __uint_as_float(q.x);
+        // byte c | 0x4B000000 is the float 2^23 + byte: one PRMT and one exact subtraction per channel
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o.x[c] = __uint_as_float(__byte_perm(q.y, 0x4B000000u, 0x7650u + c)) - 8388608.0f;
+        return o;
+    }
+};
+template <> struct RecTraits<SUCRE_REC_Z_F32> {
+    typedef float4 raw;
+    static constexpr int kBytes = 16;
+    static constexpr float kScale = 1.0f;
+    static __device__ __forceinline__ float range(const raw q) { return q.x; }
+    static __device__ __forceinline__ Obs unpack(const raw q) {
+        Obs o;
+        o.z = q.x, o.x[0] = q.y, o.x[1] = q.z, o.x[2] = q.w;
+        return o;
+    }
+};
+
 // Per-pixel statistics of one channel, two per packed accumulator so that one FFMA2 updates both:
 //   S12 = (sum D'a, sum a^2)   S34 = (sum D'h, sum a h)   S56 = (sum D'za, sum a za)   S78 = (sum D'zg, sum a zg)
 //   S9  = sum D'^2             (a = e^{-beta z}, g = e^{-gamma z}, h = 1 - g, D' the shifted residual)
@@ -203,47 +225,73 @@ struct PixelStats {
         }
     }
 
-    // kbg[c] = (kb, kg) exponent scales, Bc / nJ = B and -Jref of the channel
-    __device__ __forceinline__ void add(const float4 r, const u64 kbg[3], const float Bc[3], const float nJ[3]) {
-        const float z = r.x;
-        const float I[3] = {r.y, r.z, r.w};
+    // kbg[c] = (kb, kg) exponent scales, Bc / nJ = B and -Jref of the channel (in the store's units).
+    // MASKED: the record may be a sentinel (z == 0, colour 0): its (D', a) pair is multiplied by w = 0, which zeroes
+    // every contribution (the z-weighted ones vanish through z == 0 already).
+    template <bool MASKED>
+    __device__ __forceinline__ void add(const Obs r, const u64 kbg[3], const float Bc[3], const float nJ[3]) {
+        const float z = r.z;
         const u64 zz = pk(z, z);
+        const float w = z != 0.0f ? 1.0f : 0.0f;
+        const u64 ww = pk(w, w);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const u64 e = mul2(kbg[c], zz);
             const float a = PRECISE ? expf(lo(e)) : fast_exp2(lo(e));   // e^{-beta z}
             const float g = PRECISE ? expf(hi(e)) : fast_exp2(hi(e));   // e^{-gamma z}
             const float h = 1.0f - g;
-            const float D = fmaf(-Bc[c], h, I[c]);                      // I - B (1 - g)
+            const float D = fmaf(-Bc[c], h, r.x[c]);                    // I - B (1 - g)
             const float Dp = fmaf(nJ[c], a, D);                         // shifted residual D - Jref a
-            const u64 Da = pk(Dp, a);
+            u64 Da = pk(Dp, a);
+            if (MASKED) Da = mul2(Da, ww);
+            const float Dm = MASKED ? lo(Da) : Dp;
             S12[c] = fma2(Da, pk(a, a), S12[c]);
             if (MODE == kWriteJ) continue;
             const u64 Dz = mul2(Da, zz);                                // (D' z, a z): every broadcast factor below is a scalar
             S34[c] = fma2(Da, pk(h, h), S34[c]);
             S56[c] = fma2(Dz, pk(a, a), S56[c]);
             S78[c] = fma2(Dz, pk(g, g), S78[c]);
-            S9[c] = fmaf(Dp, Dp, S9[c]);
+            S9[c] = fmaf(Dm, Dm, S9[c]);
+        }
+    }
+
+    // parked form: kStats floats per lane, [k][lane]
+    __device__ __forceinline__ void park(float* slot, int lane) const {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            slot[(9 * c + 0) * 32 + lane] = lo(S12[c]), slot[(9 * c + 1) * 32 + lane] = hi(S12[c]);
+            slot[(9 * c + 2) * 32 + lane] = lo(S34[c]), slot[(9 * c + 3) * 32 + lane] = hi(S34[c]);
+            slot[(9 * c + 4) * 32 + lane] = lo(S56[c]), slot[(9 * c + 5) * 32 + lane] = hi(S56[c]);
+            slot[(9 * c + 6) * 32 + lane] = lo(S78[c]), slot[(9 * c + 7) * 32 + lane] = hi(S78[c]);
+            slot[(9 * c + 8) * 32 + lane] = S9[c];
+        }
+    }
+    __device__ __forceinline__ void add_parked(const float* slot, int lane) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            S12[c] = add2(S12[c], pk(slot[(9 * c + 0) * 32 + lane], slot[(9 * c + 1) * 32 + lane]));
+            S34[c] = add2(S34[c], pk(slot[(9 * c + 2) * 32 + lane], slot[(9 * c + 3) * 32 + lane]));
+            S56[c] = add2(S56[c], pk(slot[(9 * c + 4) * 32 + lane], slot[(9 * c + 5) * 32 + lane]));
+            S78[c] = add2(S78[c], pk(slot[(9 * c + 6) * 32 + lane], slot[(9 * c + 7) * 32 + lane]));
+            S9[c] += slot[(9 * c + 8) * 32 + lane];
         }
     }
 };
 
 struct FitArgs {
-    const float4* cells;
-    const long long* rec_off;
-    const long long* blk_off;
-    const long long* seg_off;
+    const unsigned char* cells;
+    const long long* row_off;
     int n_tiles;
-    int seg_views;
     long long pixels;
     float* params;         // 9: B, beta, gamma (read at start; written by the last CTA when do_step)
     float* moments;        // 18: Adam state of the 9 scalars
     float* J;              // pixels*3: Jref (closed form, in/out), the J parameter (in/out), or Jref (write-J, may be null)
     float* J_out;          // pixels*3: write-J mode output
     float* J_moments;      // pixels*6: per pixel {m[3], v[3]} (J parameter mode)
-    const int* partition;  // per global warp: first tile; [n_warps] = n_tiles
+    const long long* part_row;  // per global warp: first row of its stream; [n_warps] = rows of the store
+    const int* part_tile;       // per global warp: first tile it owns (finalises); [n_warps] = n_tiles
     double* partials;      // gridDim.x rows of kSums
-    unsigned* ticket;
+    unsigned* ticket;      // ticket[0] = CTA counter, ticket[1] = status bits
 #ifdef SUCRE_FIT_TIMING
     unsigned long long* timing;
 #endif
@@ -275,102 +323,118 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     return v;
 }
 
-template <int MODE, bool PRECISE>
-__global__ void __launch_bounds__(kFitThreads, SUCRE_FIT_CTAS)
+template <int MODE, int REC, bool PRECISE>
+__global__ void __launch_bounds__(kFitThreads, 1)
 fit_kernel(const __grid_constant__ FitArgs A) {
+    typedef RecTraits<REC> RT;
+    typedef typename RT::raw Raw;
+    constexpr int kRowBytes = 32 * RT::kBytes;
+    constexpr int CR = kChunkBytes / kRowBytes;   // rows per chunk
+    constexpr int RR = CR * kStages;              // rows in the ring
+    constexpr float kScale = RT::kScale;
+    static_assert(CR >= 2, "a chunk must hold at least two rows");
+
     extern __shared__ __align__(128) unsigned char fit_smem[];
     __shared__ __align__(8) unsigned long long bars[kFitWarps][kStages];
+    __shared__ __align__(8) unsigned long long park_bar[kFitWarps];
     // Programmatic dependent launch: let the next iteration's kernel be scheduled as soon as SM resources free up;
     // everything up to griddepcontrol.wait below touches only data that no iteration writes (offsets, partition,
     // cells), so this prologue overlaps the previous iteration's tail.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#if defined(SUCRE_FIT_WARP_REMAP) && SUCRE_FIT_WARP_REMAP
-    // untested tuning variant (tools/fit_variants.sh): the four warps of one scheduler (warp % 4) take four CONSECUTIVE
-    // ranges of the partition, whose whole-tile rounding errors cancel pairwise, instead of ranges 4 apart
-    const int gw = blockIdx.x * kFitWarps + ((warp & 3) * (kFitWarps / 4) + (warp >> 2));
-#else
     const int gw = blockIdx.x * kFitWarps + warp;
-#endif
 #ifdef SUCRE_FIT_TIMING
     if (threadIdx.x == 0) A.timing[blockIdx.x] = globaltimer();
 #endif
-    const float4* ring = reinterpret_cast<const float4*>(fit_smem) + warp * kRingStride;
-    const uint8_t* ring_bytes = reinterpret_cast<const uint8_t*>(ring);
+    const unsigned char* ring = fit_smem + (size_t)warp * kRingBytes;
+    float* const park_all = reinterpret_cast<float*>(fit_smem + (size_t)kFitWarps * kRingBytes);
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(bar_s + 8 * s, 1);
+        mbar_init(smem_u32(&park_bar[warp]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();  // the park barrier of a warp is waited on by its neighbour
 
     double acc[kSums];
 #pragma unroll
     for (int i = 0; i < kSums; ++i) acc[i] = 0.0;
 
-    const int t_begin = A.partition[gw], t_end = A.partition[gw + 1];
-    const long long C0 = A.rec_off[t_begin] + kSegHeaderCells * A.seg_off[t_begin];
-    const int n_cells = (int)(A.rec_off[t_end] + kSegHeaderCells * A.seg_off[t_end] - C0);
-    const int n_chunks = (n_cells + kChunkCells - 1) / kChunkCells;
-    const float4* src = A.cells + C0;
+    const long long B0 = A.part_row[gw], B1 = A.part_row[gw + 1];
+    const int T0 = A.part_tile[gw], T1 = A.part_tile[gw + 1];
+    const int n_rows_w = (int)(B1 - B0);
+    const int n_chunks = (n_rows_w + CR - 1) / CR;
+    const unsigned char* src = A.cells + B0 * kRowBytes;
 
-    // ring bookkeeping, all warp-uniform
+    // ring bookkeeping, all warp-uniform (stream rows are relative to B0)
     int next_issue = 0, issue_slot = 0;  // next chunk to copy and the slot it goes to
     int wait_slot = 0;                   // slot of the next chunk to wait for
     uint32_t wait_parity = 0;
-    int avail = 0;                       // cells that have landed
-    int free_at = kChunkCells;           // the oldest slot is recyclable once `pos` reaches this
-    int pos = 0, rpos = 0;               // cells consumed; same, modulo the ring size
+    int avail = 0;                       // rows that have landed
+    int release_at = CR;                 // the oldest slot is recyclable once `pos` reaches this
+    int pos = 0, rpos = 0;               // rows consumed; same, modulo the ring size
     auto issue = [&]() {  // lane 0: arm the slot's barrier and start the copy of chunk `next_issue`
-        const int first = next_issue * kChunkCells;
-        const uint32_t bytes = (uint32_t)min(kChunkCells, n_cells - first) * (uint32_t)sizeof(float4);
-        // slot 0 also refreshes the mirror of the ring's first cells behind its end (same barrier)
-        const uint32_t mirror = issue_slot == 0 ? min(bytes, (uint32_t)(kMirrorCells * sizeof(float4))) : 0u;
-        mbar_expect_tx(bar_s + 8 * issue_slot, bytes + mirror);
-        bulk_load(ring_s + issue_slot * kChunkCells * (uint32_t)sizeof(float4), src + first, bytes, bar_s + 8 * issue_slot);
-        if (mirror) bulk_load(ring_s + kRingCells * (uint32_t)sizeof(float4), src + first, mirror, bar_s + 8 * issue_slot);
+        const int first = next_issue * CR;
+        const uint32_t bytes = (uint32_t)min(CR, n_rows_w - first) * (uint32_t)kRowBytes;
+        mbar_expect_tx(bar_s + 8 * issue_slot, bytes);
+        bulk_load(ring_s + issue_slot * (uint32_t)kChunkBytes, src + (size_t)first * kRowBytes, bytes, bar_s + 8 * issue_slot);
     };
-    auto acquire = [&](int upto) {  // cells [0, upto) of the warp's stream have landed
+    auto advance_issue = [&]() {
+        if (lane == 0) issue();
+        ++next_issue;
+        issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
+    };
+    auto acquire = [&](int upto) {  // rows [0, upto) of the warp's stream have landed
         while (upto > avail) {
             mbar_wait(bar_s + 8 * wait_slot, wait_parity);
-            avail += kChunkCells;
+            avail += CR;
             if (++wait_slot == kStages) {
                 wait_slot = 0;
                 wait_parity ^= 1u;
             }
         }
     };
-    for (int c = 0; c < min(kStages, n_chunks); ++c) {
-        if (lane == 0) issue();
-        ++next_issue;
-        issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
-    }
+    auto release = [&]() {  // every lane is done with the oldest slot(s): refill
+        __syncwarp();
+        while (pos >= release_at) {
+            if (next_issue < n_chunks) advance_issue();
+            release_at += CR;
+        }
+    };
+    for (int c = 0; c < min(kStages, n_chunks); ++c) advance_issue();
 
     // the previous iteration (parameters, J, ticket) must be complete and visible from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const Coef q = load_coef(A.params);
-    // per-channel exponent scales packed (beta, gamma): one FMUL2 forms both exponents of a record
-    u64 kbg[3];
+    float Bs[3];   // B in the store's units
+    u64 kbg[3];    // per-channel exponent scales packed (beta, gamma): one FMUL2 forms both exponents of a record
 #pragma unroll
-    for (int c = 0; c < 3; ++c) kbg[c] = PRECISE ? pk(-q.beta[c], -q.gamma[c]) : pk(q.kb[c], q.kg[c]);
+    for (int c = 0; c < 3; ++c) {
+        const float B = A.params[c], beta = A.params[3 + c], gamma = A.params[6 + c];
+        Bs[c] = B * kScale;
+        kbg[c] = PRECISE ? pk(-beta, -gamma) : pk(-beta * kLog2e, -gamma * kLog2e);
+    }
+    constexpr float kInv = 1.0f / kScale;
 
-    long long p_next = (long long)t_begin * kTile + lane;
+    // work items: [the tail of tile T0-1, owned by the previous warp,] then the owned tiles T0 .. T1-1, the last of
+    // which may continue in the next warp's stream
+    const bool has_head = T0 > 0 && A.row_off[T0] > B0;
+    int t = T0 - (has_head ? 1 : 0);
+    long long rend_next = t < T1 ? A.row_off[t + 1] : 0;
+    long long p_next = (long long)t * kTile + lane;
     float Jnext[3] = {0.f, 0.f, 0.f};
-    if (A.J && t_begin < t_end && p_next < A.pixels) {
+    if (A.J && t < T1 && p_next < A.pixels) {
         Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
     }
-    long long blk_next = t_begin < t_end ? A.blk_off[t_begin + 1] : 0;
-    long long blk_cur = t_begin < t_end ? A.blk_off[t_begin] : 0;
 
 #pragma unroll 1
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const int nb = (int)(blk_next - blk_cur);
+    for (; t < T1; ++t) {
+        const bool head = t < T0;
+        const long long rend = rend_next;
         const long long p = p_next;
         float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
-        blk_cur = blk_next;
-        if (tile + 1 < t_end) {  // prefetch the next tile's extent and reference J
-            blk_next = A.blk_off[tile + 2];
+        if (t + 1 < T1) {  // prefetch the next tile's extent and reference J
+            rend_next = A.row_off[t + 2];
             p_next = p + kTile;
             if (A.J && p_next < A.pixels) {
                 Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
@@ -380,78 +444,66 @@ fit_kernel(const __grid_constant__ FitArgs A) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) Jref[c] = Jref[c] == Jref[c] ? Jref[c] : 0.f;  // a NaN reference is no reference
         }
+        const bool cut = rend > B1;                           // the tile's last rows are in the next warp's stream
+        const int rb = (int)((cut ? B1 : rend) - B0);         // stream row where this item ends
         PixelStats<MODE, PRECISE> st;
         st.clear();
-        int seen = 0;
-        if (nb > 0) {  // warp-uniform
-            const float nJ[3] = {-Jref[0], -Jref[1], -Jref[2]};
-            const int nseg = (nb + A.seg_views - 1) / A.seg_views;
+        bool seen = false;
+        {
+            const float nJ[3] = {-Jref[0] * kScale, -Jref[1] * kScale, -Jref[2] * kScale};
+            const unsigned char* lane_ring = ring + lane * RT::kBytes;
+            int r = pos;
+            // two rows per step for instruction-level parallelism (their exp / residual chains are independent until the
+            // accumulators); a lane's observations fill its column from the top, so the second row of a step can only be a
+            // sentinel if... the first may be valid: it is masked arithmetically, the first by the branch
 #pragma unroll 1
-            for (int s = 0; s < nseg; ++s) {
-                acquire(pos + kSegHeaderCells);
-                int hcell = rpos + (lane >> 4);
-                hcell -= hcell >= kRingCells ? kRingCells : 0;
-                const int cnt = ring_bytes[hcell * 16 + (lane & 15)];  // records of this lane's pixel in the segment
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int up = __shfl_up_sync(kFull, incl, o);
-                    incl += lane >= o ? up : 0;
+            for (; r + 2 <= rb; r += 2) {
+                if (r + 2 > avail) acquire(r + 2);
+                const int r1 = rpos + 1 == RR ? 0 : rpos + 1;
+                const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + rpos * kRowBytes);
+                const Raw q1 = *reinterpret_cast<const Raw*>(lane_ring + r1 * kRowBytes);
+                rpos = r1 + 1 == RR ? 0 : r1 + 1;
+                if (RT::range(q0) != 0.0f) {
+                    seen = true;
+                    st.template add<false>(RT::unpack(q0), kbg, Bs, nJ);
+                    st.template add<true>(RT::unpack(q1), kbg, Bs, nJ);
                 }
-                const int n = __shfl_sync(kFull, incl, 31);
-                acquire(pos + kSegHeaderCells + n);
-                int first = rpos + kSegHeaderCells + (incl - cnt);
-                first -= first >= kRingCells ? kRingCells : 0;
-                // every lane walks its own run (divergent trip count), two records per step for instruction-level
-                // parallelism (their exp / residual chains are independent until the accumulators); the records of a
-                // step are contiguous thanks to the mirror cells, only the walking pointer wraps
-                {
-                    const float4* rp = ring + first;
-                    int k = 0;
-#pragma unroll 1
-                    for (; k + kIlp <= cnt; k += kIlp) {
-                        float4 r[kIlp];
-#pragma unroll
-                        for (int u = 0; u < kIlp; ++u) r[u] = rp[u];
-                        rp += kIlp;
-                        rp -= rp >= ring + kRingCells ? kRingCells : 0;
-#pragma unroll
-                        for (int u = 0; u < kIlp; ++u) st.add(r[u], kbg, q.B, nJ);
-                    }
-#pragma unroll 1
-                    for (; k < cnt; ++k) {  // fewer than kIlp left: they cannot reach past the mirror
-                        st.add(*rp, kbg, q.B, nJ);
-                        ++rp;
-                    }
-                }
-                __syncwarp();
-                seen += cnt;
-                pos += kSegHeaderCells + n;
-                rpos += kSegHeaderCells + n;
-                rpos -= rpos >= kRingCells ? kRingCells : 0;
-                if (pos >= free_at) {  // every lane is done with the oldest slot(s): refill
-                    __syncwarp();
-                    while (pos >= free_at) {
-                        if (next_issue < n_chunks) {
-                            if (lane == 0) issue();
-                            ++next_issue;
-                            issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
-                        }
-                        free_at += kChunkCells;
-                    }
-                }
+                pos = r + 2;
+                if (pos >= release_at) release();
             }
+            if (r < rb) {
+                if (r + 1 > avail) acquire(r + 1);
+                const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + rpos * kRowBytes);
+                rpos = rpos + 1 == RR ? 0 : rpos + 1;
+                if (RT::range(q0) != 0.0f) {
+                    seen = true;
+                    st.template add<false>(RT::unpack(q0), kbg, Bs, nJ);
+                }
+                pos = r + 1;
+                if (pos >= release_at) release();
+            }
+        }
+        if (head) {  // hand the partial statistics of the previous warp's last tile over
+            st.park(park_all + (size_t)warp * kStats * 32, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&park_bar[warp]));
+            continue;
+        }
+        if (cut) {   // the next warp evaluated the rest of this tile first thing
+            mbar_wait(smem_u32(&park_bar[warp + 1]), 0);
+            st.add_parked(park_all + (size_t)(warp + 1) * kStats * 32, lane);
         }
         if (MODE == kWriteJ) {
             if (p < A.pixels) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    A.J_out[3 * p + c] = seen ? Jref[c] + lo(st.S12[c]) / hi(st.S12[c]) : __int_as_float(0x7fc00000);
+                    A.J_out[3 * p + c] = seen ? Jref[c] + (lo(st.S12[c]) / hi(st.S12[c])) * kInv : __int_as_float(0x7fc00000);
             }
         } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
             float Jout[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+                // all in the store's units: S1, S3, S5, S7 carry one factor kScale, S9 two
                 const float S1 = lo(st.S12[c]), S3 = lo(st.S34[c]), S5 = lo(st.S56[c]), S7 = lo(st.S78[c]), S9 = st.S9[c];
                 float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
                 if (MODE == kClosedForm) {
@@ -461,16 +513,17 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                     rzg = fmaf(-delta, hi(st.S78[c]), S7);
                     rr = fmaf(-delta, S1, S9);
                 }
-                Jout[c] = Jref[c] + delta;
-                acc[c] += (double)rh;                    // sum r (1 - e^{-gamma z})
-                acc[3 + c] += (double)(Jout[c] * rza);   // sum r J z e^{-beta z}
-                acc[6 + c] += (double)(q.B[c] * rzg);    // sum r B z e^{-gamma z}
-                acc[9] += (double)rr;                    // sum r^2
+                const float Js = fmaf(Jref[c], kScale, delta);   // J in the store's units
+                Jout[c] = Js * kInv;
+                acc[c] += (double)rh;                  // sum r (1 - e^{-gamma z})    x kScale
+                acc[3 + c] += (double)(Js * rza);      // sum r J z e^{-beta z}       x kScale^2
+                acc[6 + c] += (double)(Bs[c] * rzg);   // sum r B z e^{-gamma z}      x kScale^2
+                acc[9] += (double)rr;                  // sum r^2                     x kScale^2
                 if (MODE == kParamJ) {
                     // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step with the pre-step B, beta, gamma (sucre.py:144-148)
                     float* mv = A.J_moments + 6 * p;
                     float m = mv[c], v = mv[3 + c];
-                    Jout[c] = adam_update(Jref[c], (float)(-A.adam.grad_scale) * S1, m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
+                    Jout[c] = adam_update(Jref[c], (float)(-A.adam.grad_scale) * (S1 * kInv), m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
                     mv[c] = m;
                     mv[3 + c] = v;
                 }
@@ -485,7 +538,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     if (lane == 0) A.timing[kMaxFitCtas + gw] = globaltimer();
 #endif
 
-    // warp tree -> one slot per warp -> one row per CTA
+    // warp tree -> one slot per warp -> one row per CTA (the store's units are divided out here, in double)
     __shared__ double sm[kFitWarps][kSums];
     __shared__ unsigned s_ticket;
 #pragma unroll
@@ -498,7 +551,8 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     if (threadIdx.x < kSums) {
         double v = 0.0;
         for (int wi = 0; wi < kFitWarps; ++wi) v += sm[wi][threadIdx.x];
-        A.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v;
+        const double unit = threadIdx.x < 3 ? 1.0 / (double)kScale : 1.0 / ((double)kScale * (double)kScale);
+        A.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v * unit;
         __threadfence();
     }
     __syncthreads();
@@ -521,7 +575,8 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         // [rank]), publishes them with a system-scope release of the epoch tag, waits for the tags of all ranks in
         // its own buffer, and adds the rows in rank order — the same order on every rank, so all ranks take the
         // identical Adam step without any host or NCCL round trip.  Two parities: a rank can be at most one
-        // launch ahead of the slowest reader of its previous message.
+        // launch ahead of the slowest reader of its previous message.  The wait is bounded: after
+        // SUCRE_PEER_TIMEOUT_NS a rank gives up on a silent peer, raises status bit 0 and carries on.
         const unsigned par = A.epoch & 1u;
         if (threadIdx.x < A.world * kSums) {
             const int p = threadIdx.x / kSums, i = threadIdx.x % kSums;
@@ -533,7 +588,14 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         PeerSlot* mine = reinterpret_cast<PeerSlot*>(A.peer[A.rank]) + par * SUCRE_MAX_PEERS;
         if (threadIdx.x < A.world) {
             st_release_sys(&(reinterpret_cast<PeerSlot*>(A.peer[threadIdx.x]) + par * SUCRE_MAX_PEERS + A.rank)->flag, A.epoch);
-            while (ld_acquire_sys(&mine[threadIdx.x].flag) != A.epoch) __nanosleep(64);
+            const unsigned long long t0 = globaltimer();
+            while (ld_acquire_sys(&mine[threadIdx.x].flag) != A.epoch) {
+                __nanosleep(32);
+                if (globaltimer() - t0 > SUCRE_PEER_TIMEOUT_NS) {
+                    atomicOr(A.ticket + 1, 1u);
+                    break;
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x < kSums) {
@@ -578,30 +640,61 @@ __global__ void adam_step_kernel(const double* __restrict__ sums, AdamScalars ad
     if (i == 9 && history_row) history_row[9] = (float)sums[9];
 }
 
-// first tile of every global warp: tiles are split so that every warp gets the same estimated cost.  Cost model
-// (instructions, from the ncu source view): ~55 per block (one record step of the slowest lane), ~110 per segment
-// (header, scan, ring bookkeeping), ~250 per tile (finalisation, J load/store, double accumulation).
-#ifndef SUCRE_COST_BLOCK
-#define SUCRE_COST_BLOCK 4
-#define SUCRE_COST_SEGMENT 8
-#define SUCRE_COST_TILE 18
-#endif
-__device__ __forceinline__ long long cost_prefix(const long long* __restrict__ blk_off, const long long* __restrict__ seg_off, int t) {
-    return SUCRE_COST_BLOCK * blk_off[t] + SUCRE_COST_SEGMENT * seg_off[t] + (long long)SUCRE_COST_TILE * t;
-}
-
-__global__ void partition_kernel(const long long* __restrict__ blk_off, const long long* __restrict__ seg_off, int n_tiles,
-                                 int n_warps, int* __restrict__ partition) {
+// Static partition of the store over the resident warps.  Cost of tile t = kTileCost + rows(t), laid out on a
+// virtual axis (tile t starts at row_off[t] + kTileCost * t).  Two levels: the CTAs split the axis at the tile
+// boundaries nearest to its n_ctas-quantiles; inside a CTA, warp k starts at the k/kFitWarps-quantile of the CTA's
+// range.  A warp boundary inside the rows of a tile SPLITS the tile: the warp before owns it (and its head rows), the
+// warp after starts with its tail rows.  A tile is split at most once (a second boundary inside the same rows moves
+// up to the end of the tile) and never between two CTAs, so the two halves meet in shared memory.
+//   part_tile[w] = first tile warp w owns, part_row[w] = first row of its stream; [n_warps] = (n_tiles, rows).
+__global__ void partition_kernel(const long long* __restrict__ row_off, int n_tiles, int n_ctas, long long* __restrict__ part_row,
+                                 int* __restrict__ part_tile) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_warps = n_ctas * kFitWarps;
     if (w > n_warps) return;
-    const long long total = cost_prefix(blk_off, seg_off, n_tiles);
-    const long long target = (total * w + n_warps - 1) / n_warps;
-    int lo = 0, hi = n_tiles;  // smallest t with cost_prefix(t) >= target
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (cost_prefix(blk_off, seg_off, mid) >= target) hi = mid; else lo = mid + 1;
+    const long long R = row_off[n_tiles];
+    const long long V = R + (long long)kTileCost * n_tiles;
+    auto vstart = [&](int t) { return row_off[t] + (long long)kTileCost * t; };
+    auto tile_of = [&](long long x) {  // largest t in [0, n_tiles) with vstart(t) <= x
+        int lo = 0, hi = n_tiles - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (vstart(mid) <= x) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    };
+    auto cta_boundary = [&](int c) {  // first tile of CTA c: the tile boundary nearest to the quantile
+        if (c >= n_ctas) return n_tiles;
+        const long long x = V * c / n_ctas;
+        const int t = tile_of(x);
+        const long long off = x - vstart(t), cost = kTileCost + row_off[t + 1] - row_off[t];
+        return 2 * off < cost ? t : t + 1;
+    };
+    const int c = w / kFitWarps, k = w % kFitWarps;
+    const int tb = cta_boundary(c);
+    if (k == 0 || tb == n_tiles) {
+        part_tile[w] = tb;
+        part_row[w] = row_off[tb];
+        return;
     }
-    partition[w] = w == n_warps ? n_tiles : lo;
+    const long long Cc = vstart(tb), Cn = vstart(cta_boundary(c + 1));
+    const long long ideal = Cc + (Cn - Cc) * k / kFitWarps;
+    if (ideal >= V) {
+        part_tile[w] = n_tiles;
+        part_row[w] = R;
+        return;
+    }
+    const int t = tile_of(ideal);
+    const long long off = ideal - vstart(t) - kTileCost;  // rows of tile t before the boundary (<= 0: in its overhead part)
+    if (off <= 0) {
+        part_tile[w] = t;
+        part_row[w] = row_off[t];
+        return;
+    }
+    const long long prev = Cc + (Cn - Cc) * (k - 1) / kFitWarps;
+    const bool up = prev - vstart(t) - kTileCost > 0;     // the previous boundary already cut this tile
+    part_tile[w] = t + 1;
+    part_row[w] = up ? row_off[t + 1] : row_off[t] + off;
 }
 
 static bool precise_exp() {
@@ -613,34 +706,43 @@ static bool precise_exp() {
     return v == 1;
 }
 
-template <int MODE, bool PRECISE>
+template <int MODE, int REC, bool PRECISE>
 static int occupancy() {
-    cudaFuncSetAttribute(fit_kernel<MODE, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
+    cudaFuncSetAttribute(fit_kernel<MODE, REC, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFitSmem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<MODE, PRECISE>, kFitThreads, kFitSmem) != cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_kernel<MODE, REC, PRECISE>, kFitThreads, kFitSmem) != cudaSuccess)
         per_sm = 0;
     return per_sm;
 }
 
-// persistent grid shared by every mode (the warp->tile partition is computed for it): resident CTAs of the
-// most register-hungry instantiation
+template <int MODE>
+static int occupancy_mode() {
+    return min(min(occupancy<MODE, SUCRE_REC_Z_U8, false>(), occupancy<MODE, SUCRE_REC_Z_U8, true>()),
+               min(occupancy<MODE, SUCRE_REC_Z_F32, false>(), occupancy<MODE, SUCRE_REC_Z_F32, true>()));
+}
+
+// persistent grid shared by every mode (the warp partition is computed for it): one CTA per SM.  Function attributes
+// and the SM count are per device, so both are set up once per device ordinal.
 static int fit_grid() {
-    static int ctas = 0;
-    if (ctas == 0) {
-        int per_sm = min(min(occupancy<kClosedForm, false>(), occupancy<kClosedForm, true>()),
-                         min(min(occupancy<kParamJ, false>(), occupancy<kParamJ, true>()),
-                             min(occupancy<kWriteJ, false>(), occupancy<kWriteJ, true>())));
+    constexpr int kMaxDevices = 64;
+    static int ctas[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (ctas[dev] == 0) {
+        int per_sm = min(occupancy_mode<kClosedForm>(), min(occupancy_mode<kParamJ>(), occupancy_mode<kWriteJ>()));
         if (per_sm <= 0) per_sm = 1;
-        ctas = min(kMaxFitCtas, num_sms() * per_sm * kOversub);
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        ctas[dev] = min(kMaxFitCtas, sms * min(per_sm, 1));
     }
-    return ctas;
+    return ctas[dev];
 }
 
 // pdl = true: programmatic dependent launch — only when the preceding kernel in the stream is another fit_kernel of
 // the same loop, because the prologue before griddepcontrol.wait reads cells / offsets / partition, which must not
 // have been written by the kernel just before (gather_sample, partition_kernel).
 template <int MODE>
-static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st, bool pdl) {
+static void launch_fit(const FitArgs& a, int rec, int ctas, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(kFitThreads);
@@ -651,33 +753,36 @@ static void launch_fit(const FitArgs& a, int ctas, cudaStream_t st, bool pdl) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (precise_exp()) cudaLaunchKernelEx(&cfg, fit_kernel<MODE, true>, a);
-    else cudaLaunchKernelEx(&cfg, fit_kernel<MODE, false>, a);
+    if (rec == SUCRE_REC_Z_U8) {
+        if (precise_exp()) cudaLaunchKernelEx(&cfg, fit_kernel<MODE, SUCRE_REC_Z_U8, true>, a);
+        else cudaLaunchKernelEx(&cfg, fit_kernel<MODE, SUCRE_REC_Z_U8, false>, a);
+    } else {
+        if (precise_exp()) cudaLaunchKernelEx(&cfg, fit_kernel<MODE, SUCRE_REC_Z_F32, true>, a);
+        else cudaLaunchKernelEx(&cfg, fit_kernel<MODE, SUCRE_REC_Z_F32, false>, a);
+    }
 }
 
 static int check_store(const sucre_store* s, const char* who) {
     SUCRE_REQUIRE(s != nullptr, "%s: null store", who);
-    SUCRE_REQUIRE(s->cells && s->rec_off && s->blk_off && s->seg_off, "%s: null pointer in store", who);
+    SUCRE_REQUIRE(s->row_off, "%s: null row_off in store", who);
+    SUCRE_REQUIRE(s->n_rows >= 0 && (s->cells || s->n_rows == 0), "%s: null cells in a store of %lld rows", who, (long long)s->n_rows);
     SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && s->pixels <= (int64_t)s->n_tiles * kTile, "%s: bad store sizes", who);
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(s->cells) & 15) == 0, "%s: cells must be 16-byte aligned", who);
-    SUCRE_REQUIRE(s->record_cells == 1, "%s: this entry point reads {z, I} stores (record_cells == 1), got %d", who, s->record_cells);
-    SUCRE_REQUIRE(s->seg_views >= 1 && kSegHeaderCells + 32 * s->seg_views <= kRingCells - kChunkCells,
-                  "%s: segments of %d views do not fit the shared-memory ring", who, s->seg_views);
+    SUCRE_REQUIRE(s->record_format == SUCRE_REC_Z_U8 || s->record_format == SUCRE_REC_Z_F32,
+                  "%s: this entry point reads {z, I} stores (SUCRE_REC_Z_U8 / SUCRE_REC_Z_F32), got format %d", who, s->record_format);
     return 0;
 }
 
 static FitArgs base_args(const sucre_store* s, void* workspace) {
     FitArgs a{};
-    a.cells = reinterpret_cast<const float4*>(s->cells);
-    a.rec_off = (const long long*)s->rec_off;
-    a.blk_off = (const long long*)s->blk_off;
-    a.seg_off = (const long long*)s->seg_off;
+    a.cells = reinterpret_cast<const unsigned char*>(s->cells);
+    a.row_off = (const long long*)s->row_off;
     a.n_tiles = s->n_tiles;
-    a.seg_views = s->seg_views;
     a.pixels = s->pixels;
     char* ws = (char*)workspace;
     a.partials = (double*)(ws + kWsPartials);
-    a.partition = (const int*)(ws + kWsPartition);
+    a.part_row = (const long long*)(ws + kWsPartRow);
+    a.part_tile = (const int*)(ws + kWsPartTile);
     a.ticket = (unsigned*)(ws + kWsTicket);
 #ifdef SUCRE_FIT_TIMING
     a.timing = (unsigned long long*)(ws + kWsTiming);
@@ -698,11 +803,12 @@ extern "C" int sucre_fit_prepare(const sucre_store* store_host, void* workspace,
     if (check_store(store_host, "sucre_fit_prepare")) return 1;
     SUCRE_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sucre_fit_prepare: workspace must be non-null, 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_warps = fit_grid() * kFitWarps;
+    const int n_ctas = fit_grid();
+    const int n_warps = n_ctas * kFitWarps;
     char* ws = (char*)workspace;
     SUCRE_CUDA(cudaMemsetAsync(ws + kWsTicket, 0, 16, st));
-    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)store_host->blk_off, (const long long*)store_host->seg_off,
-                                                                 store_host->n_tiles, n_warps, (int*)(ws + kWsPartition));
+    partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)store_host->row_off, store_host->n_tiles, n_ctas,
+                                                                 (long long*)(ws + kWsPartRow), (int*)(ws + kWsPartTile));
     return check_launch("partition_kernel");
 }
 
@@ -719,8 +825,8 @@ extern "C" int sucre_fit_sums(int mode, const sucre_store* store_host, const flo
     a.sums_out = sums;
     a.do_step = 0;
     if (mode == kParamJ) a.adam = adam_scalars(t, lr, n_obs);
-    if (mode == kClosedForm) launch_fit<kClosedForm>(a, fit_grid(), (cudaStream_t)stream, false);
-    else launch_fit<kParamJ>(a, fit_grid(), (cudaStream_t)stream, false);
+    if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream, false);
+    else launch_fit<kParamJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream, false);
     return check_launch("fit_kernel");
 }
 
@@ -761,8 +867,8 @@ static int fit_loop(int mode, const sucre_store* store_host, int64_t n_obs, floa
         a.adam = adam_scalars(first_step + it, lr, n_obs);
         a.history_row = history ? history + (size_t)it * kSums : nullptr;
         a.epoch = first_epoch + (uint32_t)it;
-        if (mode == kClosedForm) launch_fit<kClosedForm>(a, ctas, (cudaStream_t)stream, it > 0);
-        else launch_fit<kParamJ>(a, ctas, (cudaStream_t)stream, it > 0);
+        if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, ctas, (cudaStream_t)stream, it > 0);
+        else launch_fit<kParamJ>(a, store_host->record_format, ctas, (cudaStream_t)stream, it > 0);
     }
     return check_launch(who);
 }
@@ -783,6 +889,18 @@ extern "C" int sucre_fit_sharded(int mode, const sucre_store* store_host, int64_
                     workspace, peers_host, rank, world, first_epoch, stream, "sucre_fit_sharded");
 }
 
+__global__ void status_kernel(unsigned* ticket, uint32_t* out) {
+    *out = ticket[1];
+    ticket[1] = 0u;
+}
+
+extern "C" int sucre_fit_status(void* workspace, uint32_t* status, void* stream) {
+    clear_error();
+    SUCRE_REQUIRE(workspace && status, "sucre_fit_status: null pointer");
+    status_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned*)((char*)workspace + kWsTicket), status);
+    return check_launch("status_kernel");
+}
+
 extern "C" int sucre_fit_write_J(const sucre_store* store_host, const float* params, const float* J_ref, float* J,
                                  void* workspace, void* stream) {
     clear_error();
@@ -792,6 +910,6 @@ extern "C" int sucre_fit_write_J(const sucre_store* store_host, const float* par
     a.params = const_cast<float*>(params);
     a.J = const_cast<float*>(J_ref);
     a.J_out = J;
-    launch_fit<kWriteJ>(a, fit_grid(), (cudaStream_t)stream, false);
+    launch_fit<kWriteJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream, false);
     return check_launch("fit_kernel<write J>");
 }

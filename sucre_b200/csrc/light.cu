@@ -8,8 +8,8 @@
 // of the plain model, the sums that carry dL/dSigma^-1, dL/dR and dL/dt — the host pushes those through matrix_exp
 // and the 2x2 inverse.  Two kernels per iteration instead of one sweep: the light gradients need the final
 // residual of every observation times per-observation geometry, which does not factor through per-pixel
-// statistics the way the plain model does.  Same store walk as fit.cu (one warp per tile, lanes own pixels and walk
-// their lane-major runs), but with direct 128-bit global loads: this optional mode is correctness-first.
+// statistics the way the plain model does.  One warp per tile, lanes own pixels and walk their ELL column with direct,
+// row-coalesced 128-bit global loads: this optional mode is correctness-first.
 #include "common.cuh"
 
 namespace sucre {
@@ -18,7 +18,6 @@ constexpr int kLightThreads = 256;
 constexpr int kLightWarps = kLightThreads / 32;
 constexpr int kLightSums = 25;
 constexpr int kLightMaxCtas = 800;  // kLightSums * kLightMaxCtas doubles fit the fit workspace's partial-sum area
-constexpr int kHdrCells = SUCRE_SEGMENT_HEADER_CELLS;
 
 struct LightParams {
     float B[3], beta[3], gamma[3], R[9], t[3], S[3];
@@ -57,28 +56,35 @@ __device__ __forceinline__ LightGeom light_geom(const LightParams& q, const floa
     return g;
 }
 
-// Walks the records of one tile of a record_cells == 2 store: f(cP cell, I cell) for every record of this lane's pixel.
+// Walks the observations of this lane's pixel in one tile of a SUCRE_REC_P_* store (ELL rows: the lane's column, top
+// to bottom, until the first sentinel): f({cP_x, cP_y, cP_z, ||cP||}, {I_r, I_g, I_b, 0}).  Returns their number.
 template <class F>
 __device__ __forceinline__ int walk_tile(const sucre_store& S, int tile, int lane, F&& f) {
-    const long long b0 = S.blk_off[tile];
-    const int nb = (int)(S.blk_off[tile + 1] - b0);
+    const long long r0 = S.row_off[tile];
+    const int n = (int)(S.row_off[tile + 1] - r0);
     const float4* cells = reinterpret_cast<const float4*>(S.cells);
-    long long cell = 2 * S.rec_off[tile] + kHdrCells * S.seg_off[tile];
     int seen = 0;
-    for (int s0 = 0; s0 < nb; s0 += S.seg_views) {
-        const int cnt = reinterpret_cast<const uint8_t*>(cells + cell)[lane];
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(kFull, incl, o);
-            incl += lane >= o ? up : 0;
+    if (S.record_format == SUCRE_REC_P_U8) {
+        const float4* col = cells + r0 * kTile + lane;
+        for (int j = 0; j < n; ++j) {
+            const float4 q = __ldg(col + (size_t)j * kTile);
+            if (q.z == 0.0f) break;  // sentinel: a real observation has cP_z = source depth > 0
+            // sucre.py:53 cP.norm(dim=0): sequential squares, no fma; loader.py:157: u8 / 255
+            const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)));
+            const uint32_t rgb = __float_as_uint(q.w);
+            f(make_float4(q.x, q.y, q.z, nrm),
+              make_float4(__fdiv_rn((float)(rgb & 0xffu), 255.0f), __fdiv_rn((float)((rgb >> 8) & 0xffu), 255.0f),
+                          __fdiv_rn((float)((rgb >> 16) & 0xffu), 255.0f), 0.f));
+            ++seen;
         }
-        const int n = __shfl_sync(kFull, incl, 31);
-        const float4* run = cells + cell + kHdrCells + 2 * (incl - cnt);
-        for (int k = 0; k < cnt; ++k) f(__ldg(run + 2 * k), __ldg(run + 2 * k + 1));
-        __syncwarp();
-        seen += cnt;
-        cell += kHdrCells + 2 * n;
+    } else {
+        const float4* col = cells + 2 * (r0 * kTile + lane);
+        for (int j = 0; j < n; ++j) {
+            const float4 c = __ldg(col + (size_t)j * 2 * kTile);
+            if (c.z == 0.0f) break;
+            f(c, __ldg(col + (size_t)j * 2 * kTile + 1));
+            ++seen;
+        }
     }
     return seen;
 }
@@ -214,11 +220,11 @@ light_reduce_kernel(const double* __restrict__ partials, int n_rows, double* __r
 
 static int check_light_store(const sucre_store* s, const char* who) {
     SUCRE_REQUIRE(s != nullptr, "%s: null store", who);
-    SUCRE_REQUIRE(s->cells && s->rec_off && s->blk_off && s->seg_off, "%s: null pointer in store", who);
+    SUCRE_REQUIRE(s->cells && s->row_off, "%s: null pointer in store", who);
     SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && s->pixels <= (int64_t)s->n_tiles * kTile, "%s: bad store sizes", who);
-    SUCRE_REQUIRE(s->record_cells == 2, "%s: the light model needs stores with the camera-frame point (record_cells == 2), got %d",
-                  who, s->record_cells);
-    SUCRE_REQUIRE(s->seg_views >= 1 && s->seg_views <= 15, "%s: bad seg_views %d", who, s->seg_views);
+    SUCRE_REQUIRE(s->record_format == SUCRE_REC_P_U8 || s->record_format == SUCRE_REC_P_F32,
+                  "%s: the light model needs stores with the camera-frame point (SUCRE_REC_P_U8 / SUCRE_REC_P_F32), got format %d",
+                  who, s->record_format);
     return 0;
 }
 

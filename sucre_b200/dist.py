@@ -2,13 +2,16 @@
 
 Two ways the path shards, both with the scene replicated on every GPU (a whole survey is <= 8.3 GB):
 
-  * by target image   `shard_targets`: independent restorations, no data-path collective (weak scaling; what
-                      `bench.py --gpus N` and the CLI's --image-list / --image-ids loops use);
+  * by target image   `shard_targets`: independent restorations, no data-path collective (what the CLI's
+                      --image-list / --image-ids loops use under torchrun, configs 3 and 5);
   * by pixel band     `restore_band_sharded`: ONE target, every rank gathers and fits a contiguous band of its
-                      tiles against all views.  Collectives: all-reduce(int64[V]) of the per-view match counts
-                      (min_cover is a whole-image criterion, sfm.py:136; its kept-sum is the global N that normalises
-                      every gradient, sucre.py:135,145), all-reduce(f64[10]) of the residual sums once per Adam
-                      iteration (sucre.py:144-148), all-gather of the J bands at the end.
+                      tiles against all views (what `bench.py --gpus N` times, configs 2 and 4).  Exchange steps:
+                      all-reduce(int64[V]) of the per-view match counts (min_cover is a whole-image criterion,
+                      sfm.py:136; its kept-sum is the global N that normalises every gradient, sucre.py:135,145),
+                      the reduction of the 10 residual sums once per Adam iteration (sucre.py:144-148) — fused into
+                      the fit kernel over NVLink peer memory when a PeerExchange is given, an NCCL all-reduce between
+                      two kernels otherwise — and the assembly of the J bands at the end (direct peer writes into
+                      symmetric memory, or an all-gather).
 
 The choreography is written against a small `ops` interface so that the same code runs with the CUDA kernels
 (`CudaBandOps`, NCCL) and, in the CPU test-suite, with a numpy stand-in over gloo (tests/test_dist_gloo.py).
@@ -17,6 +20,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -37,30 +41,56 @@ def tile_band(n_tiles_total: int, rank: int, world: int) -> tuple[int, int]:
 
 
 class PeerExchange:
-    """Exchange buffers for the in-kernel all-reduce of sucre_fit_sharded: one SUCRE_PEER_BUFFER_BYTES buffer per rank
-    in torch symmetric memory, so that every rank holds a device pointer to every peer's buffer (NVLink / NVSwitch
-    peer access).  Also hands out the epoch tags, which must advance identically on all ranks."""
+    """Symmetric-memory buffers of a group of ranks (torch symmetric memory => every rank holds a device pointer to
+    every peer's buffer, NVLink / NVSwitch peer access):
+      * the exchange buffer of sucre_fit_sharded's in-kernel all-reduce (SUCRE_PEER_BUFFER_BYTES per rank), with the
+        epoch tags, which must advance identically on all ranks;
+      * on demand, a J buffer into which every rank writes its band directly (assemble_J), replacing the all-gather."""
 
     def __init__(self, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
-        group = dist.group.WORLD if group is None else group
+        self._symm = symm_mem
+        self.group = dist.group.WORLD if group is None else group
+        self.device = torch.device(device)
         self.buffer = symm_mem.empty(_lib.PEER_BUFFER_BYTES // 4, dtype=torch.int32, device=device)
         self.buffer.zero_()
-        self.handle = symm_mem.rendezvous(self.buffer, group)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
         self.rank, self.world = self.handle.rank, self.handle.world_size
         if self.world > _lib.MAX_PEERS:
-            raise engine._lib.SucreError(f'at most {_lib.MAX_PEERS} ranks per sharded target')
+            raise _lib.SucreError(f'at most {_lib.MAX_PEERS} ranks per sharded target')
         self.buffer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self._epoch = 1
+        self._J = None          # (capacity, 3) f32 symmetric
+        self._J_handle = None
         torch.cuda.synchronize(device)
-        dist.barrier(group)  # every buffer is zeroed before anybody writes into a peer
+        dist.barrier(self.group)  # every buffer is zeroed before anybody writes into a peer
 
     def take_epochs(self, n: int) -> int:
         first = self._epoch
         self._epoch += n
         if self._epoch >= 2 ** 32:
-            raise engine._lib.SucreError('epoch counter exhausted; create a new PeerExchange')
+            raise _lib.SucreError('epoch counter exhausted; create a new PeerExchange')
         return first
+
+    def _ensure_J(self, pixels: int):
+        if self._J is None or self._J.shape[0] < pixels:   # collective: every rank asks for the same size at the same call
+            self._J = self._symm.empty((pixels, 3), dtype=torch.float32, device=self.device)
+            self._J_handle = self._symm.rendezvous(self._J, self.group)
+
+    def assemble_J(self, local: torch.Tensor, first_pixel: int, pixels: int, root_only: bool = False) -> torch.Tensor:
+        """Every rank stores its band `local` (n, 3) at rows [first_pixel, first_pixel + n) of the symmetric J buffer of
+        every rank (or of rank 0 only), then all ranks meet at a device-side barrier.  Returns this rank's (pixels, 3)
+        buffer view: complete on every rank (on rank 0 only with root_only).  The buffer is overwritten by the next
+        call: consume (or copy) the result on the same stream before restoring the next target."""
+        self._ensure_J(pixels)
+        n = local.shape[0]
+        for peer in ([0] if root_only else range(self.world)):
+            if peer == self.rank:
+                self._J[first_pixel:first_pixel + n].copy_(local)
+            else:  # a tensor aliasing rows [first_pixel, first_pixel + n) of the peer's buffer: the copy crosses NVLink
+                self._J_handle.get_buffer(peer, (n, 3), torch.float32, first_pixel * 3).copy_(local)
+        self._J_handle.barrier()   # stream-ordered after the copies: every band has landed everywhere
+        return self._J[:pixels]
 
 
 @dataclass
@@ -70,6 +100,8 @@ class BandResult:
     history: torch.Tensor    # (num_iter, 10)
     n_obs: int               # global
     view_kept: object
+    status: torch.Tensor | None = None   # device uint32 (0 = fine; bit 0: a peer exchange timed out), fused path only
+    n_local: int = 0
 
 
 class CudaBandOps:
@@ -87,7 +119,7 @@ class CudaBandOps:
     def gather(self, tile_range, min_cover, reduce_counts):
         self.store = engine.gather(self.scene, self.target_key, self.source_keys, min_cover=min_cover,
                                    tile_range=tile_range, reduce_counts=reduce_counts)
-        return self.store.n_obs, self.store.view_kept
+        return self.store.n_obs, self.store.view_kept, self.store.view_count
 
     def init_state(self, params=None):
         J0 = None
@@ -97,26 +129,24 @@ class CudaBandOps:
             J0 = self.scene.rgb_float(self.target_key).reshape(-1, 3)[lo:hi].clone()
             J0[self.scene.depth[self.target_key].view(torch.int16).reshape(-1)[lo:hi] == 0] = float('nan')
         self.state = engine.FitState.initial(self.device, params=params, J0=J0)
-        if self.store.n_obs > 0:
-            self.state.ensure_J(self.store)
-        elif self.state.J is None:
-            self.state.J = torch.zeros(self.store.J_shape, dtype=torch.float32, device=self.device)
+        self.state.ensure_J(self.store)
 
     def new_sums(self):
         return torch.zeros(10, dtype=torch.float64, device=self.device)
 
     def fit_sums(self, sums, n_obs_global, lr):
-        if self.store.n_obs > 0:
-            engine.fit_sums(self.store, self.state, sums, n_obs_global=n_obs_global, lr=lr)
-        else:
-            sums.zero_()
+        engine.fit_sums(self.store, self.state, sums, n_obs_global=n_obs_global, lr=lr)
 
     def adam_step(self, sums, n_obs_global, lr, history_row):
         engine.adam_step(self.state, sums, n_obs_global, lr, history_row)
 
     def fused_fit(self, peers: 'PeerExchange', n_obs_global: int, num_iter: int, lr: float):
-        """The whole Adam loop as one kernel per iteration with the all-reduce fused in (sucre_fit_sharded)."""
+        """The whole Adam loop as one kernel per iteration with the all-reduce fused in (sucre_fit_sharded).  A band
+        without observations still launches: it contributes zero sums and its epoch flag."""
         return engine.fit(self.store, self.state, num_iter, lr, peers=peers, n_obs_global=n_obs_global)
+
+    def status(self):
+        return engine.fit_status(self.store)
 
     def new_history(self, num_iter):
         return torch.empty((num_iter, 10), dtype=torch.float32, device=self.device)
@@ -132,11 +162,13 @@ class CudaBandOps:
 
 
 def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, lr: float = 0.05, params=None,
-                         group=None, peers: PeerExchange | None = None) -> BandResult:
+                         group=None, peers: PeerExchange | None = None, root_only: bool = False) -> BandResult:
     """One target restored by all ranks of `group`, each owning a band of its pixels.  Every rank returns the same
-    parameters and the full J.  `ops` is a CudaBandOps (or a stand-in with the same methods).
-    With `peers` (and a CudaBandOps) the per-iteration all-reduce runs inside the fit kernel over NVLink peer memory;
-    without, it is an NCCL / gloo all-reduce between a sums kernel and a step kernel."""
+    parameters and the full J (with root_only and `peers`: J is complete on rank 0 only).  `ops` is a CudaBandOps
+    (or a stand-in with the same methods).
+    With `peers` (and a CudaBandOps) the per-iteration all-reduce runs inside the fit kernel over NVLink peer memory
+    and the J bands are written straight into every rank's symmetric J buffer; without, both are NCCL / gloo
+    collectives between kernels."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     P = ops.width * ops.height
@@ -147,18 +179,19 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
-    # 1. gather this band; min_cover decided on whole-image counts
-    n_local, view_kept = ops.gather(band, min_cover, all_reduce)
-    n_obs = torch.tensor([n_local], dtype=torch.int64, device=ops.device)
-    all_reduce(n_obs)
-    n_obs = int(n_obs.item())
+    # 1. gather this band; min_cover decided on whole-image counts, whose kept-sum is the global n_obs (sucre.py:135)
+    n_local, view_kept, view_count = ops.gather(band, min_cover, all_reduce)
+    n_obs = int(np.asarray(view_count)[np.asarray(view_kept, dtype=bool)].sum())
     if n_obs == 0:
-        raise engine._lib.SucreError('restore: no observation survives the two-way check and min_cover')
+        raise _lib.SucreError('restore: no observation survives the two-way check and min_cover')
 
     # 2. Adam loop: local sums -> all-reduce(10 doubles) -> identical step on every rank
     ops.init_state(params)
-    if peers is not None and world > 1 and hasattr(ops, 'fused_fit'):
+    status = None
+    fused = peers is not None and world > 1 and hasattr(ops, 'fused_fit')
+    if fused:
         history = ops.fused_fit(peers, n_obs, num_iter, lr)
+        status = ops.status()
     else:
         sums = ops.new_sums()
         history = ops.new_history(num_iter)
@@ -167,20 +200,24 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
             all_reduce(sums)
             ops.adam_step(sums, n_obs, lr, history[it])
 
-    # 3. assemble J: bands differ by at most one tile, pad to the longest
+    # 3. assemble J
     local = ops.band_J()
-    longest = (n_tiles_total + world - 1) // world * TILE
-    padded = torch.full((longest, 3), float('nan'), dtype=local.dtype, device=local.device)
-    padded[:local.shape[0]] = local
-    if world > 1:
-        parts = [torch.empty_like(padded) for _ in range(world)]
-        dist.all_gather(parts, padded, group=group)
-    else:
-        parts = [padded]
-    J = torch.empty((P, 3), dtype=local.dtype, device=local.device)
-    for r, part in enumerate(parts):
-        lo, n = tile_band(n_tiles_total, r, world)
-        lo_px, hi_px = lo * TILE, min(P, (lo + n) * TILE)
-        J[lo_px:hi_px] = part[:hi_px - lo_px]
+    lo_px = band[0] * TILE
+    if fused:
+        J = peers.assemble_J(local, lo_px, P, root_only=root_only)
+    else:  # bands differ by at most one tile: pad to the longest
+        longest = (n_tiles_total + world - 1) // world * TILE
+        padded = torch.full((longest, 3), float('nan'), dtype=local.dtype, device=local.device)
+        padded[:local.shape[0]] = local
+        if world > 1:
+            parts = [torch.empty_like(padded) for _ in range(world)]
+            dist.all_gather(parts, padded, group=group)
+        else:
+            parts = [padded]
+        J = torch.empty((P, 3), dtype=local.dtype, device=local.device)
+        for r, part in enumerate(parts):
+            lo, n = tile_band(n_tiles_total, r, world)
+            lo_r, hi_r = lo * TILE, min(P, (lo + n) * TILE)
+            J[lo_r:hi_r] = part[:hi_r - lo_r]
     return BandResult(J=J.reshape(ops.height, ops.width, 3), params=ops.params(), history=history, n_obs=n_obs,
-                      view_kept=view_kept)
+                      view_kept=view_kept, status=status, n_local=n_local)

@@ -168,7 +168,7 @@ class DeviceScene:
 
     @staticmethod
     def footprints(target_geom: 'ViewGeom', depth_range: tuple[float, float], source_geoms, margin: int = 2,
-                   rows_only: bool = False, stacks: tuple | None = None) -> np.ndarray:
+                   rows_only: bool = False, stacks: tuple | None = None, band_rows: tuple[int, int] | None = None) -> np.ndarray:
         """Conservative footprint of a target in each source view (float64, host): (V,4) int32 rectangles
         (x0, y0, x1, y1), half-open, that contain every source pixel a valid target pixel can land on, hence every
         source pixel the gather reads (the backward leg and the sampling only touch landing pixels, sfm.py:124, 137).
@@ -178,7 +178,8 @@ class DeviceScene:
         pixels for the fp32 arithmetic of the kernels) bounds every landing pixel.  Otherwise the whole image is
         returned.  An empty rectangle (x1 <= x0) means no target pixel can land in the view.
         depth_range = (smallest non-zero, largest) target depth in metres; rows_only widens every rectangle to whole
-        image rows (one contiguous block per plane); stacks = projection_stacks(source_geoms) if the caller keeps it."""
+        image rows (one contiguous block per plane); stacks = projection_stacks(source_geoms) if the caller keeps it;
+        band_rows = (v0, v1): bound only the target's pixel rows [v0, v1) (one rank's band of a sharded target)."""
         g = target_geom
         dmin, dmax = depth_range
         Ri, ti, K, Ws, Hs = projection_stacks(source_geoms) if stacks is None else stacks
@@ -187,7 +188,8 @@ class DeviceScene:
         if V == 0 or dmax <= 0 or dmin > dmax:
             return full.astype(np.int32)
         Kinv, R, t = (x.double().numpy() for x in (g.Kinv, g.R, g.t))
-        uv1 = np.array([[0, 0, 1], [g.width, 0, 1], [0, g.height, 1], [g.width, g.height, 1]], dtype=np.float64).T
+        v0, v1 = (0, g.height) if band_rows is None else (max(0, int(band_rows[0])), min(g.height, int(band_rows[1])))
+        uv1 = np.array([[0, v0, 1], [g.width, v0, 1], [0, v1, 1], [g.width, v1, 1]], dtype=np.float64).T
         rays = Kinv @ uv1
         slab = np.concatenate([rays * (dmin * 0.999), rays * (dmax * 1.001)], axis=1)   # (3,8) camera frame
         world = R @ slab + t
@@ -266,8 +268,8 @@ class DeviceScene:
 # ------------------------------------------------------------------------------------------------------------
 @dataclass
 class ObservationStore:
-    """Tile-major segmented observation stream (layout: include/sucre_b200.h).  Replaces the reference's HDF5
-    spill file + MatchesData (loader.py:36-130)."""
+    """Tile-major ELL observation rows (layout: include/sucre_b200.h).  Replaces the reference's HDF5 spill file +
+    MatchesData (loader.py:36-130)."""
     width: int
     height: int
     source_keys: tuple
@@ -275,26 +277,23 @@ class ObservationStore:
     view_kept: np.ndarray         # (V,) bool  min_cover decision (host)
     n_obs: int                    # records in this store
     n_blocks: int
-    n_segments: int
-    cells: torch.Tensor           # (n_obs + 2*n_segments, 4) f32: per segment 2 header cells + records {z, I_r, I_g, I_b}
-    rec_off: torch.Tensor         # (n_tiles+1,) int64
-    blk_off: torch.Tensor         # (n_tiles+1,) int64
-    seg_off: torch.Tensor         # (n_tiles+1,) int64
+    n_rows: int
+    cells: torch.Tensor           # (max(n_rows, 1), 32, record bytes / 4) f32: ELL rows of records (bit patterns; see `records`)
+    row_off: torch.Tensor         # (n_tiles+1,) int64 rows before tile k
+    blk_off: torch.Tensor         # (n_tiles+1,) int64 blocks before tile k
+    rec_off: torch.Tensor         # (n_tiles+1,) int64 records before tile k
     blk_mask: torch.Tensor        # (n_blocks,) int32 (bit pattern of the uint32 lane mask)
     blk_view: torch.Tensor        # (n_blocks,) int32 index into source_keys
-    cell_src: torch.Tensor | None  # (n_cells,) int32 u2 | v2 << 16 at record cells
+    cell_src: torch.Tensor | None  # (n_rows*32,) int32 u2 | v2 << 16 per record slot, -1 at sentinels
     workspace: torch.Tensor | None = None  # fit scratch, prepared on first use
     first_tile: int = 0           # band of the target this store covers (multi-GPU pixel sharding): tiles
     n_tiles: int = 0              # [first_tile, first_tile + n_tiles); 0 = the whole target (set in __post_init__)
-    seg_views: int = 0            # source views per segment (0 = the library default, set in __post_init__)
-    record_cells: int = 1         # 1: {z, I}; 2: {cP, ||cP||}, {I, 0} (light model)
+    record_format: int = _lib.REC_Z_U8
     stats: dict = field(default_factory=dict)
 
     def __post_init__(self):
         if self.n_tiles == 0:
             self.n_tiles = (self.width * self.height + TILE - 1) // TILE
-        if self.seg_views == 0:
-            self.seg_views = _lib.seg_views()
 
     @property
     def is_band(self) -> bool:
@@ -313,67 +312,96 @@ class ObservationStore:
     def kept_keys(self) -> list:
         return [k for k, keep in zip(self.source_keys, self.view_kept) if keep]
 
+    @property
+    def has_points(self) -> bool:
+        return self.record_format in (_lib.REC_P_U8, _lib.REC_P_F32)
+
+    @property
+    def record_bytes(self) -> int:
+        return _lib.RECORD_BYTES[self.record_format]
+
+    @property
+    def stream_bytes(self) -> int:
+        """Bytes one sweep of the fit reads: every row once."""
+        return self.n_rows * TILE * self.record_bytes
+
+    @property
+    def fill(self) -> float:
+        """Fraction of the record slots that hold an observation (the rest are sentinels below shorter columns)."""
+        return self.n_obs / max(1, self.n_rows * TILE)
+
     def __len__(self) -> int:
         return self.n_obs
 
     def c_struct(self) -> _lib.SucreStore:
-        return _lib.SucreStore(self.cells.data_ptr(), self.rec_off.data_ptr(), self.blk_off.data_ptr(),
-                               self.seg_off.data_ptr(), self.n_tiles, self.seg_views, self.local_pixels,
-                               self.record_cells, 0)
+        return _lib.SucreStore(self.cells.data_ptr(), self.row_off.data_ptr(), self.n_tiles, self.record_format,
+                               self.local_pixels, self.n_rows)
 
     def record_index(self) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """(cell, pixel, view) of every record (device int64 tensors, block-major order): decodes the segment
-        structure from the block masks.  For export / parity checks, not used by the kernels."""
+        """(slot, pixel, view) of every record (device int64 tensors, block-major order); slot = row * 32 + lane.
+        Decoded from the block list: the j-th record of lane i in a tile is the tile's j-th block whose mask has bit
+        i.  For export / parity checks, not used by the kernels."""
         dev = self.cells.device
-        G, HC, RC = self.seg_views, _lib.SEG_HEADER_CELLS, self.record_cells
         nblk_tile = self.blk_off[1:] - self.blk_off[:-1]
         blk_tile = torch.repeat_interleave(torch.arange(self.n_tiles, device=dev), nblk_tile)
-        j = torch.arange(self.n_blocks, device=dev) - self.blk_off[blk_tile]
-        seg = self.seg_off[blk_tile] + j // G                                   # segment of every block
         lanes = torch.arange(32, device=dev, dtype=torch.int64)
         bits = (self.blk_mask.to(torch.int64)[:, None] >> lanes[None, :]) & 1      # (n_blocks, 32)
-        excl = torch.cumsum(bits, dim=0) - bits                                   # records of the lane before block b
-        seg_first_blk = torch.zeros(self.n_segments, dtype=torch.int64, device=dev)
-        is_first = (j % G) == 0
-        seg_first_blk[seg[is_first]] = torch.nonzero(is_first, as_tuple=True)[0]
-        k = excl - excl[seg_first_blk[seg]]                                        # rank within the lane's run
-        cnt = torch.zeros((self.n_segments, 32), dtype=torch.int64, device=dev).index_add_(0, seg, bits)
-        lane_base = torch.cumsum(cnt, dim=1) - cnt
-        n_seg = cnt.sum(dim=1)
-        seg_cell = HC * torch.arange(self.n_segments, device=dev) + RC * (torch.cumsum(n_seg, 0) - n_seg)
-        cell = seg_cell[seg][:, None] + HC + RC * (lane_base[seg] + k)
+        cs = torch.cumsum(bits, dim=0)
+        cs_pad = torch.cat([torch.zeros((1, 32), dtype=torch.int64, device=dev), cs])
+        j = cs - bits - cs_pad[self.blk_off[blk_tile]]                            # rank within the lane's column
+        slot = (self.row_off[blk_tile][:, None] + j) * TILE + lanes[None, :]
         b, lane = torch.nonzero(bits, as_tuple=True)
-        return cell[b, lane], (blk_tile[b] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[b]
+        return slot[b, lane], (blk_tile[b] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[b]
+
+    def _flat(self) -> torch.Tensor:
+        return self.cells.reshape(-1, self.cells.shape[-1])
+
+    def colours(self, slot: torch.Tensor) -> np.ndarray:
+        """(n, 3) float32 I of the records at `slot`, formed like the reference: f32(f64(u8) / 255) (loader.py:157)."""
+        flat = self._flat()
+        if self.record_format in (_lib.REC_Z_F32, _lib.REC_P_F32):
+            cols = slice(1, 4) if self.record_format == _lib.REC_Z_F32 else slice(4, 7)
+            return flat[slot][:, cols].cpu().numpy()
+        word = flat[slot][:, 1 if self.record_format == _lib.REC_Z_U8 else 3].contiguous().view(torch.int32).cpu().numpy()
+        rgb = np.stack([word & 0xff, (word >> 8) & 0xff, (word >> 16) & 0xff], axis=1)
+        return (rgb.astype(np.float64) / 255).astype(np.float32)
+
+    def ranges(self, slot: torch.Tensor) -> torch.Tensor:
+        """(n,) z = ||cP|| of the records at `slot`."""
+        flat = self._flat()
+        if self.record_format in (_lib.REC_Z_U8, _lib.REC_Z_F32):
+            return flat[slot][:, 0]
+        if self.record_format == _lib.REC_P_F32:
+            return flat[slot][:, 3]
+        c = flat[slot][:, :3]   # sequential squares like cP.norm(dim=0) on the reference's path
+        return torch.sqrt(c[:, 0] * c[:, 0] + c[:, 1] * c[:, 1] + c[:, 2] * c[:, 2])
 
     def records(self) -> torch.Tensor:
-        """(n_obs, 4) {z, I_r, I_g, I_b} of every record (headers stripped)."""
-        cell = self.record_index()[0]
-        if self.record_cells == 1:
-            return self.cells[cell]
-        return torch.cat([self.cells[cell][:, 3:4], self.cells[cell + 1][:, :3]], dim=1)
+        """(n_obs, 4) {z, I_r, I_g, I_b} of every record (device f32, block-major order like record_index)."""
+        slot = self.record_index()[0]
+        I = torch.from_numpy(self.colours(slot)).to(self.cells.device)
+        return torch.cat([self.ranges(slot)[:, None], I], dim=1)
 
     def to_reference_layout(self) -> dict:
         """Per kept view (in source_keys order) the arrays the reference's MatchesFile/MatchesData hold
-        (loader.py:68-76, 103-118): u1, v1, u2, v2 int16, z f32, I (3,n) f32 — rows ordered row-major over
-        the target like torch.where (sfm.py:96).  Host numpy; meant for parity tests and --keep-matches."""
-        cell, pixel, view = self.record_index()
+        (loader.py:68-76, 103-118): u1, v1, u2, v2 int16, z f32, I (3,n) f32 (cP (3,n) for stores with points) — rows
+        ordered row-major over the target like torch.where (sfm.py:96).  Host numpy; for parity tests and --keep-matches."""
+        slot, pixel, view = self.record_index()
         out = {}
+        flat = self._flat()
         for vi, key in enumerate(self.source_keys):
             if not self.view_kept[vi]:
                 continue
             sel = (view == vi).nonzero(as_tuple=True)[0]
             sel = sel[torch.argsort(pixel[sel])]
-            p = pixel[sel]
-            rec = self.cells[cell[sel]].cpu().numpy()
+            p, sl = pixel[sel], slot[sel]
             entry = dict(u1=(p % self.width).to(torch.int16).cpu().numpy(),
-                         v1=(p // self.width).to(torch.int16).cpu().numpy())
-            if self.record_cells == 1:
-                entry.update(z=rec[:, 0].copy(), I=np.ascontiguousarray(rec[:, 1:4].T))
-            else:
-                rec2 = self.cells[cell[sel] + 1].cpu().numpy()
-                entry.update(z=rec[:, 3].copy(), cP=np.ascontiguousarray(rec[:, :3].T), I=np.ascontiguousarray(rec2[:, :3].T))
+                         v1=(p // self.width).to(torch.int16).cpu().numpy(),
+                         z=self.ranges(sl).cpu().numpy().copy(), I=np.ascontiguousarray(self.colours(sl).T))
+            if self.has_points:
+                entry['cP'] = np.ascontiguousarray(flat[sl][:, :3].cpu().numpy().T)
             if self.cell_src is not None:
-                src = self.cell_src[cell[sel]].cpu().numpy().view(np.uint32)
+                src = self.cell_src[sl].cpu().numpy().view(np.uint32)
                 entry['u2'] = (src & 0xffff).astype(np.int16)
                 entry['v2'] = (src >> 16).astype(np.int16)
             out[key] = entry
@@ -421,17 +449,17 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
 def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
                    target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
                    reduce_counts=None, with_points: bool = False) -> ObservationStore:
-    """Stage 1 on the device: match -> count -> plan -> (one 24-byte D2H to size the store) -> sample.
+    """Stage 1 on the device: match -> count -> plan -> (one 40-byte D2H to size the store) -> sample.
     Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
     (sfm.py:127-138, loader.py:78-87, 103-118).
 
     tile_range = (first_tile, n_tiles) restricts the call to a band of the target (multi-GPU pixel sharding);
     reduce_counts(view_count) then sums the per-view match counts over all bands in place (an all-reduce), because
     min_cover is a whole-image criterion (sfm.py:136).
-    with_points: keep the camera-frame point cP of every observation (two-cell records), which the light model
-    needs (sucre.py:57); the default store keeps only its norm."""
+    with_points: keep the camera-frame point cP of every observation, which the light model needs (sucre.py:57); the
+    default store keeps only its norm.  Colour stays u8 in the records unless a listed view carries float colour
+    (--image-scale)."""
     L = _lib.lib()
-    record_cells, seg_views = (2, _lib.LIGHT_SEG_VIEWS) if with_points else (1, _lib.seg_views())
     dev = scene.device
     source_keys = tuple(source_keys)
     V = len(source_keys)
@@ -442,6 +470,9 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
     P = W * H
     first_tile, n_tiles = (0, (P + TILE - 1) // TILE) if tile_range is None else (int(tile_range[0]), int(tile_range[1]))
     table = scene.table(source_keys)
+    f32_colour = any(scene.rgb.get(k) is not None and scene.rgb[k].dtype == torch.float32 for k in source_keys)
+    fmt = (_lib.REC_P_F32 if f32_colour else _lib.REC_P_U8) if with_points else (_lib.REC_Z_F32 if f32_colour else _lib.REC_Z_U8)
+    words = _lib.RECORD_BYTES[fmt] // 4
     with torch.cuda.device(dev):
         st = _stream(dev)
         masks = torch.empty((n_tiles, V), dtype=torch.int32, device=dev)
@@ -449,40 +480,38 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
         view_kept = torch.empty(V, dtype=torch.uint8, device=dev)
         rec_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
         blk_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
-        seg_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
-        totals = torch.empty(3, dtype=torch.int64, device=dev)
+        row_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
+        totals = torch.zeros(5, dtype=torch.int64, device=dev)   # plan: {N, blocks, rows}; match statistics: {culled, in bounds}
         tptr = trec.ctypes.data
-        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(), st),
-                   'sucre_gather_match')
+        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
+                                        totals.data_ptr() + 24, st), 'sucre_gather_match')
         _lib.check(L.sucre_gather_count(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), st), 'sucre_gather_count')
         if reduce_counts is not None:
             reduce_counts(view_count)
         _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), P, float(min_cover),
-                                       seg_views, view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
-                                       seg_off.data_ptr(), totals.data_ptr(), st), 'sucre_gather_plan')
-        n_obs, n_blocks, n_segments = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
-        n_cells = record_cells * n_obs + _lib.SEG_HEADER_CELLS * n_segments
-        cells = torch.empty((max(n_cells, 1), 4), dtype=torch.float32, device=dev)
+                                       view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(), row_off.data_ptr(),
+                                       totals.data_ptr(), st), 'sucre_gather_plan')
+        n_obs, n_blocks, n_rows, culled, n_inb = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
+        cells = torch.empty((max(n_rows, 1), TILE, words), dtype=torch.float32, device=dev)
         blk_mask = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
         blk_view = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
-        cell_src = torch.empty(max(n_cells, 1), dtype=torch.int32, device=dev) if keep_src else None
+        cell_src = torch.empty(max(n_rows, 1) * TILE, dtype=torch.int32, device=dev) if keep_src else None
         if n_obs > 0:
             missing = [k for k in source_keys if k not in scene.rgb]
             if missing:
                 raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
             _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
-                                             view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(),
-                                             seg_off.data_ptr(), seg_views, record_cells, cells.data_ptr(),
-                                             blk_mask.data_ptr(),
-                                             blk_view.data_ptr(), 0 if cell_src is None else cell_src.data_ptr(), st),
-                       'sucre_gather_sample')
+                                             view_kept.data_ptr(), row_off.data_ptr(), blk_off.data_ptr(), fmt,
+                                             cells.data_ptr(), blk_mask.data_ptr(), blk_view.data_ptr(),
+                                             0 if cell_src is None else cell_src.data_ptr(), st), 'sucre_gather_sample')
         vc = view_count.cpu().numpy()
         vk = view_kept.cpu().numpy().astype(bool)
+    stats = {'tile_views_culled': culled, 'tile_views': n_tiles * V, 'n_inbounds': n_inb}
     return ObservationStore(width=W, height=H, source_keys=source_keys, view_count=vc, view_kept=vk, n_obs=n_obs,
-                            n_blocks=n_blocks, n_segments=n_segments, cells=cells[:n_cells], rec_off=rec_off,
-                            blk_off=blk_off, seg_off=seg_off, blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
-                            cell_src=None if cell_src is None else cell_src[:n_cells], first_tile=first_tile,
-                            n_tiles=n_tiles, seg_views=seg_views, record_cells=record_cells)
+                            n_blocks=n_blocks, n_rows=n_rows, cells=cells, row_off=row_off, blk_off=blk_off, rec_off=rec_off,
+                            blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
+                            cell_src=None if cell_src is None else cell_src[:n_rows * TILE], first_tile=first_tile,
+                            n_tiles=n_tiles, record_format=fmt, stats=stats)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -506,7 +535,7 @@ class FitState:
         st = FitState(params=p.to(device), moments=torch.zeros(18, dtype=torch.float32, device=device))
         if J0 is not None:
             st.J = J0.to(device=device, dtype=torch.float32).contiguous().clone()
-            st.J_moments = torch.zeros(tuple(st.J.shape[:2]) + (6,), dtype=torch.float32, device=device)
+            st.J_moments = torch.zeros(tuple(st.J.shape[:-1]) + (6,), dtype=torch.float32, device=device)
         return st
 
     @property
@@ -559,6 +588,17 @@ def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.0
                 'sucre_fit_sharded')
     state.step += num_iter
     return history
+
+
+def fit_status(store: ObservationStore) -> torch.Tensor:
+    """Device uint32 with the status bits the fit kernels left in the store's workspace since the last call (0 = fine;
+    bit 0: an in-kernel peer exchange timed out, i.e. a rank of a sharded fit went silent).  Enqueued on the current
+    stream; reading it on the host synchronises."""
+    dev = store.cells.device
+    out = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sucre_fit_status(_workspace(store).data_ptr(), out.data_ptr(), _stream(dev)), 'sucre_fit_status')
+    return out
 
 
 def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs_global: int | None = None,

@@ -112,15 +112,22 @@ class MatchesData:
         return self.store.n_obs
 
     def iter(self, batch_size: int = 1, device: str = 'cpu'):
-        """Reference-shaped view batches (loader.py:43-50) for inspection: yields (u, v, z, I) with u, v int64
-        target pixel coordinates, z (n,) the observation range (= cP.norm(dim=0), the only use the model makes of
-        cP when light_model is off, sucre.py:53) and I (3, n).  Not used by the CUDA fit."""
+        """Reference-shaped view batches (loader.py:43-50) for inspection: yields (u, v, cP, I) with u, v int64 target
+        pixel coordinates, I (3, n), and cP (3, n) the observation's camera-frame point when the store keeps it
+        (matches computed for the light model).  The default store keeps only the range z = cP.norm(dim=0) — the
+        only use the model makes of cP when light_model is off (sucre.py:53) — and then yields cP = (0, 0, z), whose
+        norm is z, so SUCRe.forward(u, v, cP) evaluates exactly as on the reference's output.  Not used by the CUDA fit."""
         per_view = list(self.store.to_reference_layout().values())
         for i in range(0, len(per_view), batch_size):
             chunk = per_view[i:i + batch_size]
+            if self.store.has_points:
+                cP = np.concatenate([c['cP'] for c in chunk], axis=1)
+            else:
+                z = np.concatenate([c['z'] for c in chunk])
+                cP = np.stack([np.zeros_like(z), np.zeros_like(z), z])
             yield (torch.from_numpy(np.concatenate([c['u1'] for c in chunk])).long().to(device),
                    torch.from_numpy(np.concatenate([c['v1'] for c in chunk])).long().to(device),
-                   torch.from_numpy(np.concatenate([c['z'] for c in chunk])).to(device),
+                   torch.from_numpy(cP).to(device),
                    torch.from_numpy(np.concatenate([c['I'] for c in chunk], axis=1)).to(device))
 
 
@@ -155,18 +162,18 @@ class MatchesFile:
 
     def check_integrity(self):
         """The invariants of loader.py:89-101 on the device-resident store: no NaN, colours >= 0, ranges >= 0 (they are
-        > 0 by construction: a match requires a positive source depth), consistent offsets.  Evaluated over all cells:
-        the header cells hold small non-negative byte counts, i.e. finite non-negative floats."""
+        > 0 by construction: a match requires a positive source depth), consistent offsets.  Evaluated over all record
+        slots at once: sentinels are all-zero, and the packed u8 colour word reads as a tiny non-negative float."""
         self._ensure_loaded()
         s = self.store
         if s.n_obs == 0:
             return
         cells = s.cells
         assert not bool(torch.isnan(cells).any()), f'In {self.path}, observations contain NaN(s).'
-        if s.record_cells == 1:  # light-model stores also carry camera-frame points, whose x / y are signed
+        if not s.has_points:  # light-model stores also carry camera-frame points, whose x / y are signed
             assert bool((cells >= 0).all()), f'In {self.path}, observations contain invalid value(s).'
         assert int(s.rec_off[-1]) == s.n_obs and int(s.blk_off[-1]) == s.n_blocks and \
-            int(s.seg_off[-1]) == s.n_segments, f'In {self.path}, corrupt offsets.'
+            int(s.row_off[-1]) == s.n_rows, f'In {self.path}, corrupt offsets.'
 
     def load_matches(self, pin_memory: bool = False, device=None) -> MatchesData:
         self._ensure_loaded(device)
@@ -187,10 +194,10 @@ class MatchesFile:
         np.savez(self.cache_path, width=s.width, height=s.height, names=np.array(self.names),
                  source_keys=np.array(s.source_keys), view_count=s.view_count, view_kept=s.view_kept,
                  n_obs=s.n_obs, cells=s.cells.cpu().numpy(), rec_off=s.rec_off.cpu().numpy(),
-                 blk_off=s.blk_off.cpu().numpy(), seg_off=s.seg_off.cpu().numpy(), blk_mask=s.blk_mask.cpu().numpy(),
+                 blk_off=s.blk_off.cpu().numpy(), row_off=s.row_off.cpu().numpy(), blk_mask=s.blk_mask.cpu().numpy(),
                  blk_view=s.blk_view.cpu().numpy(),
                  cell_src=np.zeros(0, np.int32) if s.cell_src is None else s.cell_src.cpu().numpy(),
-                 seg_views=s.seg_views, record_cells=s.record_cells)
+                 record_format=s.record_format)
         self.path.touch()  # the reference's file name marks "matches exist" (sucre.py:185)
 
     def unlink(self):
@@ -209,7 +216,7 @@ class MatchesFile:
         self.store = ObservationStore(
             width=int(z['width']), height=int(z['height']), source_keys=tuple(z['source_keys'].tolist()),
             view_count=z['view_count'], view_kept=z['view_kept'], n_obs=int(z['n_obs']),
-            n_blocks=int(z['blk_mask'].shape[0]), n_segments=int(z['seg_off'][-1]), cells=t(z['cells']),
-            rec_off=t(z['rec_off']), blk_off=t(z['blk_off']), seg_off=t(z['seg_off']), blk_mask=t(z['blk_mask']),
+            n_blocks=int(z['blk_mask'].shape[0]), n_rows=int(z['row_off'][-1]), cells=t(z['cells']),
+            rec_off=t(z['rec_off']), blk_off=t(z['blk_off']), row_off=t(z['row_off']), blk_mask=t(z['blk_mask']),
             blk_view=t(z['blk_view']), cell_src=t(z['cell_src']) if z['cell_src'].size else None,
-            seg_views=int(z['seg_views']), record_cells=int(z['record_cells']))
+            record_format=int(z['record_format']))

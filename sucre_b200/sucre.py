@@ -296,7 +296,7 @@ def adam(
 def _adam_light(sucre: SUCRe, matches_data: loader.MatchesData, lr: float, num_iter: int, save_dir, save_interval):
     """adam() with the light model: kernels for everything per-pixel, torch.optim.Adam on the 19 host scalars."""
     store = matches_data.store
-    if store.record_cells != 2:
+    if not store.has_points:
         raise engine._lib.SucreError('the light model needs matches computed with camera-frame points; rerun with '
                                      '--force-compute-matches')
     dev = sucre.device

@@ -80,6 +80,18 @@ class SyntheticScene:
         t_cw = -R_cw @ self.C[i]
         return _quat_from_rot(R_cw), t_cw
 
+    def reference_pose(self, i: int):
+        """K, R, t (cam->world) as the reference's COLMAPModel derives them (sfm.py:204-208, 219-222), from the
+        COLMAP cam_from_world quaternion + translation (quaternion -> matrix in float64 with Eigen's formula).
+        Returns (K (3,3), R (3,3), t (3,1), width, height), float32 torch tensors."""
+        from .sfm import quaternion_to_matrix
+        q, t_cw = self.cam_from_world(i)
+        R_cw = torch.tensor(quaternion_to_matrix(q), dtype=torch.float32)
+        t_cw = torch.tensor(t_cw, dtype=torch.float32).view(3, 1)
+        W, H, fx, fy, cx, cy = self.cams[self.view_cam[i]]
+        K = torch.tensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=torch.float32)
+        return K, R_cw.T, -R_cw.T @ t_cw, W, H
+
     # -- rendering ----------------------------------------------------------------------------------
     @torch.no_grad()
     def render(self, i: int, device: str | torch.device = 'cpu') -> tuple[torch.Tensor, torch.Tensor]:

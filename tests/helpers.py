@@ -35,15 +35,8 @@ def golden_device_scene(g, device='cuda'):
 
 
 def reference_pose(scene: SyntheticScene, i: int):
-    """K, R, t (cam->world) as the reference's COLMAPModel derives them (sfm.py:204-208, 219-222), from the
-    COLMAP cam_from_world quaternion + translation (quaternion -> matrix in float64 with Eigen's formula)."""
-    from sucre_b200.sfm import quaternion_to_matrix
-    q, t_cw = scene.cam_from_world(i)
-    R_cw = torch.tensor(quaternion_to_matrix(q), dtype=torch.float32)
-    t_cw = torch.tensor(t_cw, dtype=torch.float32).view(3, 1)
-    W, H, fx, fy, cx, cy = scene.cams[scene.view_cam[i]]
-    K = torch.tensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=torch.float32)
-    return K, R_cw.T, -R_cw.T @ t_cw, W, H
+    """K, R, t (cam->world), width, height as the reference's COLMAPModel derives them (SyntheticScene.reference_pose)."""
+    return scene.reference_pose(i)
 
 
 def build_device_scene(scene: SyntheticScene, views, device='cuda', render_device=None):

@@ -6,8 +6,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-SMALL = ['--views', '6', '--width', '96', '--height', '64', '--num-iter', '5', '--cpu-sample-views', '3',
-         '--cpu-sample-iters', '1', '--steps', '1', '--warmup', '0']
+SMALL = ['--views', '6', '--width', '96', '--height', '64', '--num-iter', '5', '--steps', '1', '--warmup', '0']
 
 
 def _run(env=None):
@@ -28,6 +27,11 @@ def test_reference_arm_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and 'torch_port' in d['cpu_baseline']['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'].startswith('synthetic 6-view 96x64')
+    assert set(d['config']) == {'workload', 'views', 'width', 'height', 'num_iter', 'mode', 'min_cover', 'seed'}   # same keys in both arms
+    m = d['measured']
+    assert len(m['iteration_s']) == 1 and 'ALL 6 views' in d['cpu_baseline']['sample']
+    s_image = m['gather_s'] + 5 * m['iteration_s'][0] + m['final_J_s']   # extrapolated in iterations only
+    assert abs(d['s_per_restored_image'] - s_image) < 1e-9 * s_image
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -25,12 +25,35 @@ def test_view_struct_layout_matches_header():
     assert _lib.VIEW_DTYPE.itemsize == 208
     assert [_lib.VIEW_DTYPE.fields[n][1] for n in ('K', 'Kinv', 'R', 't', 'Ri', 'ti', 'width', 'height', 'depth', 'rgb')] \
         == [0, 36, 72, 108, 120, 156, 168, 172, 176, 184]
-    assert _lib.VIEW_DTYPE.fields["rgb_format"][1] == 192
+    assert _lib.VIEW_DTYPE.fields["rgb_format"][1] == 192 and _lib.VIEW_DTYPE.fields["flags"][1] == 196
+
+
+def test_store_struct_and_record_formats_match_header():
+    header = (ROOT / 'include' / 'sucre_b200.h').read_text()
+    L = _lib.lib()
+    for name, fmt in (('Z_U8', _lib.REC_Z_U8), ('Z_F32', _lib.REC_Z_F32), ('P_U8', _lib.REC_P_U8), ('P_F32', _lib.REC_P_F32)):
+        assert f'#define SUCRE_REC_{name} {fmt}' in header
+        assert L.sucre_record_bytes(fmt) == _lib.RECORD_BYTES[fmt]
+    assert L.sucre_record_bytes(17) == 0
+    assert ctypes.sizeof(_lib.SucreStore) == 40 and 'sizeof == 40' in header
+    assert [getattr(_lib.SucreStore, f).offset for f in ('cells', 'row_off', 'n_tiles', 'record_format', 'pixels', 'n_rows')] \
+        == [0, 8, 16, 20, 24, 32]
+
+
+def test_pinhole_flags_come_from_the_values():
+    import numpy as np
+    K = np.array([[900., 0, 320], [0, 900, 240], [0, 0, 1]], dtype=np.float32)
+    Kinv = np.linalg.inv(K).astype(np.float32)
+    rec = _lib.view_record(K, Kinv, np.eye(3), np.zeros(3), np.eye(3), np.zeros(3), 640, 480)
+    assert rec['flags'] == (_lib.VIEW_K_SPARSE | _lib.VIEW_KINV_SPARSE)
+    K2 = K.copy()
+    K2[0, 1] = 1e-3   # a skew term: the general path must be used
+    assert _lib.view_record(K2, Kinv, np.eye(3), np.zeros(3), np.eye(3), np.zeros(3), 640, 480)['flags'] == _lib.VIEW_KINV_SPARSE
 
 
 def test_argument_errors_without_gpu():
     L = _lib.lib()
-    assert L.sucre_gather_plan(0, 1, 1, 0, 1, 0.0, 15, 0, 0, 0, 0, 0, 0) != 0
+    assert L.sucre_gather_plan(0, 1, 1, 0, 1, 0.0, 0, 0, 0, 0, 0, 0) != 0
     assert b'null' in L.sucre_last_error()
     assert L.sucre_adam_step(0, 0, 0, 1, 1, 0.05, 0, 0) != 0
 

@@ -64,7 +64,7 @@ class OracleBandOps:
             if keep:
                 depth, rgb = self._inputs(name)
                 self.obs.append(oracle.sample_pair(idx, depth, rgb, self.geoms[name]))
-        return sum(len(o['u1']) for o in self.obs), kept
+        return sum(len(o['u1']) for o in self.obs), kept, view_count.numpy()
 
     def init_state(self, params=None):
         self.p = np.full(9, 0.1, np.float32) if params is None else np.asarray(params, np.float32)

@@ -62,39 +62,56 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, closed_form, out_path, fused=False):
+def _blank_top(ds, world):
+    """Invalidate the target's first band (and a bit more): rank 0's band then holds no observation at all."""
+    ds.depth[4].view(torch.int16)[:240 // world + 2] = 0
+
+
+def _nccl_worker(rank, world, port, closed_form, out_path, fused=False, empty_band=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         scene = SyntheticScene(8, 320, 240, seed=11)
         ds, _ = helpers.build_device_scene(scene, range(8), device=f'cuda:{rank}')
+        if empty_band:
+            _blank_top(ds, world)
         ops = sdist.CudaBandOps(ds, 4, list(range(8)), use_closed_form=closed_form)
         peers = sdist.PeerExchange(ds.device) if fused else None
         res = sdist.restore_band_sharded(ops, num_iter=25, peers=peers)
-        if fused:  # a second target on the same exchange buffers: epochs keep advancing
+        assert res.n_local > 0 or (empty_band and rank == 0)
+        J = res.J.clone()   # the fused path returns a view of the symmetric buffer, overwritten by the next target
+        if fused:  # a second target on the same exchange buffers: epochs keep advancing; no exchange timed out
+            assert int(res.status.item()) == 0
             ops2 = sdist.CudaBandOps(ds, 3, list(range(8)), use_closed_form=closed_form)
-            res2 = sdist.restore_band_sharded(ops2, num_iter=5, peers=peers)
-            assert torch.isfinite(res2.params).all()
+            res2 = sdist.restore_band_sharded(ops2, num_iter=5, peers=peers, root_only=True)
+            assert torch.isfinite(res2.params).all() and int(res2.status.item()) == 0
+            full = torch.tensor([int(torch.isfinite(J).any())], device=ds.device)
+            dist.all_reduce(full)
+            assert int(full.item()) == world   # every rank holds the assembled J of the first target
         if rank == 0:
-            np.savez(out_path, J=res.J.cpu().numpy(), params=res.params.cpu().numpy(), history=res.history.cpu().numpy(),
+            np.savez(out_path, J=J.cpu().numpy(), params=res.params.cpu().numpy(), history=res.history.cpu().numpy(),
                      n_obs=res.n_obs)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-@pytest.mark.parametrize('closed_form,fused', [(True, False), (False, False), (True, True), (False, True)])
-def test_band_sharded_matches_single_gpu(closed_form, fused):
+@pytest.mark.parametrize('closed_form,fused,empty_band', [(True, False, False), (False, False, False), (True, True, False),
+                                                          (False, True, False), (True, True, True), (True, False, True)])
+def test_band_sharded_matches_single_gpu(closed_form, fused, empty_band):
     """fused=False: NCCL all-reduce between kernels; fused=True: all-reduce inside the fit kernel over NVLink peer
-    memory (sucre_fit_sharded)."""
+    memory (sucre_fit_sharded) and J assembled by direct peer writes.  empty_band: the first rank's band has no
+    observation at all — it must still take part in every exchange (a missing flag would hang its peers)."""
     world = min(4, torch.cuda.device_count())
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, 'res.npz')
-        mp.spawn(_nccl_worker, args=(world, _free_port(), closed_form, out, fused), nprocs=world, join=True)
+        mp.spawn(_nccl_worker, args=(world, _free_port(), closed_form, out, fused, empty_band), nprocs=world, join=True)
         z = np.load(out)
     scene = SyntheticScene(8, 320, 240, seed=11)
     ds, _ = helpers.build_device_scene(scene, range(8))
+    if empty_band:
+        _blank_top(ds, world)
     one = api.restore_resident(ds, 4, list(range(8)), use_closed_form=closed_form, num_iter=25)
     assert int(z['n_obs']) == one.n_obs
     p1 = one.params.cpu().numpy()

@@ -142,6 +142,54 @@ def test_recovers_ground_truth_parameters():
     assert np.nanmin(J) > -0.5 and np.nanmax(J) < 1.5
 
 
+@pytest.mark.parametrize('shape', [(40, 96, 64, 20), (6, 257, 131, 2), (12, 64, 48, 5), (3, 33, 7, 1)])
+def test_every_partition_shape_against_float64(shape):
+    """The fit splits rows evenly over 148 x 16 warps, cutting tiles between neighbouring warps.  Shapes that stress
+    it: tiles far longer than a warp's share (40 views on a small image), ragged last tiles, stores smaller than the
+    grid, and a band of empty tiles (target depth zeroed).  Checked: the kernel's sums against an independent float64
+    evaluation over the exported records, J against the float64 closed form, and a short J-parameter run against the
+    oracle."""
+    V, W, H, target = shape
+    scene = SyntheticScene(V, W, H, seed=13)
+    ds, host = helpers.build_device_scene(scene, range(V))
+    if H > 16:  # rows 4..11 of the target become invalid: empty tiles in the middle of the store
+        ds.depth[target].view(torch.int16)[4:12] = 0
+        host[target][0][4:12] = 0
+    keys = list(range(V))
+    store = engine.gather(ds, target, keys)
+    assert store.n_obs > 0 and store.n_rows * 32 >= store.n_obs
+    state = engine.FitState.initial(ds.device)
+    sums = torch.zeros(10, dtype=torch.float64, device=ds.device)
+    engine.fit_sums(store, state, sums)
+    engine.fit_sums(store, state, sums)    # second evaluation: reference point = J of the first
+    J = engine.closed_form_J(store, state.params).reshape(-1, 3)
+    _, pixel, _ = store.record_index()
+    rec = store.records().double()
+    z, I = rec[:, :1], rec[:, 1:]
+    B, beta, gamma = (state.params[i:i + 3].double() for i in (0, 3, 6))
+    a, e = torch.exp(-beta * z), torch.exp(-gamma * z)
+    num = torch.zeros((W * H, 3), dtype=torch.float64, device=ds.device).index_add_(0, pixel, (I - B * (1 - e)) * a)
+    den = torch.zeros((W * H, 3), dtype=torch.float64, device=ds.device).index_add_(0, pixel, a * a)
+    J64 = num / den                                                       # 0/0 = NaN where unobserved (sucre.py:77)
+    assert torch.equal(torch.isnan(J64), torch.isnan(J))
+    assert float((J.double() - J64).nan_to_num(0.0).abs().max()) < 1e-5
+    Jp = J64[pixel]
+    r = I - (Jp * a + B * (1 - e))
+    ref = torch.cat([(r * (1 - e)).sum(0), (r * Jp * z * a).sum(0), (r * B * z * e).sum(0), (r * r).sum().reshape(1)])
+    scale = torch.cat([(r * (1 - e)).abs().sum(0), (r * Jp * z * a).abs().sum(0), (r * B * z * e).abs().sum(0),
+                       (r * r).sum().reshape(1)])
+    assert float(((sums - ref).abs() / scale).max()) < 1e-5
+    # J-parameter mode on the same store: 5 iterations against the oracle
+    kept, _ = helpers.oracle_gather(host, target, keys)
+    J0 = oracle.initial_J(host[target][1], host[target][0])
+    oref = oracle.fit([o for _, o in kept], W, H, closed_form=False, num_iter=5, J0=J0)
+    sp = engine.FitState.initial(ds.device, J0=torch.from_numpy(J0))
+    hist = engine.fit(store, sp, 5).cpu().numpy()
+    assert _rel(sp.params.cpu().numpy(), oref['params']) < P_RTOL and _rel(hist[:, 9], oref['cost']) < 1e-5
+    Jg = sp.J.cpu().numpy()
+    assert np.array_equal(np.isnan(Jg), np.isnan(oref['J'])) and np.nanmax(np.abs(Jg - oref['J'])) < J_ATOL
+
+
 def test_empty_store_raises():
     scene = SyntheticScene(2, 64, 48, seed=1)
     ds, _ = helpers.build_device_scene(scene, range(2))

@@ -41,6 +41,10 @@ def test_every_pixel_view_matches_the_oracle(full):
         mine[pixel[sel]] = src[sel]
         assert np.array_equal(mine.cpu().numpy(), idx.reshape(-1)), f'view {s}'
     assert store.n_obs == int(store.view_count[store.view_kept].sum())
+    # the match kernel's own statistics (bench.py's roofline_gather): in-bounds forward projections counted on the
+    # device equal the oracle's, and the frustum pre-test skipped (tile, view) pairs without changing any mask
+    assert store.stats['n_inbounds'] == n_in_total, (store.stats, n_in_total)
+    assert 0 < store.stats['tile_views_culled'] < store.stats['tile_views']
     print(f'config 2: {store.n_obs} observations, {int(store.view_kept.sum())}/{V} views kept, '
           f'{n_in_total} in-bounds forward projections')
 
@@ -65,7 +69,8 @@ def test_store_structure_invariants(full):
     rec = store.records()
     assert not torch.isnan(rec).any() and (rec[:, 0] > 0).all() and (rec[:, 1:] >= 0).all() and (rec[:, 1:] <= 1).all()
     cell, pixel, view = store.record_index()
-    assert torch.unique(cell).numel() == store.n_obs                       # every record cell used exactly once
+    assert torch.unique(cell).numel() == store.n_obs                       # every record slot used exactly once
+    assert store.n_rows * 32 >= store.n_obs and 0.5 < store.fill <= 1.0
     key = view * (W * H) + pixel
     assert torch.unique(key).numel() == store.n_obs                        # a pixel is matched at most once per view
     srckey = view * (1 << 32) + store.cell_src[cell].to(torch.int64) % (1 << 32)
@@ -88,8 +93,8 @@ def test_fit_properties_at_full_size(full):
     engine.fit_sums(store, state, first)   # reference point J_ref = 0: the statistics still cancel (~1e-5)
     engine.fit_sums(store, state, sums)    # reference point = J of the previous evaluation: residual-scale products
     J = engine.closed_form_J(store, state.params).reshape(-1, 3)
-    cell, pixel, _ = store.record_index()
-    rec = store.cells[cell].double()
+    _, pixel, _ = store.record_index()
+    rec = store.records().double()
     z, I = rec[:, :1], rec[:, 1:]
     B, beta, gamma = (state.params[i:i + 3].double() for i in (0, 3, 6))
     a, e = torch.exp(-beta * z), torch.exp(-gamma * z)

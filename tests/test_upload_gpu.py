@@ -38,6 +38,29 @@ def test_footprint_upload_is_bit_identical_to_full_upload(closed):
         _same(full, api.restore_resident(resident, target, sources, **{k: v for k, v in kw.items() if k != 'device'}))
 
 
+def test_stream_pipeline_matches_single_calls_and_never_reads_outside_the_rectangles():
+    """api.restore_stream (double-buffered uploads on a copy stream, read-back overlapped) yields, target after target,
+    exactly what restore_from_host returns.  Its scene buffers are reused without being cleared, so whatever earlier
+    targets left outside the current target's rectangles must never be read: the results stay bit-identical."""
+    scene = SyntheticScene(20, 200, 136, seed=1)
+    views = list(range(20))
+    host, _ = _host_scene(scene, views)
+    host = host.pin()
+    kw = dict(min_cover=1e-6, use_closed_form=True, num_iter=8, lr=0.05)
+    targets = [11, 3, 18, 0, 11, 7]
+    singles = [api.restore_from_host(host, t, views, device='cuda:0', upload='full', **kw) for t in targets]
+    for mode in ('footprint', 'full'):
+        got = list(api.restore_stream(host, targets, views, device='cuda:0', upload=mode, **kw))
+        assert len(got) == len(targets)
+        for a, b, t in zip(singles, got, targets):
+            _same(a, b)
+            assert b.h2d_bytes == api.h2d_bytes(host, t, views, mode)
+    out = [torch.empty((136, 200, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for k, r in enumerate(api.restore_stream(host, targets[:3], views, device='cuda:0', out_J=out, **kw)):
+        assert r.J is out[k % 2]
+        _same(singles[k], r)
+
+
 def test_scene_upload_copies_exactly_the_rectangles():
     H, W, n = 37, 53, 5
     g = torch.Generator().manual_seed(0)

@@ -15,7 +15,7 @@ for spec in "$@"; do
     touch fit.cu
     make --no-print-directory EXTRA="$flags" >/dev/null
     cp ../libsucre_b200.so "$root/variants/$name.so"
-    printf '%-24s %s | %s\n' "$name" "$flags" "$(grep -A2 'fit_kernelILi0ELb0' build/fit.ptxas.log | tail -1 | sed 's/ptxas info    : //')"
+    printf '%-24s %s | %s\n' "$name" "$flags" "$(grep -A2 'fit_kernelILi0ELi0ELb0' build/fit.ptxas.log | tail -1 | sed 's/ptxas info    : //')"
 done
 touch fit.cu
 make --no-print-directory >/dev/null
