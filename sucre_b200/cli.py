@@ -2,10 +2,19 @@
 (reference: sucre/sucre.py:222-307): same option names, defaults, mutual exclusion and target / pairing selection.
 
     python -m sucre_b200.sucre --image-dir D --depth-dir D --model-dir D --output-dir D (--image-name N | --image-list F | --image-ids A B) [...]
+
+Multi-GPU (configs 3 and 5): launched under torchrun, one process per GPU,
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 -m sucre_b200.sucre ... --image-ids 1 1001
+
+every rank restores a contiguous share of the targets on its own GPU (cuda:LOCAL_RANK), decoding only the views its
+targets overlap.  Targets are independent (sucre.py:243-261 is a plain loop), so no process group is created and
+nothing is exchanged; the output files are named after the targets, so ranks never write the same file.
 """
 from __future__ import annotations
 
 import argparse
+import os
 from pathlib import Path
 
 # (flag, argparse keywords) in the reference's order; defaults are the reference's (sucre.py:265-305)
@@ -64,6 +73,15 @@ def parse_args(args: argparse.Namespace):
         targets = [colmap_model[name] for name in args.image_list.read_text().splitlines()]
     else:  # ids missing from the model are skipped
         targets = [colmap_model.images[i] for i in range(*args.image_ids) if i in colmap_model.images]
+
+    # under torchrun: this rank's share of the targets, on this rank's GPU
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', '1'), ('RANK', '0'), ('LOCAL_RANK', '0')))
+    if world > 1:
+        from .dist import shard_targets
+        targets = shard_targets(targets, rank, world, contiguous=True)
+        if args.device == 'cuda':
+            args.device = f'cuda:{local}'
+        print(f'Rank {rank}/{world}: {len(targets)} target(s) on {args.device}.')
 
     excluded = set(args.filter_images_path.read_text().splitlines()) if args.filter_images_path else set()
     pairing = [im for im in colmap_model.images.values() if im.name not in excluded]

@@ -108,14 +108,14 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 // latency is covered by the copies in flight instead of by occupancy, and the arithmetic reads one record per lane
 // and row from shared memory.  A slot is refilled as soon as the walk has left it.
 #ifndef SUCRE_FIT_CHUNK_BYTES
-#define SUCRE_FIT_CHUNK_BYTES 2560
+#define SUCRE_FIT_CHUNK_BYTES 3584
 #endif
 #ifndef SUCRE_FIT_STAGES
-#define SUCRE_FIT_STAGES 4
+#define SUCRE_FIT_STAGES 3
 #endif
-constexpr int kChunkBytes = SUCRE_FIT_CHUNK_BYTES;   // 10 rows of 8-byte records, 5 rows of 16-byte records
+constexpr int kChunkBytes = SUCRE_FIT_CHUNK_BYTES;   // 14 rows of 8-byte records, 7 rows of 16-byte records
 constexpr int kStages = SUCRE_FIT_STAGES;
-constexpr int kRingBytes = kChunkBytes * kStages;    // 10 KB per warp
+constexpr int kRingBytes = kChunkBytes * kStages;    // 10.5 KB per warp
 constexpr size_t kParkBytes = (size_t)kFitWarps * kStats * 32 * sizeof(float);   // 54 KB: parked statistics of split tiles
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingBytes + kParkBytes;
 static_assert(kChunkBytes % 512 == 0, "a chunk must hold whole rows of both record sizes");
@@ -178,7 +178,9 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
 }
 
 // one record as the arithmetic wants it: range z and the three colour values in the store's units
-// (SUCRE_REC_Z_U8: the bytes as exact floats 0..255; SUCRE_REC_Z_F32: I in [0,1])
+// (SUCRE_REC_Z_U8: the bytes as exact floats 0..255; SUCRE_REC_Z_F32: I in [0,1]).  For u8 colour, x holds the
+// "magic" floats 2^23 + byte (byte | 0x4B000000, one PRMT each, ALU pipe) and kBias = -2^23 is added — exactly —
+// where the value is first used, packed for red + green.
 struct Obs {
     float z, x[3];
 };
@@ -187,13 +189,13 @@ template <> struct RecTraits<SUCRE_REC_Z_U8> {
     typedef uint2 raw;
     static constexpr int kBytes = 8;
     static constexpr float kScale = 255.0f;
+    static constexpr float kBias = -8388608.0f;
     static __device__ __forceinline__ float range(const raw q) { return __uint_as_float(q.x); }
     static __device__ __forceinline__ Obs unpack(const raw q) {
         Obs o;
         o.z = __uint_as_float(q.x);
-        // byte c | 0x4B000000 is the float 2^23 + byte: one PRMT and one exact subtraction per channel
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o.x[c] = __uint_as_float(__byte_perm(q.y, 0x4B000000u, 0x7650u + c)) - 8388608.0f;
+        for (int c = 0; c < 3; ++c) o.x[c] = __uint_as_float(__byte_perm(q.y, 0x4B000000u, 0x7650u + c));
         return o;
     }
 };
@@ -201,6 +203,7 @@ template <> struct RecTraits<SUCRE_REC_Z_F32> {
     typedef float4 raw;
     static constexpr int kBytes = 16;
     static constexpr float kScale = 1.0f;
+    static constexpr float kBias = 0.0f;
     static __device__ __forceinline__ float range(const raw q) { return q.x; }
     static __device__ __forceinline__ Obs unpack(const raw q) {
         Obs o;
@@ -209,71 +212,112 @@ template <> struct RecTraits<SUCRE_REC_Z_F32> {
     }
 };
 
-// Per-pixel statistics of one channel, two per packed accumulator so that one FFMA2 updates both:
-//   S12 = (sum D'a, sum a^2)   S34 = (sum D'h, sum a h)   S56 = (sum D'za, sum a za)   S78 = (sum D'zg, sum a zg)
-//   S9  = sum D'^2             (a = e^{-beta z}, g = e^{-gamma z}, h = 1 - g, D' the shifted residual)
-template <int MODE, bool PRECISE>
+// Per-pixel statistics, nine per channel (k = 0..8: S1 .. S9 of the header comment), all driven by fma.rn.f32x2:
+//   red + green  CHANNEL-packed: every quantity of the pair of channels lives in one 64-bit register — exponents,
+//                a, g, h, D, D' and each of the nine sums — so one packed instruction serves both channels of a row;
+//   blue         ROW-packed: the two rows of a step share the registers instead (even rows in the low half, odd
+//                rows in the high half; the halves are added when the tile is finalised).
+// Per step of two rows: 54 packed arithmetic instructions + 12 MUFU.EX2 for 6 channel-records.
+template <int MODE, bool PRECISE, int REC>
 struct PixelStats {
-    u64 S12[3], S34[3], S56[3], S78[3];
-    float S9[3];
+    u64 P[9];   // (red, green) of S1 .. S9
+    u64 Q[9];   // blue: (even rows, odd rows) of S1 .. S9
 
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            S12[c] = S34[c] = S56[c] = S78[c] = 0ull;
-            S9[c] = 0.f;
+        for (int k = 0; k < 9; ++k) P[k] = Q[k] = 0ull;
+    }
+
+    // statistic k of channel c
+    __device__ __forceinline__ float get(int c, int k) const {
+        if (c == 0) return lo(P[k]);
+        if (c == 1) return hi(P[k]);
+        return lo(Q[k]) + hi(Q[k]);
+    }
+
+    // Constants of the sweep, in the store's units: exponent scales (kb, kg), -B, and -Jref per tile.
+    struct Consts {
+        u64 kb_rg, kg_rg, nB_rg;   // (kb_r, kb_g), (kg_r, kg_g), (-B_r, -B_g)
+        float kb_b, kg_b, nB_b;
+    };
+
+    // The nine updates of one packed pair (D', a, g, h given; zz = the ranges).
+    static __device__ __forceinline__ void accumulate(u64 (&S)[9], const u64 Dp, const u64 a, const u64 g, const u64 h, const u64 zz) {
+        S[0] = fma2(Dp, a, S[0]);
+        S[1] = fma2(a, a, S[1]);
+        if (MODE != kWriteJ) {
+            S[2] = fma2(Dp, h, S[2]);
+            S[3] = fma2(a, h, S[3]);
+#if !defined(SUCRE_EXPERIMENT_FEWSTATS)   // timing experiment only (wrong results): a third of the FMA work removed
+            const u64 Dz = mul2(Dp, zz), az = mul2(a, zz);
+            S[4] = fma2(Dz, a, S[4]);
+            S[5] = fma2(az, a, S[5]);
+            S[6] = fma2(Dz, g, S[6]);
+            S[7] = fma2(az, g, S[7]);
+#endif
+            S[8] = fma2(Dp, Dp, S[8]);
         }
     }
 
-    // kbg[c] = (kb, kg) exponent scales, Bc / nJ = B and -Jref of the channel (in the store's units).
-    // MASKED: the record may be a sentinel (z == 0, colour 0): its (D', a) pair is multiplied by w = 0, which zeroes
-    // every contribution (the z-weighted ones vanish through z == 0 already).
-    template <bool MASKED>
-    __device__ __forceinline__ void add(const Obs r, const u64 kbg[3], const float Bc[3], const float nJ[3]) {
-        const float z = r.z;
-        const u64 zz = pk(z, z);
-        const float w = z != 0.0f ? 1.0f : 0.0f;
-        const u64 ww = pk(w, w);
+    static __device__ __forceinline__ u64 exp2_pair(const u64 e) {
+#if defined(SUCRE_EXPERIMENT_NOEXP)      // timing experiment only (wrong results): no MUFU at all
+        return add2(e, pk(1.0f, 1.0f));
+#elif defined(SUCRE_EXPERIMENT_HALFEXP)  // timing experiment only: half of the MUFUs
+        return pk(fast_exp2(lo(e)), hi(e) + 1.0f);
+#else
+        return pk(PRECISE ? expf(lo(e)) : fast_exp2(lo(e)), PRECISE ? expf(hi(e)) : fast_exp2(hi(e)));
+#endif
+    }
+
+    // One step: rows r0 and r1 of this lane's column.  Either may be a sentinel (z == 0, colour 0): a is multiplied by
+    // w = (z != 0), and since z == 0 gives g = 1, h = 0, D = 0, the masked a makes D' = D - Jref a vanish too — every
+    // statistic carries a factor D' or a, so a sentinel adds exactly nothing, without a branch.  For a real record
+    // w = 1 and nothing changes.  (An odd last row is a step whose second row is an all-zero record.)
+    __device__ __forceinline__ void add(const Obs r0, const Obs r1, const Consts& k, const u64 nJ_rg, const float nJ_b) {
+        const u64 one = pk(1.0f, 1.0f), neg = pk(-1.0f, -1.0f);
+        const u64 bias = pk(RecTraits<REC>::kBias, RecTraits<REC>::kBias);
+        const float w0 = r0.z != 0.0f ? 1.0f : 0.0f, w1 = r1.z != 0.0f ? 1.0f : 0.0f;
+        // red + green, row by row
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const u64 e = mul2(kbg[c], zz);
-            const float a = PRECISE ? expf(lo(e)) : fast_exp2(lo(e));   // e^{-beta z}
-            const float g = PRECISE ? expf(hi(e)) : fast_exp2(hi(e));   // e^{-gamma z}
-            const float h = 1.0f - g;
-            const float D = fmaf(-Bc[c], h, r.x[c]);                    // I - B (1 - g)
-            const float Dp = fmaf(nJ[c], a, D);                         // shifted residual D - Jref a
-            u64 Da = pk(Dp, a);
-            if (MASKED) Da = mul2(Da, ww);
-            const float Dm = MASKED ? lo(Da) : Dp;
-            S12[c] = fma2(Da, pk(a, a), S12[c]);
-            if (MODE == kWriteJ) continue;
-            const u64 Dz = mul2(Da, zz);                                // (D' z, a z): every broadcast factor below is a scalar
-            S34[c] = fma2(Da, pk(h, h), S34[c]);
-            S56[c] = fma2(Dz, pk(a, a), S56[c]);
-            S78[c] = fma2(Dz, pk(g, g), S78[c]);
-            S9[c] = fmaf(Dm, Dm, S9[c]);
+        for (int i = 0; i < 2; ++i) {
+            const Obs& r = i == 0 ? r0 : r1;
+            const float w = i == 0 ? w0 : w1;
+            const u64 zz = pk(r.z, r.z);
+            const u64 a = mul2(exp2_pair(mul2(k.kb_rg, zz)), pk(w, w));
+            const u64 g = exp2_pair(mul2(k.kg_rg, zz));
+            const u64 h = fma2(g, neg, one);                               // 1 - g
+            u64 x = pk(r.x[0], r.x[1]);
+            if (RecTraits<REC>::kBias != 0.0f) x = add2(x, bias);
+            const u64 D = fma2(k.nB_rg, h, x);                             // I - B (1 - g)
+            const u64 Dp = fma2(nJ_rg, a, D);                              // shifted residual D - Jref a
+            accumulate(P, Dp, a, g, h, zz);
+        }
+        // blue, both rows at once
+        {
+            const u64 zz = pk(r0.z, r1.z);
+            const u64 a = mul2(exp2_pair(mul2(zz, pk(k.kb_b, k.kb_b))), pk(w0, w1));
+            const u64 g = exp2_pair(mul2(zz, pk(k.kg_b, k.kg_b)));
+            const u64 h = fma2(g, neg, one);
+            u64 x = pk(r0.x[2], r1.x[2]);
+            if (RecTraits<REC>::kBias != 0.0f) x = add2(x, bias);
+            const u64 D = fma2(pk(k.nB_b, k.nB_b), h, x);
+            const u64 Dp = fma2(pk(nJ_b, nJ_b), a, D);
+            accumulate(Q, Dp, a, g, h, zz);
         }
     }
 
-    // parked form: kStats floats per lane, [k][lane]
+    // parked form: kStats floats per lane, [9 * c + k][lane]
     __device__ __forceinline__ void park(float* slot, int lane) const {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            slot[(9 * c + 0) * 32 + lane] = lo(S12[c]), slot[(9 * c + 1) * 32 + lane] = hi(S12[c]);
-            slot[(9 * c + 2) * 32 + lane] = lo(S34[c]), slot[(9 * c + 3) * 32 + lane] = hi(S34[c]);
-            slot[(9 * c + 4) * 32 + lane] = lo(S56[c]), slot[(9 * c + 5) * 32 + lane] = hi(S56[c]);
-            slot[(9 * c + 6) * 32 + lane] = lo(S78[c]), slot[(9 * c + 7) * 32 + lane] = hi(S78[c]);
-            slot[(9 * c + 8) * 32 + lane] = S9[c];
-        }
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) slot[(9 * c + k) * 32 + lane] = get(c, k);
     }
     __device__ __forceinline__ void add_parked(const float* slot, int lane) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            S12[c] = add2(S12[c], pk(slot[(9 * c + 0) * 32 + lane], slot[(9 * c + 1) * 32 + lane]));
-            S34[c] = add2(S34[c], pk(slot[(9 * c + 2) * 32 + lane], slot[(9 * c + 3) * 32 + lane]));
-            S56[c] = add2(S56[c], pk(slot[(9 * c + 4) * 32 + lane], slot[(9 * c + 5) * 32 + lane]));
-            S78[c] = add2(S78[c], pk(slot[(9 * c + 6) * 32 + lane], slot[(9 * c + 7) * 32 + lane]));
-            S9[c] += slot[(9 * c + 8) * 32 + lane];
+        for (int k = 0; k < 9; ++k) {
+            P[k] = add2(P[k], pk(slot[k * 32 + lane], slot[(9 + k) * 32 + lane]));
+            Q[k] = add2(Q[k], pk(slot[(18 + k) * 32 + lane], 0.f));
         }
     }
 };
@@ -330,7 +374,6 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     typedef typename RT::raw Raw;
     constexpr int kRowBytes = 32 * RT::kBytes;
     constexpr int CR = kChunkBytes / kRowBytes;   // rows per chunk
-    constexpr int RR = CR * kStages;              // rows in the ring
     constexpr float kScale = RT::kScale;
     static_assert(CR >= 2, "a chunk must hold at least two rows");
 
@@ -357,9 +400,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     }
     __syncthreads();  // the park barrier of a warp is waited on by its neighbour
 
-    double acc[kSums];
+    // per-thread partial sums of the ten global sums: fp32 over this warp's tiles (a few dozen per-pixel values, each
+    // itself an fp32 sum), promoted to double for everything that follows (warp tree, CTA row, last CTA, peers)
+    float acc[kSums];
 #pragma unroll
-    for (int i = 0; i < kSums; ++i) acc[i] = 0.0;
+    for (int i = 0; i < kSums; ++i) acc[i] = 0.f;
 
     const long long B0 = A.part_row[gw], B1 = A.part_row[gw + 1];
     const int T0 = A.part_tile[gw], T1 = A.part_tile[gw + 1];
@@ -373,7 +418,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     uint32_t wait_parity = 0;
     int avail = 0;                       // rows that have landed
     int release_at = CR;                 // the oldest slot is recyclable once `pos` reaches this
-    int pos = 0, rpos = 0;               // rows consumed; same, modulo the ring size
+    int pos = 0, roff = 0;               // rows consumed; byte offset of row `pos` in the ring
     auto issue = [&]() {  // lane 0: arm the slot's barrier and start the copy of chunk `next_issue`
         const int first = next_issue * CR;
         const uint32_t bytes = (uint32_t)min(CR, n_rows_w - first) * (uint32_t)kRowBytes;
@@ -407,12 +452,18 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     // the previous iteration (parameters, J, ticket) must be complete and visible from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
     float Bs[3];   // B in the store's units
-    u64 kbg[3];    // per-channel exponent scales packed (beta, gamma): one FMUL2 forms both exponents of a record
+    typename PixelStats<MODE, PRECISE, REC>::Consts kc;
+    {
+        float kb[3], kg[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float B = A.params[c], beta = A.params[3 + c], gamma = A.params[6 + c];
-        Bs[c] = B * kScale;
-        kbg[c] = PRECISE ? pk(-beta, -gamma) : pk(-beta * kLog2e, -gamma * kLog2e);
+        for (int c = 0; c < 3; ++c) {
+            const float B = A.params[c], beta = A.params[3 + c], gamma = A.params[6 + c];
+            Bs[c] = B * kScale;
+            kb[c] = PRECISE ? -beta : -beta * kLog2e;     // e^{-beta z} = 2^{kb z}
+            kg[c] = PRECISE ? -gamma : -gamma * kLog2e;
+        }
+        kc.kb_rg = pk(kb[0], kb[1]), kc.kg_rg = pk(kg[0], kg[1]), kc.nB_rg = pk(-Bs[0], -Bs[1]);
+        kc.kb_b = kb[2], kc.kg_b = kg[2], kc.nB_b = -Bs[2];
     }
     constexpr float kInv = 1.0f / kScale;
 
@@ -446,43 +497,45 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         }
         const bool cut = rend > B1;                           // the tile's last rows are in the next warp's stream
         const int rb = (int)((cut ? B1 : rend) - B0);         // stream row where this item ends
-        PixelStats<MODE, PRECISE> st;
+        PixelStats<MODE, PRECISE, REC> st;
         st.clear();
-        bool seen = false;
+        unsigned seen_bits = 0;   // OR of the z bit patterns of the lane's records: non-zero iff it has an observation
         {
-            const float nJ[3] = {-Jref[0] * kScale, -Jref[1] * kScale, -Jref[2] * kScale};
+            const u64 nJ_rg = pk(-Jref[0] * kScale, -Jref[1] * kScale);
+            const float nJ_b = -Jref[2] * kScale;
             const unsigned char* lane_ring = ring + lane * RT::kBytes;
             int r = pos;
-            // two rows per step for instruction-level parallelism (their exp / residual chains are independent until the
-            // accumulators); a lane's observations fill its column from the top, so the second row of a step can only be a
-            // sentinel if... the first may be valid: it is masked arithmetically, the first by the branch
+            // Two rows per step for instruction-level parallelism (their exp / residual chains are independent until the
+            // accumulators); the body is branch-free (sentinels are masked arithmetically).  The ring is dealt with
+            // outside the inner loop: it runs up to what has landed, then the consumed slots are refilled and the next
+            // chunk is awaited.
+            while (true) {
+                const int lim = min(rb, avail);
 #pragma unroll 1
-            for (; r + 2 <= rb; r += 2) {
-                if (r + 2 > avail) acquire(r + 2);
-                const int r1 = rpos + 1 == RR ? 0 : rpos + 1;
-                const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + rpos * kRowBytes);
-                const Raw q1 = *reinterpret_cast<const Raw*>(lane_ring + r1 * kRowBytes);
-                rpos = r1 + 1 == RR ? 0 : r1 + 1;
-                if (RT::range(q0) != 0.0f) {
-                    seen = true;
-                    st.template add<false>(RT::unpack(q0), kbg, Bs, nJ);
-                    st.template add<true>(RT::unpack(q1), kbg, Bs, nJ);
+                for (; r + 2 <= lim; r += 2) {
+                    const int o1 = roff + kRowBytes == kRingBytes ? 0 : roff + kRowBytes;
+                    const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
+                    const Raw q1 = *reinterpret_cast<const Raw*>(lane_ring + o1);
+                    roff = o1 + kRowBytes == kRingBytes ? 0 : o1 + kRowBytes;
+                    seen_bits |= __float_as_uint(RT::range(q0));
+                    st.add(RT::unpack(q0), RT::unpack(q1), kc, nJ_rg, nJ_b);
                 }
-                pos = r + 2;
+                pos = r;
                 if (pos >= release_at) release();
+                if (r + 2 > rb) break;
+                acquire(r + 2);
             }
-            if (r < rb) {
+            if (r < rb) {  // odd row count: one last row
                 if (r + 1 > avail) acquire(r + 1);
-                const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + rpos * kRowBytes);
-                rpos = rpos + 1 == RR ? 0 : rpos + 1;
-                if (RT::range(q0) != 0.0f) {
-                    seen = true;
-                    st.template add<false>(RT::unpack(q0), kbg, Bs, nJ);
-                }
+                const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
+                roff = roff + kRowBytes == kRingBytes ? 0 : roff + kRowBytes;
+                seen_bits |= __float_as_uint(RT::range(q0));
+                st.add(RT::unpack(q0), RT::unpack(Raw{}), kc, nJ_rg, nJ_b);
                 pos = r + 1;
                 if (pos >= release_at) release();
             }
         }
+        const bool seen = seen_bits != 0;
         if (head) {  // hand the partial statistics of the previous warp's last tile over
             st.park(park_all + (size_t)warp * kStats * 32, lane);
             __syncwarp();
@@ -497,28 +550,28 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             if (p < A.pixels) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    A.J_out[3 * p + c] = seen ? Jref[c] + (lo(st.S12[c]) / hi(st.S12[c])) * kInv : __int_as_float(0x7fc00000);
+                    A.J_out[3 * p + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
             }
         } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
             float Jout[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 // all in the store's units: S1, S3, S5, S7 carry one factor kScale, S9 two
-                const float S1 = lo(st.S12[c]), S3 = lo(st.S34[c]), S5 = lo(st.S56[c]), S7 = lo(st.S78[c]), S9 = st.S9[c];
+                const float S1 = st.get(c, 0), S3 = st.get(c, 2), S5 = st.get(c, 4), S7 = st.get(c, 6), S9 = st.get(c, 8);
                 float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
                 if (MODE == kClosedForm) {
-                    delta = S1 / hi(st.S12[c]);
-                    rh = fmaf(-delta, hi(st.S34[c]), S3);
-                    rza = fmaf(-delta, hi(st.S56[c]), S5);
-                    rzg = fmaf(-delta, hi(st.S78[c]), S7);
+                    delta = S1 / st.get(c, 1);
+                    rh = fmaf(-delta, st.get(c, 3), S3);
+                    rza = fmaf(-delta, st.get(c, 5), S5);
+                    rzg = fmaf(-delta, st.get(c, 7), S7);
                     rr = fmaf(-delta, S1, S9);
                 }
                 const float Js = fmaf(Jref[c], kScale, delta);   // J in the store's units
                 Jout[c] = Js * kInv;
-                acc[c] += (double)rh;                  // sum r (1 - e^{-gamma z})    x kScale
-                acc[3 + c] += (double)(Js * rza);      // sum r J z e^{-beta z}       x kScale^2
-                acc[6 + c] += (double)(Bs[c] * rzg);   // sum r B z e^{-gamma z}      x kScale^2
-                acc[9] += (double)rr;                  // sum r^2                     x kScale^2
+                acc[c] += rh;                          // sum r (1 - e^{-gamma z})    x kScale
+                acc[3 + c] = fmaf(Js, rza, acc[3 + c]);      // sum r J z e^{-beta z}       x kScale^2
+                acc[6 + c] = fmaf(Bs[c], rzg, acc[6 + c]);   // sum r B z e^{-gamma z}      x kScale^2
+                acc[9] += rr;                          // sum r^2                     x kScale^2
                 if (MODE == kParamJ) {
                     // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step with the pre-step B, beta, gamma (sucre.py:144-148)
                     float* mv = A.J_moments + 6 * p;
@@ -543,7 +596,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     __shared__ unsigned s_ticket;
 #pragma unroll
     for (int i = 0; i < kSums; ++i) {
-        double v = acc[i];
+        double v = (double)acc[i];
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
         if (lane == 0) sm[warp][i] = v;
     }

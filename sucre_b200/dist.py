@@ -28,8 +28,13 @@ from . import _lib, engine
 from ._lib import TILE
 
 
-def shard_targets(targets: list, rank: int, world: int) -> list:
-    """Round-robin assignment of target images to ranks (every rank keeps the whole scene)."""
+def shard_targets(targets: list, rank: int, world: int, contiguous: bool = False) -> list:
+    """Assignment of target images to ranks: round-robin, or (contiguous) equal consecutive runs of the list — along a
+    survey track neighbouring targets overlap the same source views, so a rank then decodes and keeps resident only
+    its stretch of the survey."""
+    if contiguous:
+        n = len(targets)
+        return list(targets[n * rank // world:n * (rank + 1) // world])
     return list(targets[rank::world])
 
 

@@ -108,6 +108,20 @@ class DeviceScene:
         self._cull_tables.clear()
         self._ranges.pop(key, None)
 
+    def remove_views(self, keys):
+        """Forgets views (their device memory is released once no store / table refers to it)."""
+        for k in keys:
+            self.geom.pop(k, None)
+            self.depth.pop(k, None)
+            self.rgb.pop(k, None)
+            self._ranges.pop(k, None)
+        self._tables.clear()
+        self._cull_tables.clear()
+
+    def view_bytes(self, key) -> int:
+        d, c = self.depth[key], self.rgb.get(key)
+        return d.numel() * d.element_size() + (0 if c is None else c.numel() * c.element_size())
+
     def add_views(self, keys, geoms, depth_u16: torch.Tensor, rgb_u8: torch.Tensor):
         """Bulk form: stacked (V,H,W) / (V,H,W,3) tensors moved with one copy each."""
         d = depth_u16.to(self.device, non_blocking=True)

@@ -59,8 +59,12 @@ def load_depth_u16(depth_map_path: Path, width: int, height: int) -> Tensor:
     """(H,W) uint16 millimetres.  A size mismatch is resolved with nearest-neighbour like loader.py:168-169;
     nearest resampling commutes with the /1000 scaling, so the u16 grid is preserved."""
     depth = _imread(depth_map_path, cv2.IMREAD_UNCHANGED)
-    if depth.dtype != np.uint16 or depth.ndim != 2:
-        raise ValueError(f'{depth_map_path}: expected a single-channel 16-bit depth map, got {depth.dtype} {depth.shape}')
+    if depth.ndim != 2:
+        raise ValueError(f'{depth_map_path}: expected a single-channel depth map, got shape {depth.shape}')
+    if depth.dtype == np.uint8:      # the reference divides whatever integer the file holds by 1000 (loader.py:167)
+        depth = depth.astype(np.uint16)
+    elif depth.dtype != np.uint16:   # float / 32-bit maps have no exact 16-bit millimetre form
+        raise ValueError(f'{depth_map_path}: expected an 8- or 16-bit integer depth map in millimetres, got {depth.dtype}')
     if (depth.shape[0] != height) or (depth.shape[1] != width):
         depth = cv2.resize(depth, (width, height), interpolation=cv2.INTER_NEAREST)
     return torch.from_numpy(np.ascontiguousarray(depth))

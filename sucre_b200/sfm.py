@@ -230,6 +230,11 @@ class COLMAPModel:
 
         self.imagename2id = {image.name: image.id for image in self.images.values()}
         self._scenes: dict = {}
+        self._lru: dict = {}            # per device: view id -> tick of its last use
+        self._tick = 0
+        # device bytes the decoded views may occupy per GPU (None: 60 % of the device memory); beyond it the least
+        # recently used views that the current target does not need are dropped and decoded again when needed
+        self.scene_budget_bytes: int | None = None
 
     def __getitem__(self, image_name: str) -> Image:
         return self.images[self.imagename2id[image_name]]
@@ -244,12 +249,34 @@ class COLMAPModel:
         key = str(torch.device(device))
         if key not in self._scenes:
             self._scenes[key] = DeviceScene(device)
-        scene = self._scenes[key]
-        todo, seen = [], set()
+            self._lru[key] = {}
+        scene, lru = self._scenes[key], self._lru[key]
+        self._tick += 1
+        todo, seen, wanted = [], set(), []
         for im in (self.images.values() if images is None else images):
+            wanted.append(im.id)
             if im.id not in scene and im.id not in seen:
                 todo.append(im)
                 seen.add(im.id)
+        for i in wanted:
+            lru[i] = self._tick
+        if todo:  # stay within the residency budget: drop the least recently used views this call does not ask for
+            budget = self.scene_budget_bytes if self.scene_budget_bytes is not None else \
+                int(0.6 * torch.cuda.get_device_properties(torch.device(device)).total_memory)
+            per_view = {im.id: 5 * im.camera.width * im.camera.height for im in todo}
+            resident = sum(scene.view_bytes(i) for i in scene.geom)
+            excess = resident + sum(per_view.values()) - budget
+            if excess > 0:
+                keep = set(wanted)
+                victims = []
+                for i in sorted((i for i in scene.geom if i not in keep), key=lambda i: lru.get(i, 0)):
+                    if excess <= 0:
+                        break
+                    excess -= scene.view_bytes(i)
+                    victims.append(i)
+                scene.remove_views(victims)
+                for i in victims:
+                    lru.pop(i, None)
         if todo:
             def decode(im):
                 return im, im.get_depth_u16(), im.get_rgb_device_form()
@@ -266,5 +293,7 @@ class COLMAPModel:
     def drop_scene(self, device=None):
         if device is None:
             self._scenes.clear()
+            self._lru.clear()
         else:
             self._scenes.pop(str(torch.device(device)), None)
+            self._lru.pop(str(torch.device(device)), None)

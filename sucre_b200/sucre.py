@@ -98,6 +98,10 @@ class SUCRe:
             sd['J'] = self.J.detach().clone()
         return sd
 
+    def state_dict_cpu(self) -> dict:
+        """state_dict() with host tensors, leaving the model on its device (the plots are rendered there afterwards)."""
+        return {k: v.cpu() for k, v in self.state_dict().items()}
+
     def load_state_dict(self, state_dict: dict, strict: bool = True):
         known = {'B': 0, 'beta': 3, 'gamma': 6}
         for key, value in state_dict.items():
@@ -158,12 +162,12 @@ class SUCRe:
     @torch.no_grad()
     def plot_J(self) -> Image.Image:
         """Per-channel 1-99 percentile stretch of the valid pixels of J (sucre.py:84-94), evaluated on J's device
-        (torch.quantile's linear interpolation is numpy.percentile's default): only the uint8 image crosses to the host."""
+        (sort + numpy.percentile's default linear interpolation; torch.quantile refuses inputs above 2^24 elements, i.e.
+        targets beyond 16.7 Mpixel): only the uint8 image crosses to the host."""
         J = self.J
         valid = ~torch.isnan(J).any(dim=2)
         Jv = J[valid]                                                        # (n, 3)
-        lo = torch.stack([torch.quantile(Jv[:, c], 0.01) for c in range(3)])  # per channel: quantile() caps its input size
-        hi = torch.stack([torch.quantile(Jv[:, c], 0.99) for c in range(3)])
+        lo, hi = _percentiles(Jv, 0.01), _percentiles(Jv, 0.99)
         Jv = torch.clamp(Jv, lo, hi)
         Jv = Jv - Jv.min(dim=0).values
         Jv = Jv / Jv.max(dim=0).values
@@ -209,6 +213,15 @@ class SUCRe:
                 img.save(path)
             else:
                 writer.submit(img.save, path)
+
+
+def _percentiles(x: Tensor, q: float) -> Tensor:
+    """Per-column q-quantile of x (n, c) with numpy.percentile's default linear interpolation, any n."""
+    xs = torch.sort(x, dim=0).values
+    pos = q * (xs.shape[0] - 1)
+    i0 = int(np.floor(pos))
+    i1 = min(i0 + 1, xs.shape[0] - 1)
+    return xs[i0] + (xs[i1] - xs[i0]) * (pos - i0)
 
 
 def _jet(x: np.ndarray) -> np.ndarray:
@@ -387,13 +400,14 @@ def restore_image(
     adam(sucre=sucre, matches_data=matches_data, lr=lr, num_iter=num_iter, batch_size=batch_size,
          save_dir=output_dir, save_interval=save_interval, device=device)
 
-    sucre.save_plots(save_dir=output_dir, writer=writer)
+    # the parameters first: a failure while rendering the plots must not lose the result of the fit
     J = sucre.J.detach().cpu()
-    payload = {**sucre.cpu().state_dict(), 'J': J}
+    payload = {**sucre.state_dict_cpu(), 'J': J}
     if writer is None:
         torch.save(payload, (output_dir / image.name).with_suffix('.pt'))
     else:
         writer.submit(torch.save, payload, (output_dir / image.name).with_suffix('.pt'))
+    sucre.save_plots(save_dir=output_dir, writer=writer)
 
     if keep_matches:
         matches_file.save()

@@ -51,9 +51,12 @@ def test_bands_compose_to_the_whole_image():
         engine.fit_sums(b, sb, s)
         acc += s
         Js.append(engine.closed_form_J(b, sb.params))
-    assert torch.allclose(acc, sums, rtol=1e-12, atol=0)
+    # band sums add up to the whole-image sums (not bit for bit: the fit cuts tiles between warps at different places
+    # in a band and in the whole image, which reorders the fp32 additions inside a pixel's statistics)
+    assert torch.allclose(acc, sums, rtol=2e-4, atol=0)
     J = engine.closed_form_J(full, state.params).reshape(-1, 3)
-    assert torch.equal(torch.cat(Js).nan_to_num(-7.0), J.nan_to_num(-7.0))
+    assert torch.equal(torch.isnan(torch.cat(Js)), torch.isnan(J))
+    assert float((torch.cat(Js) - J).nan_to_num(0.0).abs().max()) < 1e-6
 
 
 def _free_port():

@@ -75,7 +75,7 @@ def test_gather_api_errors():
     with pytest.raises(engine._lib.SucreError):
         engine.DeviceScene('cpu')
     L = engine._lib.lib()
-    assert L.sucre_gather_match(0, 0, 1, 0, 1, 0, 0) != 0 and b'null' in L.sucre_last_error()
+    assert L.sucre_gather_match(0, 0, 1, 0, 1, 0, 0, 0) != 0 and b'null' in L.sucre_last_error()
 
 
 def test_view_culling_changes_nothing():

@@ -119,6 +119,28 @@ def test_target_and_pairing_selection(scene_dir, tmp_path, monkeypatch):
     assert calls[0]['use_closed_form'] and calls[0]['min_cover'] == 0.01 and calls[0]['num_iter'] == 7
 
 
+def test_cli_shards_targets_over_torchrun_ranks(scene_dir, tmp_path, monkeypatch):
+    """Under torchrun (WORLD_SIZE / RANK / LOCAL_RANK) every rank takes a contiguous share of the targets on its own
+    GPU; the shares cover the target list exactly once and the pairing list is untouched (sucre.py:243-261 is a loop
+    over independent targets)."""
+    scene, root, dirs = scene_dir
+    base = ['--image-dir', str(dirs['images']), '--depth-dir', str(dirs['depth']), '--model-dir', str(dirs['model']),
+            '--output-dir', str(tmp_path / 'out'), '--image-ids', '1', '6']
+    seen = []
+    for rank in range(3):
+        calls = []
+        monkeypatch.setattr(sucre, 'restore_image', lambda **kw: calls.append(kw))
+        for k, v in (('WORLD_SIZE', '3'), ('RANK', str(rank)), ('LOCAL_RANK', str(rank))):
+            monkeypatch.setenv(k, v)
+        sucre.main(base)
+        assert all(c['device'] == f'cuda:{rank}' for c in calls)
+        assert all([im.id for im in c['image_list']] == [1, 2, 3, 4, 5] for c in calls)
+        seen.append([c['image'].id for c in calls])
+    assert sum(seen, []) == [1, 2, 3, 4, 5] and max(map(len, seen)) - min(map(len, seen)) <= 1
+    from sucre_b200.dist import shard_targets
+    assert [shard_targets(list(range(10)), r, 4, contiguous=True) for r in range(4)] == [[0, 1], [2, 3, 4], [5, 6], [7, 8, 9]]
+
+
 def test_no_cpu_path():
     from sucre_b200 import engine
     with pytest.raises(engine._lib.SucreError):
