@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 7
+#define SUCRE_ABI_VERSION 8
 #define SUCRE_TILE_PIXELS 32
 #define SUCRE_REC_Z_U8 0
 #define SUCRE_REC_Z_F32 1
@@ -92,6 +92,15 @@ typedef struct sucre_store {
     int64_t n_rows;          /* host copy of row_off[n_tiles] */
 } sucre_store;
 
+/* The tiles of a target that one call (one rank) covers.  Local tile k is the target's tile
+ *   first_tile + (k / chunk_tiles) * stride_tiles + k % chunk_tiles,      k in [0, n_tiles).
+ * Whole image or contiguous band: chunk_tiles = n_tiles.  Cyclic sharding over N ranks in chunks of C tiles (every
+ * rank then sees every region of the image, so the observation counts balance): rank r has first_tile = r*C,
+ * chunk_tiles = C, stride_tiles = N*C.  masks / offsets / cells / J of a call are in LOCAL tile order. */
+typedef struct sucre_band {
+    int32_t first_tile, n_tiles, chunk_tiles, stride_tiles;
+} sucre_band;
+
 int sucre_abi_version(void);
 int sucre_record_bytes(int record_format); /* 8, 16, 16, 32; 0 for an unknown format */
 const char* sucre_last_error(void);
@@ -117,8 +126,8 @@ int sucre_scene_upload(void* dst, const void* src_host, int n, const int32_t* sr
  * (sfm.py:115-138, 154-159, 171-175), unproject_depth(_map) / project_to_view / Pose.transform
  * (sfm.py:49-55, 90-107) and load_depth_map's scaling (loader.py:166-170).
  *
- * A call may cover the whole target or a band of it: tiles [first_tile, first_tile + n_tiles) (multi-GPU pixel
- * sharding); masks / offsets / cells / J of such a call are local to the band.
+ * A call may cover the whole target or a band of it (struct sucre_band, multi-GPU pixel sharding); masks / offsets /
+ * cells / J of such a call are local to the band.
  *
  * sucre_gather_match: for every target pixel of the band and every listed view, the reference's two-way integer
  * round-trip test.  masks[k*n_views + s] receives the lane mask of local tile k against view s.
@@ -126,8 +135,8 @@ int sucre_scene_upload(void* dst, const void* src_host, int n, const int32_t* sr
  * none of the warp's 64 target pixels can land (their mask words are written as 0, which is what the full evaluation
  * gives).  stats (optional, may be NULL; int64[2], ACCUMULATED, zero it first): [0] += (tile, view) pairs skipped by
  * that test, [1] += forward projections that landed inside the source image (SURVEY.md §8d's n_inbounds). */
-int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
-                       int n_tiles, uint32_t* masks, int64_t* stats, void* stream);
+int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
+                       uint32_t* masks, int64_t* stats, void* stream);
 
 /* sucre_gather_count: view_count[n_views] (int64) = matches per view over the band (kept or not).
  * Multi-GPU callers all-reduce view_count before sucre_gather_plan: min_cover is a whole-image criterion. */
@@ -151,10 +160,16 @@ int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int
  * replaced by this device-resident store.  record_format: SUCRE_REC_*; the U8 formats require every kept view to be
  * SUCRE_RGB_U8.  cell_src (optional, may be NULL; one uint32 per record slot, index row*32 + lane) receives
  * u2 | v2 << 16, the integer source pixel (what the reference stores as int16 u2, v2), 0xffffffff at sentinels. */
-int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
-                        int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
+int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
+                        const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
                         const int64_t* blk_off, int record_format, void* cells, uint32_t* blk_mask, int32_t* blk_view,
                         uint32_t* cell_src, void* stream);
+
+/* sucre_band_scatter_J: copies a band's J (J_band[pixels_local*3], local tile order) to its place in n_dst whole-image
+ * J buffers (target_pixels*3 floats each; dst_ptrs_host[i] = device address — this GPU's or a peer's NVLink-mapped
+ * buffer).  The assembly step of a target sharded over several GPUs ("the final gather of J") as direct peer writes. */
+int sucre_band_scatter_J(const float* J_band, const sucre_band* band_host, int64_t target_pixels,
+                         const uint64_t* dst_ptrs_host, int n_dst, void* stream);
 
 /* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
  * Replaces SUCRe.compute_l_z / update_J / forward (sucre.py:52-82) and adam() (sucre.py:124-157) for

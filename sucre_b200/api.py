@@ -222,7 +222,7 @@ def restore_from_host_sharded(host: HostScene, target: int, sources=None, *, dev
     rank = tdist.get_rank() if tdist.is_initialized() else 0
     g = host.geoms[target]
     n_tiles = (g.width * g.height + engine.TILE - 1) // engine.TILE
-    lo, n = sdist.tile_band(n_tiles, rank, world)
+    lo, n = sdist.tile_band(n_tiles, rank, world)   # contiguous bands: a rank then needs a small part of every source view
     v0, v1 = lo * engine.TILE // g.width, min(g.height, ((lo + n) * engine.TILE - 1) // g.width + 1)
     needed = sorted(set(sources) | {target})
     scene = engine.DeviceScene(device)
@@ -238,7 +238,7 @@ def restore_from_host_sharded(host: HostScene, target: int, sources=None, *, dev
     h2d = scene.upload_rects((d, c), host.depth, host.rgb, needed, rects)
     ops = sdist.CudaBandOps(scene, target, sources, use_closed_form=use_closed_form)
     res = sdist.restore_band_sharded(ops, min_cover=min_cover, num_iter=num_iter, lr=lr, params=params, peers=peers,
-                                     root_only=peers is not None)
+                                     root_only=peers is not None, layout='contiguous')
     J = None
     if rank == 0:
         J = res.J.cpu() if out_J is None else out_J.copy_(res.J, non_blocking=True)

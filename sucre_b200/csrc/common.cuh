@@ -34,6 +34,11 @@ inline int check_launch(const char* what) {
         if (e_ != cudaSuccess) return ::sucre::set_error(#call ": %s", cudaGetErrorString(e_)); \
     } while (0)
 
+// global tile of local tile k of a band (include/sucre_b200.h)
+__host__ __device__ inline int band_tile(const sucre_band& b, int k) {
+    return b.first_tile + (k / b.chunk_tiles) * b.stride_tiles + k % b.chunk_tiles;
+}
+
 inline int num_sms() {
     static int n = 0;
     if (n == 0) {

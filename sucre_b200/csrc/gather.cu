@@ -136,7 +136,7 @@ __device__ __forceinline__ bool may_land(const sucre_view& S, const float (*wc)[
 template <int PIX>
 __global__ void __launch_bounds__(kWarps * 32)
 gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
-                    uint32_t* __restrict__ masks, int first_tile, int n_tiles, unsigned long long* __restrict__ stats, int cull) {
+                    uint32_t* __restrict__ masks, const sucre_band band, unsigned long long* __restrict__ stats, int cull) {
     __shared__ __align__(16) sucre_view sv[kChunk];  // 6.5 KB
     const int vbase = blockIdx.y * kChunk;
     const int nv = min(kChunk, n_views - vbase);
@@ -148,7 +148,8 @@ gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __re
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile0 = (blockIdx.x * kWarps + warp) * PIX;  // local tile index; global tile = first_tile + local
+    const int n_tiles = band.n_tiles;
+    const int tile0 = (blockIdx.x * kWarps + warp) * PIX;  // local tile index; global tile = band_tile(band, local)
     if (tile0 >= n_tiles) return;
     const int P = T.width * T.height;
     const bool t_sparse = (T.flags & SUCRE_VIEW_K_SPARSE) != 0;
@@ -161,8 +162,9 @@ gather_match_kernel(const __grid_constant__ sucre_view T, const sucre_view* __re
     unsigned dlo = 0x7f800000u, dhi = 0u;
 #pragma unroll
     for (int k = 0; k < PIX; ++k) {
-        const int p = (first_tile + tile0 + k) * kTile + lane;
-        const bool inside = p < P && tile0 + k < n_tiles;
+        const bool here = tile0 + k < n_tiles;
+        const int p = (here ? band_tile(band, tile0 + k) : 0) * kTile + lane;
+        const bool inside = here && p < P;
         const float d1 = __fdiv_rn((float)(inside ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
         valid[k] = d1 > 0.0f;  // sfm.py:96
         v1[k] = p / T.width;
@@ -437,15 +439,15 @@ __device__ __forceinline__ void write_sentinel(void* cells, long long at, int fo
 __global__ void __launch_bounds__(256)
 gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                      const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
-                     const long long* __restrict__ row_off, const long long* __restrict__ blk_off, int first_tile, int n_tiles,
+                     const long long* __restrict__ row_off, const long long* __restrict__ blk_off, const sucre_band band,
                      int format, void* __restrict__ cells, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
                      uint32_t* __restrict__ cell_src) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= n_tiles) return;
+    if (tile >= band.n_tiles) return;
     const uint32_t lt = (1u << lane) - 1u;
     const int P = T.width * T.height;
-    const int p = (first_tile + tile) * kTile + lane;
+    const int p = band_tile(band, tile) * kTile + lane;
     float w0, w1, w2;
     {
         const float d1 = __fdiv_rn((float)(p < P ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
@@ -520,11 +522,31 @@ static bool match_cull_enabled() {  // SUCRE_MATCH_CULL=0 switches the frustum p
 
 using namespace sucre;
 
-static int check_tile_range(const sucre_view* t, int first_tile, int n_tiles, const char* who) {
+static int check_band(const sucre_view* t, const sucre_band* b, const char* who) {
     const int total = (t->width * t->height + kTile - 1) / kTile;
-    SUCRE_REQUIRE(first_tile >= 0 && n_tiles > 0 && first_tile + n_tiles <= total,
-                  "%s: tiles [%d, %d) outside the target's %d tiles", who, first_tile, first_tile + n_tiles, total);
+    SUCRE_REQUIRE(b != nullptr, "%s: null band", who);
+    SUCRE_REQUIRE(b->first_tile >= 0 && b->n_tiles > 0 && b->chunk_tiles > 0 && b->stride_tiles >= 0,
+                  "%s: bad band {%d, %d, %d, %d}", who, b->first_tile, b->n_tiles, b->chunk_tiles, b->stride_tiles);
+    SUCRE_REQUIRE(b->n_tiles <= b->chunk_tiles || b->stride_tiles >= b->chunk_tiles, "%s: the chunks of a band must not overlap", who);
+    SUCRE_REQUIRE(band_tile(*b, b->n_tiles - 1) < total, "%s: band {%d, %d, %d, %d} reaches tile %d of the target's %d tiles", who,
+                  b->first_tile, b->n_tiles, b->chunk_tiles, b->stride_tiles, band_tile(*b, b->n_tiles - 1), total);
     return 0;
+}
+
+// one float of the band's J -> its place in every destination image
+struct ScatterPtrs {
+    unsigned long long p[SUCRE_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256)
+scatter_J_kernel(const float* __restrict__ J_band, const sucre_band band, long long floats_local, long long floats_total,
+                 const ScatterPtrs dst, int n_dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= floats_local) return;
+    const long long px = i / 3;
+    const long long g = ((long long)band_tile(band, (int)(px / kTile)) * kTile + px % kTile) * 3 + i % 3;
+    if (g >= floats_total) return;  // beyond the last pixel of the image (its last tile is partial)
+    const float v = J_band[i];
+    for (int d = 0; d < n_dst; ++d) reinterpret_cast<float*>(dst.p[d])[g] = v;
 }
 
 extern "C" int sucre_record_bytes(int record_format) {
@@ -537,16 +559,17 @@ extern "C" int sucre_record_bytes(int record_format) {
     }
 }
 
-extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
-                                  int n_tiles, uint32_t* masks, int64_t* stats, void* stream) {
+extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
+                                  uint32_t* masks, int64_t* stats, void* stream) {
     clear_error();
     if (check_view_host(target_host, "sucre_gather_match(target)")) return 1;
     SUCRE_REQUIRE(views && masks, "sucre_gather_match: null pointer");
     SUCRE_REQUIRE(n_views > 0, "sucre_gather_match: n_views = %d", n_views);
-    if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_match")) return 1;
+    if (check_band(target_host, band_host, "sucre_gather_match")) return 1;
     constexpr int PIX = SUCRE_MATCH_PIX;
+    const int n_tiles = band_host->n_tiles;
     dim3 grid((n_tiles + kWarps * PIX - 1) / (kWarps * PIX), (n_views + kChunk - 1) / kChunk);
-    gather_match_kernel<PIX><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*target_host, views, n_views, masks, first_tile, n_tiles,
+    gather_match_kernel<PIX><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*target_host, views, n_views, masks, *band_host,
                                                                              (unsigned long long*)stats, match_cull_enabled() ? 1 : 0);
     return check_launch("gather_match_kernel");
 }
@@ -575,19 +598,38 @@ extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views
     return check_launch("sucre_gather_plan kernels");
 }
 
-extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, int first_tile,
-                                   int n_tiles, const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
+extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
+                                   const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
                                    const int64_t* blk_off, int record_format, void* cells, uint32_t* blk_mask, int32_t* blk_view,
                                    uint32_t* cell_src, void* stream) {
     clear_error();
     if (check_view_host(target_host, "sucre_gather_sample(target)")) return 1;
     SUCRE_REQUIRE(views && masks && view_kept && row_off && blk_off && cells && blk_mask && blk_view,
                   "sucre_gather_sample: null pointer");
-    if (check_tile_range(target_host, first_tile, n_tiles, "sucre_gather_sample")) return 1;
+    if (check_band(target_host, band_host, "sucre_gather_sample")) return 1;
+    const int n_tiles = band_host->n_tiles;
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(cells) & 15) == 0, "sucre_gather_sample: cells must be 16-byte aligned");
     SUCRE_REQUIRE(sucre_record_bytes(record_format) != 0, "sucre_gather_sample: unknown record format %d", record_format);
     gather_sample_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        *target_host, views, n_views, masks, view_kept, (const long long*)row_off, (const long long*)blk_off, first_tile, n_tiles,
+        *target_host, views, n_views, masks, view_kept, (const long long*)row_off, (const long long*)blk_off, *band_host,
         record_format, cells, blk_mask, blk_view, cell_src);
     return check_launch("gather_sample_kernel");
+}
+
+extern "C" int sucre_band_scatter_J(const float* J_band, const sucre_band* band_host, int64_t target_pixels,
+                                    const uint64_t* dst_ptrs_host, int n_dst, void* stream) {
+    clear_error();
+    SUCRE_REQUIRE(J_band && band_host && dst_ptrs_host, "sucre_band_scatter_J: null pointer");
+    SUCRE_REQUIRE(n_dst >= 1 && n_dst <= SUCRE_MAX_PEERS && target_pixels > 0 && band_host->n_tiles > 0 && band_host->chunk_tiles > 0,
+                  "sucre_band_scatter_J: bad arguments");
+    SUCRE_REQUIRE((long long)band_tile(*band_host, band_host->n_tiles - 1) * kTile < target_pixels, "sucre_band_scatter_J: band outside the image");
+    ScatterPtrs ptrs{};   // passed by value: no device-side table to manage
+    for (int i = 0; i < n_dst; ++i) {
+        SUCRE_REQUIRE(dst_ptrs_host[i] != 0, "sucre_band_scatter_J: null destination %d", i);
+        ptrs.p[i] = dst_ptrs_host[i];
+    }
+    const long long floats_local = (long long)band_host->n_tiles * kTile * 3;
+    scatter_J_kernel<<<(unsigned)((floats_local + 255) / 256), 256, 0, (cudaStream_t)stream>>>(J_band, *band_host, floats_local,
+                                                                                             target_pixels * 3, ptrs, n_dst);
+    return check_launch("scatter_J_kernel");
 }

@@ -45,6 +45,21 @@ def tile_band(n_tiles_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, hi - lo
 
 
+def make_band(n_tiles_total: int, rank: int, world: int, layout: str = 'cyclic') -> _lib.Band:
+    """The tiles of a target that `rank` of `world` restores.  'cyclic' (default): chunks of up to 64 tiles dealt
+    round-robin, so that every rank sees every region of the image and the observation counts balance (contiguous
+    bands differ by ~10 % on 8 ranks, tools/band_balance.py); 'contiguous': equal consecutive runs of tiles (what a rank
+    that uploads from the host wants: its band then sees a small part of every source view)."""
+    if world == 1:
+        return _lib.Band.whole(n_tiles_total)
+    if layout == 'contiguous':
+        return _lib.Band.contiguous(n_tiles_total, rank, world)
+    if layout != 'cyclic':
+        raise ValueError(f'layout must be cyclic or contiguous, got {layout!r}')
+    chunk = min(64, max(1, n_tiles_total // (world * 4)))
+    return _lib.Band.cyclic(n_tiles_total, rank, world, chunk)
+
+
 class PeerExchange:
     """Symmetric-memory buffers of a group of ranks (torch symmetric memory => every rank holds a device pointer to
     every peer's buffer, NVLink / NVSwitch peer access):
@@ -82,19 +97,17 @@ class PeerExchange:
             self._J = self._symm.empty((pixels, 3), dtype=torch.float32, device=self.device)
             self._J_handle = self._symm.rendezvous(self._J, self.group)
 
-    def assemble_J(self, local: torch.Tensor, first_pixel: int, pixels: int, root_only: bool = False) -> torch.Tensor:
-        """Every rank stores its band `local` (n, 3) at rows [first_pixel, first_pixel + n) of the symmetric J buffer of
-        every rank (or of rank 0 only), then all ranks meet at a device-side barrier.  Returns this rank's (pixels, 3)
-        buffer view: complete on every rank (on rank 0 only with root_only).  The buffer is overwritten by the next
-        call: consume (or copy) the result on the same stream before restoring the next target."""
+    def assemble_J(self, store: engine.ObservationStore, local: torch.Tensor, root_only: bool = False) -> torch.Tensor:
+        """Every rank writes its band `local` (local_pixels, 3) to its place in the symmetric whole-image J buffer of
+        every rank (or of rank 0 only) — one kernel storing through NVLink-mapped pointers (sucre_band_scatter_J) —
+        then all ranks meet at a device-side barrier.  Returns this rank's (pixels, 3) buffer view: complete on every
+        rank (on rank 0 only with root_only).  The buffer is overwritten by the next call: consume (or copy) the
+        result on the same stream before restoring the next target."""
+        pixels = store.width * store.height
         self._ensure_J(pixels)
-        n = local.shape[0]
-        for peer in ([0] if root_only else range(self.world)):
-            if peer == self.rank:
-                self._J[first_pixel:first_pixel + n].copy_(local)
-            else:  # a tensor aliasing rows [first_pixel, first_pixel + n) of the peer's buffer: the copy crosses NVLink
-                self._J_handle.get_buffer(peer, (n, 3), torch.float32, first_pixel * 3).copy_(local)
-        self._J_handle.barrier()   # stream-ordered after the copies: every band has landed everywhere
+        ptrs = [int(p) for p in self._J_handle.buffer_ptrs]
+        engine.scatter_J(store, local.contiguous(), ptrs[:1] if root_only else ptrs)
+        self._J_handle.barrier()   # stream-ordered after the stores: every band has landed everywhere
         return self._J[:pixels]
 
 
@@ -121,18 +134,17 @@ class CudaBandOps:
         self.store: engine.ObservationStore | None = None
         self.state: engine.FitState | None = None
 
-    def gather(self, tile_range, min_cover, reduce_counts):
+    def gather(self, band: _lib.Band, min_cover, reduce_counts):
         self.store = engine.gather(self.scene, self.target_key, self.source_keys, min_cover=min_cover,
-                                   tile_range=tile_range, reduce_counts=reduce_counts)
+                                   band=band, reduce_counts=reduce_counts)
         return self.store.n_obs, self.store.view_kept, self.store.view_count
 
     def init_state(self, params=None):
         J0 = None
         if not self.use_closed_form:  # J parameter: this band of the target image, NaN where depth <= 0 (sucre.py:47-49)
-            lo = self.store.first_tile * TILE
-            hi = lo + self.store.local_pixels
-            J0 = self.scene.rgb_float(self.target_key).reshape(-1, 3)[lo:hi].clone()
-            J0[self.scene.depth[self.target_key].view(torch.int16).reshape(-1)[lo:hi] == 0] = float('nan')
+            px = self.store.global_pixels()
+            J0 = self.scene.rgb_float(self.target_key).reshape(-1, 3)[px]
+            J0[self.scene.depth[self.target_key].view(torch.int16).reshape(-1)[px] == 0] = float('nan')
         self.state = engine.FitState.initial(self.device, params=params, J0=J0)
         self.state.ensure_J(self.store)
 
@@ -167,9 +179,10 @@ class CudaBandOps:
 
 
 def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, lr: float = 0.05, params=None,
-                         group=None, peers: PeerExchange | None = None, root_only: bool = False) -> BandResult:
-    """One target restored by all ranks of `group`, each owning a band of its pixels.  Every rank returns the same
-    parameters and the full J (with root_only and `peers`: J is complete on rank 0 only).  `ops` is a CudaBandOps
+                         group=None, peers: PeerExchange | None = None, root_only: bool = False,
+                         layout: str = 'cyclic') -> BandResult:
+    """One target restored by all ranks of `group`, each owning a band of its tiles (make_band).  Every rank returns the
+    same parameters and the full J (with root_only and `peers`: J is complete on rank 0 only).  `ops` is a CudaBandOps
     (or a stand-in with the same methods).
     With `peers` (and a CudaBandOps) the per-iteration all-reduce runs inside the fit kernel over NVLink peer memory
     and the J bands are written straight into every rank's symmetric J buffer; without, both are NCCL / gloo
@@ -178,7 +191,9 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     P = ops.width * ops.height
     n_tiles_total = (P + TILE - 1) // TILE
-    band = tile_band(n_tiles_total, rank, world)
+    band = make_band(n_tiles_total, rank, world, layout)
+    if band.n_tiles == 0:
+        raise _lib.SucreError(f'restore: {world} ranks are too many for a target of {n_tiles_total} tiles')
 
     def all_reduce(t):
         if world > 1:
@@ -207,11 +222,11 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
 
     # 3. assemble J
     local = ops.band_J()
-    lo_px = band[0] * TILE
     if fused:
-        J = peers.assemble_J(local, lo_px, P, root_only=root_only)
-    else:  # bands differ by at most one tile: pad to the longest
-        longest = (n_tiles_total + world - 1) // world * TILE
+        J = peers.assemble_J(ops.store, local, root_only=root_only)
+    else:  # local sizes differ by at most one chunk: pad to the longest, gather, scatter by every rank's pixel list
+        sizes = [make_band(n_tiles_total, r, world, layout) for r in range(world)]
+        longest = max(b.n_tiles for b in sizes) * TILE
         padded = torch.full((longest, 3), float('nan'), dtype=local.dtype, device=local.device)
         padded[:local.shape[0]] = local
         if world > 1:
@@ -220,9 +235,8 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
         else:
             parts = [padded]
         J = torch.empty((P, 3), dtype=local.dtype, device=local.device)
-        for r, part in enumerate(parts):
-            lo, n = tile_band(n_tiles_total, r, world)
-            lo_r, hi_r = lo * TILE, min(P, (lo + n) * TILE)
-            J[lo_r:hi_r] = part[:hi_r - lo_r]
+        for b, part in zip(sizes, parts):
+            px = torch.from_numpy(b.pixels(P)).to(local.device)
+            J[px] = part[:px.shape[0]]
     return BandResult(J=J.reshape(ops.height, ops.width, 3), params=ops.params(), history=history, n_obs=n_obs,
                       view_kept=view_kept, status=status, n_local=n_local)

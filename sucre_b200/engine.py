@@ -300,23 +300,33 @@ class ObservationStore:
     blk_view: torch.Tensor        # (n_blocks,) int32 index into source_keys
     cell_src: torch.Tensor | None  # (n_rows*32,) int32 u2 | v2 << 16 per record slot, -1 at sentinels
     workspace: torch.Tensor | None = None  # fit scratch, prepared on first use
-    first_tile: int = 0           # band of the target this store covers (multi-GPU pixel sharding): tiles
-    n_tiles: int = 0              # [first_tile, first_tile + n_tiles); 0 = the whole target (set in __post_init__)
+    band: _lib.Band | None = None  # the tiles of the target this store covers (multi-GPU pixel sharding); None = all
     record_format: int = _lib.REC_Z_U8
     stats: dict = field(default_factory=dict)
 
     def __post_init__(self):
-        if self.n_tiles == 0:
-            self.n_tiles = (self.width * self.height + TILE - 1) // TILE
+        if self.band is None:
+            self.band = _lib.Band.whole((self.width * self.height + TILE - 1) // TILE)
+
+    @property
+    def n_tiles(self) -> int:
+        return self.band.n_tiles
 
     @property
     def is_band(self) -> bool:
-        return self.first_tile != 0 or self.n_tiles != (self.width * self.height + TILE - 1) // TILE
+        return self.band.as_tuple() != _lib.Band.whole((self.width * self.height + TILE - 1) // TILE).as_tuple()
 
     @property
     def local_pixels(self) -> int:
-        """Target pixels covered by this store (flat range starting at first_tile * 32)."""
-        return min(self.width * self.height - self.first_tile * TILE, self.n_tiles * TILE)
+        """Target pixels covered by this store, in local order; only the image's last tile can be partial, and it is
+        the band's last local tile if the band owns it."""
+        P = self.width * self.height
+        last_global = int(self.band.tiles()[-1]) if self.band.n_tiles else 0
+        return self.band.n_tiles * TILE - max(0, (last_global + 1) * TILE - P)
+
+    def global_pixels(self) -> torch.Tensor:
+        """Flat index in the image of every local pixel (device int64)."""
+        return torch.from_numpy(self.band.pixels(self.width * self.height)).to(self.cells.device)
 
     @property
     def J_shape(self) -> tuple:
@@ -365,7 +375,8 @@ class ObservationStore:
         j = cs - bits - cs_pad[self.blk_off[blk_tile]]                            # rank within the lane's column
         slot = (self.row_off[blk_tile][:, None] + j) * TILE + lanes[None, :]
         b, lane = torch.nonzero(bits, as_tuple=True)
-        return slot[b, lane], (blk_tile[b] + self.first_tile) * TILE + lane, self.blk_view.to(torch.int64)[b]
+        gtile = torch.from_numpy(self.band.tiles()).to(dev)
+        return slot[b, lane], gtile[blk_tile[b]] * TILE + lane, self.blk_view.to(torch.int64)[b]
 
     def _flat(self) -> torch.Tensor:
         return self.cells.reshape(-1, self.cells.shape[-1])
@@ -427,7 +438,7 @@ def _stream(device) -> int:
 
 
 def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
-           target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
+           target_record: np.ndarray | None = None, band: _lib.Band | None = None,
            reduce_counts=None, with_points: bool = False, cull_views: bool | None = None,
            keep_mask: np.ndarray | None = None) -> ObservationStore:
     """Stage 1 (see _gather_listed) behind a conservative view-level frustum pre-test: source views in which no target
@@ -439,7 +450,7 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
     source_keys = tuple(source_keys)
     if cull_views is None:
         cull_views = len(source_keys) >= 128
-    kw = dict(min_cover=min_cover, keep_src=keep_src, target_record=target_record, tile_range=tile_range,
+    kw = dict(min_cover=min_cover, keep_src=keep_src, target_record=target_record, band=band,
               reduce_counts=reduce_counts, with_points=with_points)
     if keep_mask is None and (not cull_views or len(source_keys) < 2 or target_record is not None
                               or target_key not in scene.geom):
@@ -461,13 +472,13 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
 
 
 def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
-                   target_record: np.ndarray | None = None, tile_range: tuple[int, int] | None = None,
+                   target_record: np.ndarray | None = None, band: _lib.Band | None = None,
                    reduce_counts=None, with_points: bool = False) -> ObservationStore:
     """Stage 1 on the device: match -> count -> plan -> (one 40-byte D2H to size the store) -> sample.
     Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
     (sfm.py:127-138, loader.py:78-87, 103-118).
 
-    tile_range = (first_tile, n_tiles) restricts the call to a band of the target (multi-GPU pixel sharding);
+    band (a _lib.Band) restricts the call to a band of the target's tiles (multi-GPU pixel sharding);
     reduce_counts(view_count) then sums the per-view match counts over all bands in place (an all-reduce), because
     min_cover is a whole-image criterion (sfm.py:136).
     with_points: keep the camera-frame point cP of every observation, which the light model needs (sucre.py:57); the
@@ -482,7 +493,8 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
     trec = scene.record(target_key) if target_record is None else target_record
     W, H = int(trec['width']), int(trec['height'])
     P = W * H
-    first_tile, n_tiles = (0, (P + TILE - 1) // TILE) if tile_range is None else (int(tile_range[0]), int(tile_range[1]))
+    band = _lib.Band.whole((P + TILE - 1) // TILE) if band is None else band
+    n_tiles = band.n_tiles
     table = scene.table(source_keys)
     f32_colour = any(scene.rgb.get(k) is not None and scene.rgb[k].dtype == torch.float32 for k in source_keys)
     fmt = (_lib.REC_P_F32 if f32_colour else _lib.REC_P_U8) if with_points else (_lib.REC_Z_F32 if f32_colour else _lib.REC_Z_U8)
@@ -497,7 +509,7 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
         row_off = torch.empty(n_tiles + 1, dtype=torch.int64, device=dev)
         totals = torch.zeros(5, dtype=torch.int64, device=dev)   # plan: {N, blocks, rows}; match statistics: {culled, in bounds}
         tptr = trec.ctypes.data
-        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
+        _lib.check(L.sucre_gather_match(tptr, table.data_ptr(), V, C.byref(band), masks.data_ptr(),
                                         totals.data_ptr() + 24, st), 'sucre_gather_match')
         _lib.check(L.sucre_gather_count(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), st), 'sucre_gather_count')
         if reduce_counts is not None:
@@ -514,7 +526,7 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
             missing = [k for k in source_keys if k not in scene.rgb]
             if missing:
                 raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
-            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, first_tile, n_tiles, masks.data_ptr(),
+            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, C.byref(band), masks.data_ptr(),
                                              view_kept.data_ptr(), row_off.data_ptr(), blk_off.data_ptr(), fmt,
                                              cells.data_ptr(), blk_mask.data_ptr(), blk_view.data_ptr(),
                                              0 if cell_src is None else cell_src.data_ptr(), st), 'sucre_gather_sample')
@@ -524,8 +536,8 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
     return ObservationStore(width=W, height=H, source_keys=source_keys, view_count=vc, view_kept=vk, n_obs=n_obs,
                             n_blocks=n_blocks, n_rows=n_rows, cells=cells, row_off=row_off, blk_off=blk_off, rec_off=rec_off,
                             blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
-                            cell_src=None if cell_src is None else cell_src[:n_rows * TILE], first_tile=first_tile,
-                            n_tiles=n_tiles, record_format=fmt, stats=stats)
+                            cell_src=None if cell_src is None else cell_src[:n_rows * TILE], band=band,
+                            record_format=fmt, stats=stats)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -613,6 +625,16 @@ def fit_status(store: ObservationStore) -> torch.Tensor:
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().sucre_fit_status(_workspace(store).data_ptr(), out.data_ptr(), _stream(dev)), 'sucre_fit_status')
     return out
+
+
+def scatter_J(store: ObservationStore, J_band: torch.Tensor, dst_ptrs: list[int]):
+    """Writes a band's J (local order) to its place in whole-image J buffers given by device address — this GPU's or
+    peers' NVLink-mapped ones (sucre_band_scatter_J)."""
+    dev = store.cells.device
+    ptrs = (C.c_uint64 * len(dst_ptrs))(*dst_ptrs)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sucre_band_scatter_J(J_band.data_ptr(), C.byref(store.band), store.width * store.height, ptrs,
+                                                   len(dst_ptrs), _stream(dev)), 'sucre_band_scatter_J')
 
 
 def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs_global: int | None = None,

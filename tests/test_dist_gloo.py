@@ -43,17 +43,19 @@ class OracleBandOps:
     def _inputs(self, name):
         return self.g.inputs(self.g.view_index(name))
 
-    def gather(self, tile_range, min_cover, reduce_counts):
-        lo = tile_range[0] * TILE
-        hi = min(self.width * self.height, lo + tile_range[1] * TILE)
-        self.lo, self.hi = lo, hi
+    def gather(self, band, min_cover, reduce_counts):
+        P = self.width * self.height
+        self.px = band.pixels(P)                     # global pixel of every local pixel
+        self.local_of = np.full(P, -1, np.int64)
+        self.local_of[self.px] = np.arange(len(self.px))
+        mine = np.zeros(P, bool)
+        mine[self.px] = True
         depthT = self._inputs(self.target)[0]
         per_view, counts = [], []
         for name in self.order:
             idx, _, _ = oracle.match_pair(depthT, self.geoms[self.target], self._inputs(name)[0], self.geoms[name])
             flat = idx.reshape(-1).copy()
-            flat[:lo] = -1
-            flat[hi:] = -1
+            flat[~mine] = -1
             per_view.append(flat.reshape(idx.shape))
             counts.append(int((flat >= 0).sum()))
         view_count = torch.tensor(counts, dtype=torch.int64)
@@ -80,10 +82,10 @@ class OracleBandOps:
 
     def _J(self):
         B, beta, gamma = self.p[0:3].astype(np.float64), self.p[3:6].astype(np.float64), self.p[6:9].astype(np.float64)
-        n = self.hi - self.lo
+        n = len(self.px)
         num, den = np.zeros((n, 3)), np.zeros((n, 3))
         for o in self.obs:
-            pix = o['v1'].astype(np.int64) * self.width + o['u1'] - self.lo
+            pix = self.local_of[o['v1'].astype(np.int64) * self.width + o['u1']]
             z = o['z'].astype(np.float64)[:, None]
             a = np.exp(-beta * z)
             num[pix] += (o['I'].T - B * (1 - np.exp(-gamma * z))) * a
@@ -96,7 +98,7 @@ class OracleBandOps:
         J = self._J()
         out = np.zeros(10)
         for o in self.obs:
-            pix = o['v1'].astype(np.int64) * self.width + o['u1'] - self.lo
+            pix = self.local_of[o['v1'].astype(np.int64) * self.width + o['u1']]
             z = o['z'].astype(np.float64)[:, None]
             a, e = np.exp(-beta * z), np.exp(-gamma * z)
             r = o['I'].T - (J[pix] * a + B * (1 - e))
@@ -145,6 +147,7 @@ def _worker(rank, world, port, case, out_path):
 
 @pytest.mark.parametrize('case,world', [('tiny6_closed', 2), ('mixed8_image0004', 2), ('tiny6_closed', 3)])
 def test_band_sharded_restore_over_gloo(case, world):
+    """Cyclic bands (the default layout of restore_band_sharded) over gloo."""
     g = Golden(case)
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, 'res.npz')
@@ -169,6 +172,16 @@ def test_partitions_cover_everything_once():
             assert bands[0][0] == 0 and sum(n for _, n in bands) == n_tiles
             assert all(bands[r][0] + bands[r][1] == bands[r + 1][0] for r in range(world - 1))
             assert max(n for _, n in bands) - min(n for _, n in bands) <= 1
+            for layout in ('cyclic', 'contiguous'):      # every tile exactly once, in increasing order within a rank
+                parts = [sdist.make_band(n_tiles, r, world, layout) for r in range(world)]
+                tiles = [b.tiles() for b in parts]
+                assert all((np.diff(t) > 0).all() for t in tiles)
+                assert np.array_equal(np.sort(np.concatenate(tiles)), np.arange(n_tiles))
+                P = n_tiles * 32 - 5
+                px = np.concatenate([b.pixels(P) for b in parts])
+                assert np.array_equal(np.sort(px), np.arange(P))
+                if layout == 'cyclic' and n_tiles >= 96:
+                    assert max(b.n_tiles for b in parts) - min(b.n_tiles for b in parts) <= 64
     targets = list(range(50))
     parts = [sdist.shard_targets(targets, r, 8) for r in range(8)]
     assert sorted(sum(parts, [])) == targets and max(map(len, parts)) - min(map(len, parts)) <= 1

@@ -19,26 +19,30 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 
-def test_bands_compose_to_the_whole_image():
+@pytest.mark.parametrize('layout', ['contiguous', 'cyclic'])
+def test_bands_compose_to_the_whole_image(layout):
     scene = SyntheticScene(7, 150, 101, seed=9)   # 15150 pixels = 473 tiles + 14 pixels
     ds, _ = helpers.build_device_scene(scene, range(7))
     keys = list(range(7))
     full = engine.gather(ds, 3, keys, min_cover=0.2, keep_src=True)
     n_tiles = full.n_tiles
+    from sucre_b200._lib import Band
     counts = []
     for r in range(3):
-        counts.append(engine.gather(ds, 3, keys, min_cover=0.0, tile_range=sdist.tile_band(n_tiles, r, 3)).view_count)
+        counts.append(engine.gather(ds, 3, keys, min_cover=0.0, band=sdist.make_band(n_tiles, r, 3, layout)).view_count)
     total = torch.from_numpy(np.sum(counts, axis=0)).cuda()
     assert np.array_equal(total.cpu().numpy(), full.view_count)
-    bands = [engine.gather(ds, 3, keys, min_cover=0.2, keep_src=True, tile_range=sdist.tile_band(n_tiles, r, 3),
+    bands = [engine.gather(ds, 3, keys, min_cover=0.2, keep_src=True, band=sdist.make_band(n_tiles, r, 3, layout),
                            reduce_counts=lambda vc: vc.copy_(total)) for r in range(3)]
     assert sum(b.n_obs for b in bands) == full.n_obs and all(np.array_equal(b.view_kept, full.view_kept) for b in bands)
+    assert sum(b.local_pixels for b in bands) == 150 * 101
     whole = full.to_reference_layout()
     parts = [b.to_reference_layout() for b in bands]
     for key, ref in whole.items():
+        order = np.argsort(np.concatenate([p[key]['v1'].astype(np.int64) * 150 + p[key]['u1'] for p in parts]), kind='stable')
         for f in ('u1', 'v1', 'u2', 'v2', 'z', 'I'):
             cat = np.concatenate([p[key][f] for p in parts], axis=-1)
-            assert np.array_equal(cat, ref[f]), (key, f)
+            assert np.array_equal(cat[..., order], ref[f]), (key, f)   # the bands' records, in target order, are the image's
     # one objective evaluation: band sums add up to the whole-image sums; band J's tile the whole J
     state = engine.FitState.initial(ds.device)
     sums = torch.zeros(10, dtype=torch.float64, device=ds.device)
@@ -55,8 +59,16 @@ def test_bands_compose_to_the_whole_image():
     # in a band and in the whole image, which reorders the fp32 additions inside a pixel's statistics)
     assert torch.allclose(acc, sums, rtol=2e-4, atol=0)
     J = engine.closed_form_J(full, state.params).reshape(-1, 3)
-    assert torch.equal(torch.isnan(torch.cat(Js)), torch.isnan(J))
-    assert float((torch.cat(Js) - J).nan_to_num(0.0).abs().max()) < 1e-6
+    Jb = torch.full_like(J, -5.0)
+    for b, Jr in zip(bands, Js):
+        Jb[b.global_pixels()] = Jr[:b.local_pixels]
+    assert torch.equal(torch.isnan(Jb), torch.isnan(J))
+    assert float((Jb - J).nan_to_num(0.0).abs().max()) < 1e-6
+    # the scatter kernel puts a band's J at the same places
+    out = torch.full_like(J, -5.0)
+    for b, Jr in zip(bands, Js):
+        engine.scatter_J(b, Jr.contiguous(), [out.data_ptr()])
+    assert torch.equal(out.nan_to_num(7.0), Jb.nan_to_num(7.0))
 
 
 def _free_port():

@@ -23,7 +23,7 @@ for path in (sys.argv[1:] or [str(_lib.LIB_PATH)]):
     _lib._lib, _lib.LIB_PATH = None, Path(path).resolve()
     if store is None:
         nt = (W * H + 31) // 32
-        store = engine.gather(ds, 55, list(range(V)), tile_range=None if band == 1 else (0, nt // band))
+        store = engine.gather(ds, 55, list(range(V)), band=None if band == 1 else _lib.Band.cyclic(nt, 0, band))
     store.workspace = None
     best, params = 1e9, None
     for rep in range(4):
