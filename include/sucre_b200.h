@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 8
+#define SUCRE_ABI_VERSION 9
 #define SUCRE_TILE_PIXELS 32
 #define SUCRE_REC_Z_U8 0
 #define SUCRE_REC_Z_F32 1
@@ -209,24 +209,25 @@ int sucre_fit_sums(int mode, const sucre_store* store_host, const float* params,
 int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_t n_obs, int t, double lr,
                     float* history_row, void* stream);
 
-/* The whole single-GPU loop of adam() (sucre.py:138-148): num_iter kernels, each = one sweep + the Adam step of
- * the 9 scalars (steps first_step .. first_step+num_iter-1).  history (optional) = num_iter x 10 floats.
- * For the final update_J of closed-form mode (sucre.py:156) call sucre_fit_write_J. */
+/* The whole single-GPU loop of adam() (sucre.py:138-148) as ONE launch of a resident grid (one per 1024 iterations):
+ * every iteration = one sweep of the store + the Adam step of the 9 scalars in the last CTA to finish, which then raises
+ * the flag the other CTAs wait on (steps first_step .. first_step+num_iter-1).  history (optional) = num_iter x 10
+ * floats.  For the final update_J of closed-form mode (sucre.py:156) call sucre_fit_write_J. */
 int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
               float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
               void* stream);
 
 /* The same loop for ONE target whose tiles are sharded over `world` GPUs (store_host = this rank's band, n_obs_global
  * = observations of all bands): the all-reduce of the 10 sums is fused into the kernel — the last CTA of every rank
- * stores its sums into every peer's exchange buffer over NVLink (peers_host[p] = device address of rank p's buffer,
- * SUCRE_PEER_BUFFER_BYTES each, zeroed once, mapped into this process, e.g. torch symmetric memory), waits for all
- * ranks' tags and adds the rows in rank order, so every rank applies the identical Adam step with no host or NCCL
- * round trip.  first_epoch: a tag >= 1 for the first iteration, identical on all ranks, and increasing by num_iter
+ * stores its sums, as 8-byte words tagged with the iteration's epoch, into every peer's exchange buffer over NVLink
+ * (peers_host[p] = device address of rank p's buffer, SUCRE_PEER_BUFFER_BYTES each, zeroed once, mapped into this
+ * process, e.g. torch symmetric memory), polls its own buffer for the words of all ranks and adds the rows in rank
+ * order, so every rank applies the identical Adam step with no host or NCCL round trip.  first_epoch: a tag >= 1 for the first iteration, identical on all ranks, and increasing by num_iter
  * from one call on the same buffers to the next.  All ranks must make the same sequence of calls.  A rank that waits
  * longer than SUCRE_PEER_TIMEOUT_NS for a peer stops waiting, sets bit 0 of the status word
  * (sucre_fit_status) and carries on with what it has, so a dead peer cannot hang the node. */
 #define SUCRE_MAX_PEERS 16
-#define SUCRE_PEER_BUFFER_BYTES 3072
+#define SUCRE_PEER_BUFFER_BYTES 5120
 #define SUCRE_PEER_TIMEOUT_NS 2000000000ull
 int sucre_fit_sharded(int mode, const sucre_store* store_host, int64_t n_obs_global, float* params, float* adam_state,
                       float* J, float* J_moments, int first_step, int num_iter, double lr, float* history,

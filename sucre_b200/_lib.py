@@ -9,7 +9,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 8
+ABI_VERSION = 9
 TILE = 32
 REC_Z_U8, REC_Z_F32, REC_P_U8, REC_P_F32 = 0, 1, 2, 3
 RECORD_BYTES = {REC_Z_U8: 8, REC_Z_F32: 16, REC_P_U8: 16, REC_P_F32: 32}
@@ -77,7 +77,7 @@ class Band(C.Structure):
 
 
 assert C.sizeof(Band) == 16
-MAX_PEERS, PEER_BUFFER_BYTES = 16, 3072
+MAX_PEERS, PEER_BUFFER_BYTES = 16, 5120
 
 
 _lib = None

@@ -55,14 +55,11 @@ constexpr int kTileCost = SUCRE_FIT_TILE_COST;
 constexpr size_t kWsPartials = 0;                                                     // double[kMaxFitCtas][kSums]
 constexpr size_t kWsPartRow = kWsPartials + sizeof(double) * kSums * kMaxFitCtas;      // long long[kMaxFitCtas*kFitWarps + 1]
 constexpr size_t kWsPartTile = kWsPartRow + sizeof(long long) * (kMaxFitCtas * kFitWarps + 2);  // int[kMaxFitCtas*kFitWarps + 1]
-constexpr size_t kWsTicket = kWsPartTile + sizeof(int) * (kMaxFitCtas * kFitWarps + 4);  // unsigned ticket, unsigned status; 16-aligned
-#ifdef SUCRE_FIT_TIMING  // developer build: %globaltimer at CTA start and at the end of every warp's tile loop (tools/fit_timing.py)
-constexpr size_t kWsTiming = kWsTicket + 16;   // u64[kMaxFitCtas] CTA start, u64[kMaxFitCtas*kFitWarps] warp end, u64 last CTA end
-constexpr size_t kWsBytes = kWsTiming + 8 * (kMaxFitCtas + kMaxFitCtas * kFitWarps + 1);
-#else
-constexpr size_t kWsBytes = kWsTicket + 16;
-#endif
-static_assert(kWsPartRow % 8 == 0 && kWsPartTile % 8 == 0 && kWsTicket % 16 == 0, "workspace alignment");
+constexpr size_t kWsTicket = kWsPartTile + sizeof(int) * (kMaxFitCtas * kFitWarps + 4);  // unsigned ticket, status, iteration flag; 16-aligned
+constexpr int kMaxLoopIters = 1024;   // Adam iterations per launch of the persistent loop (longer runs are split)
+constexpr size_t kWsAdamTab = kWsTicket + 16;                        // AdamScalars[kMaxLoopIters]
+constexpr size_t kWsBytes = kWsAdamTab + 16 * kMaxLoopIters;
+static_assert(kWsPartRow % 8 == 0 && kWsPartTile % 8 == 0 && kWsTicket % 16 == 0 && kWsAdamTab % 16 == 0, "workspace alignment");
 
 __device__ __forceinline__ unsigned long long globaltimer() {
     unsigned long long t;
@@ -93,6 +90,8 @@ struct AdamScalars {
     double grad_scale;  // 2 / (3 n_obs): d/dtheta of sum r^2 / n_obs / 3 (sucre.py:145)
 };
 
+static_assert(sizeof(AdamScalars) == 16, "Adam table entry");
+
 static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
     const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
     AdamScalars s;
@@ -108,17 +107,18 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 // latency is covered by the copies in flight instead of by occupancy, and the arithmetic reads one record per lane
 // and row from shared memory.  A slot is refilled as soon as the walk has left it.
 #ifndef SUCRE_FIT_CHUNK_BYTES
-#define SUCRE_FIT_CHUNK_BYTES 3584
+#define SUCRE_FIT_CHUNK_BYTES 4096
 #endif
 #ifndef SUCRE_FIT_STAGES
-#define SUCRE_FIT_STAGES 3
+#define SUCRE_FIT_STAGES 2
 #endif
-constexpr int kChunkBytes = SUCRE_FIT_CHUNK_BYTES;   // 14 rows of 8-byte records, 7 rows of 16-byte records
+constexpr int kChunkBytes = SUCRE_FIT_CHUNK_BYTES;   // 16 rows of 8-byte records, 8 rows of 16-byte records
 constexpr int kStages = SUCRE_FIT_STAGES;
-constexpr int kRingBytes = kChunkBytes * kStages;    // 10.5 KB per warp
+constexpr int kRingBytes = kChunkBytes * kStages;    // 8 KB per warp; a power of two, so a row offset wraps with one AND
 constexpr size_t kParkBytes = (size_t)kFitWarps * kStats * 32 * sizeof(float);   // 54 KB: parked statistics of split tiles
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingBytes + kParkBytes;
 static_assert(kChunkBytes % 512 == 0, "a chunk must hold whole rows of both record sizes");
+static_assert((kRingBytes & (kRingBytes - 1)) == 0 && kStages >= 2, "the ring size must be a power of two, at least two slots");
 static_assert(kFitSmem <= 225 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -327,7 +327,7 @@ struct FitArgs {
     const long long* row_off;
     int n_tiles;
     long long pixels;
-    float* params;         // 9: B, beta, gamma (read at start; written by the last CTA when do_step)
+    float* params;         // 9: B, beta, gamma (read at the start of every iteration; written by the last CTA when do_step)
     float* moments;        // 18: Adam state of the 9 scalars
     float* J;              // pixels*3: Jref (closed form, in/out), the J parameter (in/out), or Jref (write-J, may be null)
     float* J_out;          // pixels*3: write-J mode output
@@ -335,38 +335,49 @@ struct FitArgs {
     const long long* part_row;  // per global warp: first row of its stream; [n_warps] = rows of the store
     const int* part_tile;       // per global warp: first tile it owns (finalises); [n_warps] = n_tiles
     double* partials;      // gridDim.x rows of kSums
-    unsigned* ticket;      // ticket[0] = CTA counter, ticket[1] = status bits
-#ifdef SUCRE_FIT_TIMING
-    unsigned long long* timing;
-#endif
+    unsigned* ticket;      // ticket[0] = CTA counter, ticket[1] = status bits, ticket[2] = iterations completed by this launch
     double* sums_out;      // if non-null the last CTA stores the reduced sums here
-    float* history_row;    // if non-null: params after the step + cost
+    float* history;        // if non-null: num_iter rows of {params after the step [9], cost}
     int do_step;           // apply Adam to the 9 scalars in the last CTA
-    AdamScalars adam;
+    int num_iter;          // iterations this launch runs (the grid stays resident and meets at a flag between them)
+    const AdamScalars* adam_tab;   // num_iter entries (device)
     // pixel-band sharding over several GPUs: one-shot all-reduce of the 10 sums over NVLink peer memory, fused
     // into the last CTA (world == 1: single GPU, nothing exchanged)
     int rank, world;
-    unsigned epoch;                           // unique, increasing tag of this launch on every rank
+    unsigned epoch;                           // tag of the first iteration; unique and increasing on every rank
     unsigned long long peer[SUCRE_MAX_PEERS]; // peer[p] = address of rank p's exchange buffer (PeerSlot[2][SUCRE_MAX_PEERS])
 };
 
-// what rank r leaves in every peer's buffer at [epoch & 1][r]
+// What rank r leaves in every peer's buffer at [epoch & 1][r]: the 10 sums as 20 words {epoch : 32 | half of a double : 32}.
+// An aligned 8-byte store is atomic, so a word whose tag is the current epoch carries valid data: no fence, no
+// separate flag, one NVLink store latency per exchange (the layout of NCCL's LL protocol).
+constexpr int kLLWords = 2 * kSums;
 struct PeerSlot {
-    double sums[kSums];
-    unsigned flag;
-    unsigned pad[3];
+    unsigned long long w[kLLWords];
 };
-static_assert(sizeof(PeerSlot) == 96 && sizeof(PeerSlot) * 2 * SUCRE_MAX_PEERS == SUCRE_PEER_BUFFER_BYTES, "peer buffer layout");
+static_assert(sizeof(PeerSlot) == 160 && sizeof(PeerSlot) * 2 * SUCRE_MAX_PEERS == SUCRE_PEER_BUFFER_BYTES, "peer buffer layout");
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
+// One launch = num_iter Adam iterations (MODE kWriteJ: one sweep).  The grid (one CTA per SM, all resident) stays on the
+// machine: after an iteration every CTA leaves its row of partial sums, the last one (ticket) reduces them, exchanges
+// them with the other GPUs if the target is sharded, takes the Adam step and raises the iteration flag; meanwhile the
+// other CTAs have already started the bulk copies of the next iteration's first rows and wait on the flag.
 template <int MODE, int REC, bool PRECISE>
 __global__ void __launch_bounds__(kFitThreads, 1)
 fit_kernel(const __grid_constant__ FitArgs A) {
@@ -375,20 +386,18 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     constexpr int kRowBytes = 32 * RT::kBytes;
     constexpr int CR = kChunkBytes / kRowBytes;   // rows per chunk
     constexpr float kScale = RT::kScale;
+    constexpr float kInv = 1.0f / kScale;
     static_assert(CR >= 2, "a chunk must hold at least two rows");
 
     extern __shared__ __align__(128) unsigned char fit_smem[];
     __shared__ __align__(8) unsigned long long bars[kFitWarps][kStages];
     __shared__ __align__(8) unsigned long long park_bar[kFitWarps];
-    // Programmatic dependent launch: let the next iteration's kernel be scheduled as soon as SM resources free up;
-    // everything up to griddepcontrol.wait below touches only data that no iteration writes (offsets, partition,
-    // cells), so this prologue overlaps the previous iteration's tail.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ double sm[kFitWarps][kSums];
+    __shared__ double tot[kSums];
+    __shared__ unsigned ll_half[SUCRE_MAX_PEERS][kLLWords];
+    __shared__ unsigned s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
-#ifdef SUCRE_FIT_TIMING
-    if (threadIdx.x == 0) A.timing[blockIdx.x] = globaltimer();
-#endif
     const unsigned char* ring = fit_smem + (size_t)warp * kRingBytes;
     float* const park_all = reinterpret_cast<float*>(fit_smem + (size_t)kFitWarps * kRingBytes);
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
@@ -400,19 +409,19 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     }
     __syncthreads();  // the park barrier of a warp is waited on by its neighbour
 
-    // per-thread partial sums of the ten global sums: fp32 over this warp's tiles (a few dozen per-pixel values, each
-    // itself an fp32 sum), promoted to double for everything that follows (warp tree, CTA row, last CTA, peers)
-    float acc[kSums];
-#pragma unroll
-    for (int i = 0; i < kSums; ++i) acc[i] = 0.f;
-
     const long long B0 = A.part_row[gw], B1 = A.part_row[gw + 1];
     const int T0 = A.part_tile[gw], T1 = A.part_tile[gw + 1];
     const int n_rows_w = (int)(B1 - B0);
     const int n_chunks = (n_rows_w + CR - 1) / CR;
     const unsigned char* src = A.cells + B0 * kRowBytes;
+    // work items: [the tail of tile T0-1, owned by the previous warp,] then the owned tiles T0 .. T1-1, the last of
+    // which may continue in the next warp's stream
+    const bool has_head = T0 > 0 && A.row_off[T0] > B0;
+    const int t_first = T0 - (has_head ? 1 : 0);
 
-    // ring bookkeeping, all warp-uniform (stream rows are relative to B0)
+    // ring bookkeeping, all warp-uniform (stream rows are relative to B0).  Slots and barrier phases carry over from
+    // one iteration to the next: an iteration ends with every issued chunk consumed, so the next one starts at
+    // whatever slot comes next.
     int next_issue = 0, issue_slot = 0;  // next chunk to copy and the slot it goes to
     int wait_slot = 0;                   // slot of the next chunk to wait for
     uint32_t wait_parity = 0;
@@ -447,234 +456,248 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             release_at += CR;
         }
     };
-    for (int c = 0; c < min(kStages, n_chunks); ++c) advance_issue();
+    auto restart_stream = [&]() {  // the cells never change: the first copies of an iteration can start before its parameters exist
+        __syncwarp();
+        next_issue = 0, avail = 0, release_at = CR, pos = 0;
+        roff = issue_slot * kChunkBytes;
+        for (int c = 0; c < min(kStages, n_chunks); ++c) advance_issue();
+    };
+    restart_stream();
 
-    // the previous iteration (parameters, J, ticket) must be complete and visible from here on
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    float Bs[3];   // B in the store's units
-    typename PixelStats<MODE, PRECISE, REC>::Consts kc;
-    {
-        float kb[3], kg[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float B = A.params[c], beta = A.params[3 + c], gamma = A.params[6 + c];
-            Bs[c] = B * kScale;
-            kb[c] = PRECISE ? -beta : -beta * kLog2e;     // e^{-beta z} = 2^{kb z}
-            kg[c] = PRECISE ? -gamma : -gamma * kLog2e;
-        }
-        kc.kb_rg = pk(kb[0], kb[1]), kc.kg_rg = pk(kg[0], kg[1]), kc.nB_rg = pk(-Bs[0], -Bs[1]);
-        kc.kb_b = kb[2], kc.kg_b = kg[2], kc.nB_b = -Bs[2];
-    }
-    constexpr float kInv = 1.0f / kScale;
-
-    // work items: [the tail of tile T0-1, owned by the previous warp,] then the owned tiles T0 .. T1-1, the last of
-    // which may continue in the next warp's stream
-    const bool has_head = T0 > 0 && A.row_off[T0] > B0;
-    int t = T0 - (has_head ? 1 : 0);
-    long long rend_next = t < T1 ? A.row_off[t + 1] : 0;
-    long long p_next = (long long)t * kTile + lane;
-    float Jnext[3] = {0.f, 0.f, 0.f};
-    if (A.J && t < T1 && p_next < A.pixels) {
-        Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
-    }
-
+    const int n_iter = MODE == kWriteJ ? 1 : A.num_iter;
 #pragma unroll 1
-    for (; t < T1; ++t) {
-        const bool head = t < T0;
-        const long long rend = rend_next;
-        const long long p = p_next;
-        float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
-        if (t + 1 < T1) {  // prefetch the next tile's extent and reference J
-            rend_next = A.row_off[t + 2];
-            p_next = p + kTile;
-            if (A.J && p_next < A.pixels) {
-                Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
-            }
+    for (int it = 0; it < n_iter; ++it) {
+        if (it > 0) {  // the step of the previous iteration (parameters, moments, ticket) is complete once the flag says so
+            if (threadIdx.x == 0)
+                while (ld_acquire_gpu(A.ticket + 2) < (unsigned)it) __nanosleep(20);
+            __syncthreads();
         }
-        if (MODE == kWriteJ) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Jref[c] = Jref[c] == Jref[c] ? Jref[c] : 0.f;  // a NaN reference is no reference
-        }
-        const bool cut = rend > B1;                           // the tile's last rows are in the next warp's stream
-        const int rb = (int)((cut ? B1 : rend) - B0);         // stream row where this item ends
-        PixelStats<MODE, PRECISE, REC> st;
-        st.clear();
-        unsigned seen_bits = 0;   // OR of the z bit patterns of the lane's records: non-zero iff it has an observation
+        float Bs[3];   // B in the store's units
+        typename PixelStats<MODE, PRECISE, REC>::Consts kc;
         {
-            const u64 nJ_rg = pk(-Jref[0] * kScale, -Jref[1] * kScale);
-            const float nJ_b = -Jref[2] * kScale;
-            const unsigned char* lane_ring = ring + lane * RT::kBytes;
-            int r = pos;
-            // Two rows per step for instruction-level parallelism (their exp / residual chains are independent until the
-            // accumulators); the body is branch-free (sentinels are masked arithmetically).  The ring is dealt with
-            // outside the inner loop: it runs up to what has landed, then the consumed slots are refilled and the next
-            // chunk is awaited.
-            while (true) {
-                const int lim = min(rb, avail);
+            float kb[3], kg[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {   // written by another SM between iterations: read through L2
+                const float B = __ldcg(A.params + c), beta = __ldcg(A.params + 3 + c), gamma = __ldcg(A.params + 6 + c);
+                Bs[c] = B * kScale;
+                kb[c] = PRECISE ? -beta : -beta * kLog2e;     // e^{-beta z} = 2^{kb z}
+                kg[c] = PRECISE ? -gamma : -gamma * kLog2e;
+            }
+            kc.kb_rg = pk(kb[0], kb[1]), kc.kg_rg = pk(kg[0], kg[1]), kc.nB_rg = pk(-Bs[0], -Bs[1]);
+            kc.kb_b = kb[2], kc.kg_b = kg[2], kc.nB_b = -Bs[2];
+        }
+        const AdamScalars ad = (MODE == kWriteJ || A.adam_tab == nullptr) ? AdamScalars{0.f, 1.f, 0.0} : A.adam_tab[it];
+
+        // per-thread partial sums of the ten global sums: fp32 over this warp's tiles (a few dozen per-pixel values,
+        // each itself an fp32 sum), promoted to double for everything that follows (warp tree, CTA row, last CTA, peers)
+        float acc[kSums];
+#pragma unroll
+        for (int i = 0; i < kSums; ++i) acc[i] = 0.f;
+
+        int t = t_first;
+        long long rend_next = t < T1 ? A.row_off[t + 1] : 0;
+        long long p_next = (long long)t * kTile + lane;
+        float Jnext[3] = {0.f, 0.f, 0.f};
+        if (A.J && t < T1 && p_next < A.pixels) {
+            Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
+        }
+
 #pragma unroll 1
-                for (; r + 2 <= lim; r += 2) {
-                    const int o1 = roff + kRowBytes == kRingBytes ? 0 : roff + kRowBytes;
+        for (; t < T1; ++t) {
+            const bool head = t < T0;
+            const long long rend = rend_next;
+            const long long p = p_next;
+            float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
+            if (t + 1 < T1) {  // prefetch the next tile's extent and reference J
+                rend_next = A.row_off[t + 2];
+                p_next = p + kTile;
+                if (A.J && p_next < A.pixels) {
+                    Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
+                }
+            }
+            if (MODE == kWriteJ) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Jref[c] = Jref[c] == Jref[c] ? Jref[c] : 0.f;  // a NaN reference is no reference
+            }
+            const bool cut = rend > B1;                           // the tile's last rows are in the next warp's stream
+            const int rb = (int)((cut ? B1 : rend) - B0);         // stream row where this item ends
+            PixelStats<MODE, PRECISE, REC> st;
+            st.clear();
+            unsigned seen_bits = 0;   // OR of the z bit patterns of the lane's records: non-zero iff it has an observation
+            {
+                const u64 nJ_rg = pk(-Jref[0] * kScale, -Jref[1] * kScale);
+                const float nJ_b = -Jref[2] * kScale;
+                const unsigned char* lane_ring = ring + lane * RT::kBytes;
+                int r = pos;
+                // Two rows per step for instruction-level parallelism (their exp / residual chains are independent until
+                // the accumulators); the body is branch-free (sentinels are masked arithmetically).  The ring is dealt
+                // with outside the inner loop: it runs up to what has landed, then the consumed slots are refilled and
+                // the next chunk is awaited.
+                while (true) {
+                    const int lim = min(rb, avail);
+#pragma unroll 1
+                    for (; r + 2 <= lim; r += 2) {
+                        const int o1 = (roff + kRowBytes) & (kRingBytes - 1);
+                        const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
+                        const Raw q1 = *reinterpret_cast<const Raw*>(lane_ring + o1);
+                        roff = (o1 + kRowBytes) & (kRingBytes - 1);
+                        seen_bits |= __float_as_uint(RT::range(q0));
+                        st.add(RT::unpack(q0), RT::unpack(q1), kc, nJ_rg, nJ_b);
+                    }
+                    pos = r;
+                    if (pos >= release_at) release();
+                    if (r + 2 > rb) break;
+                    acquire(r + 2);
+                }
+                if (r < rb) {  // odd row count: one last row, paired with an all-zero record
+                    if (r + 1 > avail) acquire(r + 1);
                     const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
-                    const Raw q1 = *reinterpret_cast<const Raw*>(lane_ring + o1);
-                    roff = o1 + kRowBytes == kRingBytes ? 0 : o1 + kRowBytes;
+                    roff = (roff + kRowBytes) & (kRingBytes - 1);
                     seen_bits |= __float_as_uint(RT::range(q0));
-                    st.add(RT::unpack(q0), RT::unpack(q1), kc, nJ_rg, nJ_b);
+                    st.add(RT::unpack(q0), RT::unpack(Raw{}), kc, nJ_rg, nJ_b);
+                    pos = r + 1;
+                    if (pos >= release_at) release();
                 }
-                pos = r;
-                if (pos >= release_at) release();
-                if (r + 2 > rb) break;
-                acquire(r + 2);
             }
-            if (r < rb) {  // odd row count: one last row
-                if (r + 1 > avail) acquire(r + 1);
-                const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
-                roff = roff + kRowBytes == kRingBytes ? 0 : roff + kRowBytes;
-                seen_bits |= __float_as_uint(RT::range(q0));
-                st.add(RT::unpack(q0), RT::unpack(Raw{}), kc, nJ_rg, nJ_b);
-                pos = r + 1;
-                if (pos >= release_at) release();
+            const bool seen = seen_bits != 0;
+            if (head) {  // hand the partial statistics of the previous warp's last tile over
+                st.park(park_all + (size_t)warp * kStats * 32, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&park_bar[warp]));
+                continue;
             }
-        }
-        const bool seen = seen_bits != 0;
-        if (head) {  // hand the partial statistics of the previous warp's last tile over
-            st.park(park_all + (size_t)warp * kStats * 32, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&park_bar[warp]));
-            continue;
-        }
-        if (cut) {   // the next warp evaluated the rest of this tile first thing
-            mbar_wait(smem_u32(&park_bar[warp + 1]), 0);
-            st.add_parked(park_all + (size_t)(warp + 1) * kStats * 32, lane);
-        }
-        if (MODE == kWriteJ) {
-            if (p < A.pixels) {
+            if (cut) {   // the next warp evaluated the rest of this tile first thing (one arrival per iteration: phase = it & 1)
+                mbar_wait(smem_u32(&park_bar[warp + 1]), (uint32_t)it & 1u);
+                st.add_parked(park_all + (size_t)(warp + 1) * kStats * 32, lane);
+            }
+            if (MODE == kWriteJ) {
+                if (p < A.pixels) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    A.J_out[3 * p + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
-            }
-        } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
-            float Jout[3];
+                    for (int c = 0; c < 3; ++c)
+                        A.J_out[3 * p + c] = seen ? Jref[c] + __fdividef(st.get(c, 0), st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
+                }
+            } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
+                float Jout[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                // all in the store's units: S1, S3, S5, S7 carry one factor kScale, S9 two
-                const float S1 = st.get(c, 0), S3 = st.get(c, 2), S5 = st.get(c, 4), S7 = st.get(c, 6), S9 = st.get(c, 8);
-                float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
-                if (MODE == kClosedForm) {
-                    delta = S1 / st.get(c, 1);
-                    rh = fmaf(-delta, st.get(c, 3), S3);
-                    rza = fmaf(-delta, st.get(c, 5), S5);
-                    rzg = fmaf(-delta, st.get(c, 7), S7);
-                    rr = fmaf(-delta, S1, S9);
+                for (int c = 0; c < 3; ++c) {
+                    // all in the store's units: S1, S3, S5, S7 carry one factor kScale, S9 two
+                    const float S1 = st.get(c, 0), S3 = st.get(c, 2), S5 = st.get(c, 4), S7 = st.get(c, 6), S9 = st.get(c, 8);
+                    float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
+                    if (MODE == kClosedForm) {
+                        delta = __fdividef(S1, st.get(c, 1));
+                        rh = fmaf(-delta, st.get(c, 3), S3);
+                        rza = fmaf(-delta, st.get(c, 5), S5);
+                        rzg = fmaf(-delta, st.get(c, 7), S7);
+                        rr = fmaf(-delta, S1, S9);
+                    }
+                    const float Js = fmaf(Jref[c], kScale, delta);   // J in the store's units
+                    Jout[c] = Js * kInv;
+                    acc[c] += rh;                                // sum r (1 - e^{-gamma z})    x kScale
+                    acc[3 + c] = fmaf(Js, rza, acc[3 + c]);      // sum r J z e^{-beta z}       x kScale^2
+                    acc[6 + c] = fmaf(Bs[c], rzg, acc[6 + c]);   // sum r B z e^{-gamma z}      x kScale^2
+                    acc[9] += rr;                                // sum r^2                     x kScale^2
+                    if (MODE == kParamJ) {
+                        // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step with the pre-step B, beta, gamma (sucre.py:144-148)
+                        float* mv = A.J_moments + 6 * p;
+                        float m = mv[c], v = mv[3 + c];
+                        Jout[c] = adam_update(Jref[c], (float)(-ad.grad_scale) * (S1 * kInv), m, v, ad.neg_step_size, ad.bc2_sqrt);
+                        mv[c] = m;
+                        mv[3 + c] = v;
+                    }
                 }
-                const float Js = fmaf(Jref[c], kScale, delta);   // J in the store's units
-                Jout[c] = Js * kInv;
-                acc[c] += rh;                          // sum r (1 - e^{-gamma z})    x kScale
-                acc[3 + c] = fmaf(Js, rza, acc[3 + c]);      // sum r J z e^{-beta z}       x kScale^2
-                acc[6 + c] = fmaf(Bs[c], rzg, acc[6 + c]);   // sum r B z e^{-gamma z}      x kScale^2
-                acc[9] += rr;                          // sum r^2                     x kScale^2
-                if (MODE == kParamJ) {
-                    // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step with the pre-step B, beta, gamma (sucre.py:144-148)
-                    float* mv = A.J_moments + 6 * p;
-                    float m = mv[c], v = mv[3 + c];
-                    Jout[c] = adam_update(Jref[c], (float)(-A.adam.grad_scale) * (S1 * kInv), m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
-                    mv[c] = m;
-                    mv[3 + c] = v;
-                }
+                A.J[3 * p + 0] = Jout[0];
+                A.J[3 * p + 1] = Jout[1];
+                A.J[3 * p + 2] = Jout[2];
             }
-            A.J[3 * p + 0] = Jout[0];
-            A.J[3 * p + 1] = Jout[1];
-            A.J[3 * p + 2] = Jout[2];
         }
-    }
-    if (MODE == kWriteJ) return;
-#ifdef SUCRE_FIT_TIMING
-    if (lane == 0) A.timing[kMaxFitCtas + gw] = globaltimer();
-#endif
+        if (MODE == kWriteJ) return;
+        if (it + 1 < n_iter) restart_stream();   // next iteration's first rows: in flight while the sums are reduced
 
-    // warp tree -> one slot per warp -> one row per CTA (the store's units are divided out here, in double)
-    __shared__ double sm[kFitWarps][kSums];
-    __shared__ unsigned s_ticket;
+        // warp tree -> one slot per warp -> one row per CTA (the store's units are divided out here, in double)
 #pragma unroll
-    for (int i = 0; i < kSums; ++i) {
-        double v = (double)acc[i];
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        if (lane == 0) sm[warp][i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kSums) {
-        double v = 0.0;
-        for (int wi = 0; wi < kFitWarps; ++wi) v += sm[wi][threadIdx.x];
-        const double unit = threadIdx.x < 3 ? 1.0 / (double)kScale : 1.0 / ((double)kScale * (double)kScale);
-        A.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v * unit;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-
-    // last CTA: fixed-order reduction of the rows, then the Adam step of the 9 scalars
-    __threadfence();
-    __shared__ double tot[kSums];
-    for (int col = warp; col < kSums; col += kFitWarps) {
-        double v = 0.0;
-        for (int r = lane; r < (int)gridDim.x; r += 32) v += __ldcg(A.partials + (size_t)r * kSums + col);
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        if (lane == 0) tot[col] = v;
-    }
-    __syncthreads();
-    if (A.world > 1) {
-        // One-shot all-reduce over NVLink: every rank stores its 10 sums into every peer's buffer (slot [epoch&1]
-        // [rank]), publishes them with a system-scope release of the epoch tag, waits for the tags of all ranks in
-        // its own buffer, and adds the rows in rank order — the same order on every rank, so all ranks take the
-        // identical Adam step without any host or NCCL round trip.  Two parities: a rank can be at most one
-        // launch ahead of the slowest reader of its previous message.  The wait is bounded: after
-        // SUCRE_PEER_TIMEOUT_NS a rank gives up on a silent peer, raises status bit 0 and carries on.
-        const unsigned par = A.epoch & 1u;
-        if (threadIdx.x < A.world * kSums) {
-            const int p = threadIdx.x / kSums, i = threadIdx.x % kSums;
-            PeerSlot* dst = reinterpret_cast<PeerSlot*>(A.peer[p]) + par * SUCRE_MAX_PEERS + A.rank;
-            dst->sums[i] = tot[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        PeerSlot* mine = reinterpret_cast<PeerSlot*>(A.peer[A.rank]) + par * SUCRE_MAX_PEERS;
-        if (threadIdx.x < A.world) {
-            st_release_sys(&(reinterpret_cast<PeerSlot*>(A.peer[threadIdx.x]) + par * SUCRE_MAX_PEERS + A.rank)->flag, A.epoch);
-            const unsigned long long t0 = globaltimer();
-            while (ld_acquire_sys(&mine[threadIdx.x].flag) != A.epoch) {
-                __nanosleep(32);
-                if (globaltimer() - t0 > SUCRE_PEER_TIMEOUT_NS) {
-                    atomicOr(A.ticket + 1, 1u);
-                    break;
-                }
-            }
+        for (int i = 0; i < kSums; ++i) {
+            double v = (double)acc[i];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (lane == 0) sm[warp][i] = v;
         }
         __syncthreads();
         if (threadIdx.x < kSums) {
             double v = 0.0;
-            for (int p = 0; p < A.world; ++p) v += *reinterpret_cast<volatile double*>(&mine[p].sums[threadIdx.x]);
-            tot[threadIdx.x] = v;
+            for (int wi = 0; wi < kFitWarps; ++wi) v += sm[wi][threadIdx.x];
+            const double unit = threadIdx.x < 3 ? 1.0 / (double)kScale : 1.0 / ((double)kScale * (double)kScale);
+            A.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v * unit;
+            __threadfence();
         }
         __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        if (s_ticket != gridDim.x - 1) continue;   // (uniform per CTA) on to the next iteration's flag
+
+        // last CTA: fixed-order reduction of the rows, then the Adam step of the 9 scalars
+        __threadfence();
+        for (int col = warp; col < kSums; col += kFitWarps) {
+            double v = 0.0;
+            for (int r = lane; r < (int)gridDim.x; r += 32) v += __ldcg(A.partials + (size_t)r * kSums + col);
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (lane == 0) tot[col] = v;
+        }
+        __syncthreads();
+        if (A.world > 1) {
+            // One-shot all-reduce over NVLink: every rank stores its 10 sums, as 20 tagged 8-byte words, into every
+            // peer's buffer (slot [epoch & 1][rank]) and polls the words of all ranks in its own buffer until they carry
+            // this epoch; the rows are then added in rank order — the same order on every rank, so all ranks take the
+            // identical Adam step without any host or NCCL round trip.  Two parities: a rank can be at most one
+            // iteration ahead of the slowest reader of its previous message.  The wait is bounded: after
+            // SUCRE_PEER_TIMEOUT_NS a rank gives up on a silent peer, raises status bit 0 and carries on.
+            const unsigned epoch = A.epoch + (unsigned)it;
+            const unsigned par = epoch & 1u;
+            if (threadIdx.x < A.world * kLLWords) {
+                const int p = threadIdx.x / kLLWords, j = threadIdx.x % kLLWords;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[j >> 1]);
+                const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+                PeerSlot* dst = reinterpret_cast<PeerSlot*>(A.peer[p]) + par * SUCRE_MAX_PEERS + A.rank;
+                st_relaxed_sys(&dst->w[j], ((unsigned long long)epoch << 32) | half);
+                const PeerSlot* mine = reinterpret_cast<const PeerSlot*>(A.peer[A.rank]) + par * SUCRE_MAX_PEERS + p;
+                const unsigned long long t0 = globaltimer();
+                unsigned long long word;
+                while ((unsigned)((word = ld_relaxed_sys(&mine->w[j])) >> 32) != epoch) {
+                    if (globaltimer() - t0 > SUCRE_PEER_TIMEOUT_NS) {
+                        atomicOr(A.ticket + 1, 1u);
+                        break;
+                    }
+                }
+                ll_half[p][j] = (unsigned)word;
+            }
+            __syncthreads();
+            if (threadIdx.x < kSums) {
+                double v = 0.0;
+                for (int p = 0; p < A.world; ++p)
+                    v += __longlong_as_double((long long)(((unsigned long long)ll_half[p][2 * threadIdx.x + 1] << 32) | ll_half[p][2 * threadIdx.x]));
+                tot[threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < kSums && A.sums_out) A.sums_out[threadIdx.x] = tot[threadIdx.x];
+        float* history_row = A.history ? A.history + (size_t)it * kSums : nullptr;
+        if (A.do_step && threadIdx.x < 9) {
+            const int i = threadIdx.x;
+            // B: -2 r (1-g); beta: +2 r J z a; gamma: -2 r B z g   (all times 1 / 3N)
+            const float g = (float)((i >= 3 && i < 6 ? ad.grad_scale : -ad.grad_scale) * tot[i]);
+            float m = A.moments[i], v = A.moments[9 + i];
+            const float pnew = adam_update(__ldcg(A.params + i), g, m, v, ad.neg_step_size, ad.bc2_sqrt);
+            A.moments[i] = m;
+            A.moments[9 + i] = v;
+            A.params[i] = pnew;
+            if (history_row) history_row[i] = pnew;
+        }
+        if (threadIdx.x == 9 && history_row) history_row[9] = (float)tot[9];
+        if (threadIdx.x == 0) *A.ticket = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {   // everything above is visible to whoever sees the flag
+            __threadfence();
+            st_release_gpu(A.ticket + 2, (unsigned)(it + 1));
+        }
     }
-    if (threadIdx.x < kSums && A.sums_out) A.sums_out[threadIdx.x] = tot[threadIdx.x];
-    if (A.do_step && threadIdx.x < 9) {
-        const int i = threadIdx.x;
-        // B: -2 r (1-g); beta: +2 r J z a; gamma: -2 r B z g   (all times 1 / 3N)
-        const float g = (float)((i >= 3 && i < 6 ? A.adam.grad_scale : -A.adam.grad_scale) * tot[i]);
-        float m = A.moments[i], v = A.moments[9 + i];
-        const float pnew = adam_update(A.params[i], g, m, v, A.adam.neg_step_size, A.adam.bc2_sqrt);
-        A.moments[i] = m;
-        A.moments[9 + i] = v;
-        A.params[i] = pnew;
-        if (A.history_row) A.history_row[i] = pnew;
-    }
-    if (threadIdx.x == 9 && A.history_row) A.history_row[9] = (float)tot[9];
-    if (threadIdx.x == 0) *A.ticket = 0u;
-#ifdef SUCRE_FIT_TIMING
-    if (threadIdx.x == 0) A.timing[kMaxFitCtas + kMaxFitCtas * kFitWarps] = globaltimer();
-#endif
 }
 
 // Adam step of the 9 scalars from already reduced sums (multi-GPU: after the all-reduce)
@@ -791,21 +814,13 @@ static int fit_grid() {
     return ctas[dev];
 }
 
-// pdl = true: programmatic dependent launch — only when the preceding kernel in the stream is another fit_kernel of
-// the same loop, because the prologue before griddepcontrol.wait reads cells / offsets / partition, which must not
-// have been written by the kernel just before (gather_sample, partition_kernel).
 template <int MODE>
-static void launch_fit(const FitArgs& a, int rec, int ctas, cudaStream_t st, bool pdl) {
+static void launch_fit(const FitArgs& a, int rec, int ctas, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(kFitThreads);
     cfg.dynamicSmemBytes = kFitSmem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // pairs with griddepcontrol.* in the kernel
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
     if (rec == SUCRE_REC_Z_U8) {
         if (precise_exp()) cudaLaunchKernelEx(&cfg, fit_kernel<MODE, SUCRE_REC_Z_U8, true>, a);
         else cudaLaunchKernelEx(&cfg, fit_kernel<MODE, SUCRE_REC_Z_U8, false>, a);
@@ -837,9 +852,8 @@ static FitArgs base_args(const sucre_store* s, void* workspace) {
     a.part_row = (const long long*)(ws + kWsPartRow);
     a.part_tile = (const int*)(ws + kWsPartTile);
     a.ticket = (unsigned*)(ws + kWsTicket);
-#ifdef SUCRE_FIT_TIMING
-    a.timing = (unsigned long long*)(ws + kWsTiming);
-#endif
+    a.adam_tab = (const AdamScalars*)(ws + kWsAdamTab);
+    a.num_iter = 1;
     a.rank = 0;
     a.world = 1;
     return a;
@@ -877,9 +891,10 @@ extern "C" int sucre_fit_sums(int mode, const sucre_store* store_host, const flo
     a.J_moments = J_moments;
     a.sums_out = sums;
     a.do_step = 0;
-    if (mode == kParamJ) a.adam = adam_scalars(t, lr, n_obs);
-    if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream, false);
-    else launch_fit<kParamJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream, false);
+    const AdamScalars one = mode == kParamJ ? adam_scalars(t, lr, n_obs) : AdamScalars{0.f, 1.f, 0.0};
+    SUCRE_CUDA(cudaMemcpyAsync((char*)workspace + kWsAdamTab, &one, sizeof one, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
+    else launch_fit<kParamJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
     return check_launch("fit_kernel");
 }
 
@@ -916,12 +931,20 @@ static int fit_loop(int mode, const sucre_store* store_host, int64_t n_obs, floa
         }
     }
     const int ctas = fit_grid();
-    for (int it = 0; it < num_iter; ++it) {
-        a.adam = adam_scalars(first_step + it, lr, n_obs);
-        a.history_row = history ? history + (size_t)it * kSums : nullptr;
-        a.epoch = first_epoch + (uint32_t)it;
-        if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, ctas, (cudaStream_t)stream, it > 0);
-        else launch_fit<kParamJ>(a, store_host->record_format, ctas, (cudaStream_t)stream, it > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the whole loop is ONE launch per kMaxLoopIters iterations: the per-iteration Adam scalars (python-float arithmetic of
+    // torch.optim.Adam, evaluated here in double) go to the workspace, the iteration flag is cleared, the grid stays resident
+    for (int done = 0; done < num_iter; done += kMaxLoopIters) {
+        const int n = min(kMaxLoopIters, num_iter - done);
+        AdamScalars tab[kMaxLoopIters];
+        for (int it = 0; it < n; ++it) tab[it] = adam_scalars(first_step + done + it, lr, n_obs);
+        SUCRE_CUDA(cudaMemcpyAsync((char*)workspace + kWsAdamTab, tab, sizeof(AdamScalars) * n, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+        SUCRE_CUDA(cudaMemsetAsync((char*)workspace + kWsTicket + 8, 0, 4, st));
+        a.num_iter = n;
+        a.history = history ? history + (size_t)done * kSums : nullptr;
+        a.epoch = first_epoch + (uint32_t)done;
+        if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, ctas, st);
+        else launch_fit<kParamJ>(a, store_host->record_format, ctas, st);
     }
     return check_launch(who);
 }
@@ -963,6 +986,6 @@ extern "C" int sucre_fit_write_J(const sucre_store* store_host, const float* par
     a.params = const_cast<float*>(params);
     a.J = const_cast<float*>(J_ref);
     a.J_out = J;
-    launch_fit<kWriteJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream, false);
+    launch_fit<kWriteJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
     return check_launch("fit_kernel<write J>");
 }

@@ -117,3 +117,74 @@ def test_fit_properties_at_full_size(full):
     assert np.max(np.abs(p - oref['params']) / np.abs(oref['params'])) < 1e-4
     Jg = res.J.cpu().numpy()
     assert np.array_equal(np.isnan(Jg), np.isnan(oref['J'])) and np.nanmax(np.abs(Jg - oref['J'])) < 1e-3
+
+
+def test_param_mode_at_full_size_vs_oracle(full):
+    """The default CLI mode (J is an Adam parameter, sucre.py:47-50) at BASELINE configs[1] size: 40 iterations of the
+    fused kernel (per-pixel Adam step of J inside the sweep) against the oracle on the same observations."""
+    ds, host, store = full
+    kept, _ = helpers.oracle_gather(host, TARGET, [s for s in range(V) if store.view_kept[s]])
+    J0 = oracle.initial_J(host[TARGET][1], host[TARGET][0])
+    oref = oracle.fit([o for _, o in kept], W, H, closed_form=False, num_iter=40, J0=J0)
+    state = engine.FitState.initial(ds.device, J0=torch.from_numpy(J0))
+    hist = engine.fit(store, state, 40).cpu().numpy()
+    p = state.params.cpu().numpy()
+    assert np.max(np.abs(p - oref['params']) / np.abs(oref['params'])) < 1e-4
+    assert np.max(np.abs(hist[:, :9] - oref['history']) / np.maximum(np.abs(oref['history']), 0.05)) < 1e-4
+    assert np.max(np.abs(hist[:, 9] - oref['cost']) / oref['cost']) < 1e-5
+    Jg = state.J.cpu().numpy()
+    assert np.array_equal(np.isnan(Jg), np.isnan(oref['J'])) and np.nanmax(np.abs(Jg - oref['J'])) < 1e-3
+
+
+def test_light_model_sums_at_full_size_against_float64():
+    """--light-model at BASELINE configs[1] size: the store with camera-frame points (u8 colour, 16-byte records), the
+    closed-form J with the light terms and the 25 reduced sums of one residual pass against an independent float64
+    evaluation of sucre.py:54-61, 66-82 over the exported records."""
+    from sucre_b200 import light
+    scene = SyntheticScene(V, W, H, seed=0)
+    ds, host = helpers.build_device_scene(scene, range(V), render_device='cuda')
+    store = engine.gather(ds, TARGET, list(range(V)), with_points=True)
+    assert store.has_points and store.record_bytes == 16 and store.n_obs > 3e7
+    dev = ds.device
+    B, beta, gamma = (torch.tensor(x, dtype=torch.float32).view(3, 1) for x in ((0.07, 0.2, 0.3), (0.4, 0.15, 0.1), (0.3, 0.2, 0.12)))
+    cam2light = torch.tensor([0.02, -0.03, 0.01, 0.05, -0.04, 0.02], dtype=torch.float32)
+    sigma = torch.tensor([[0.9, 0.1], [-0.05, 1.1]], dtype=torch.float32)
+    p24 = light.derive(B, beta, gamma, cam2light, sigma).to(dev)
+    J = engine.light_J(store, p24)
+    sums = torch.zeros(25, dtype=torch.float64, device=dev)
+    engine.light_sums(store, p24, J, sums)
+    # float64 evaluation
+    slot, pixel, _ = store.record_index()
+    flat = store.cells.reshape(-1, 4)
+    cP = flat[slot][:, :3].double()
+    I = torch.from_numpy(store.colours(slot)).to(dev).double()
+    q = p24.double()
+    Bq, bq, gq, R, t, S = q[0:3], q[3:6], q[6:9], q[9:18].view(3, 3), q[18:21], q[21:24]
+    lP = cP @ R.T + t
+    nl = lP.norm(dim=1)
+    x, y = lP[:, 0] / lP[:, 2], lP[:, 1] / lP[:, 2]
+    l = torch.exp(-0.5 * (S[0] * x * x + 2 * S[1] * x * y + S[2] * y * y))[:, None]
+    z = (cP.norm(dim=1) + nl)[:, None]
+    a, e = torch.exp(-bq * z), torch.exp(-gq * z)
+    absorb, back = l * a, l * Bq * (1 - e)
+    num = torch.zeros((W * H, 3), dtype=torch.float64, device=dev).index_add_(0, pixel, (I - back) * absorb)
+    den = torch.zeros((W * H, 3), dtype=torch.float64, device=dev).index_add_(0, pixel, absorb * absorb)
+    J64 = num / den
+    Jf = J.reshape(-1, 3)
+    assert torch.equal(torch.isnan(J64), torch.isnan(Jf)) and float((Jf.double() - J64).nan_to_num(0.0).abs().max()) < 1e-4
+    Jp = Jf.double()[pixel]                                  # the residual pass reads the fp32 J the kernel wrote
+    M = Jp * a + Bq * (1 - e)
+    r = I - l * M
+    g_l = (r * M).sum(1)
+    g_z = (r * l * (-bq * Jp * a + gq * Bq * e)).sum(1)
+    dlx, dly = -l[:, 0] * (S[0] * x + S[1] * y), -l[:, 0] * (S[1] * x + S[2] * y)
+    iz = 1.0 / lP[:, 2]
+    gP = torch.stack([g_l * dlx * iz + g_z * lP[:, 0] / nl, g_l * dly * iz + g_z * lP[:, 1] / nl,
+                      -g_l * (dlx * x + dly * y) * iz + g_z * lP[:, 2] / nl], dim=1)
+    gll = g_l * l[:, 0]
+    terms = [r * l * (1 - e), r * l * Jp * z * a, r * l * Bq * z * e, (r * r).sum(1, keepdim=True),
+             torch.stack([gll * x * x, gll * x * y, gll * y * y], dim=1),
+             (gP[:, :, None] * cP[:, None, :]).reshape(-1, 9), gP]
+    ref = torch.cat([t_.sum(0) for t_ in terms])
+    scale = torch.cat([t_.abs().sum(0) for t_ in terms])
+    assert float(((sums - ref).abs() / scale).max()) < 2e-5
