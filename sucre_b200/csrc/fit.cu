@@ -52,8 +52,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kTileCost = SUCRE_FIT_TILE_COST;
 
 // workspace layout (bytes)
-constexpr size_t kWsPartials = 0;                                                     // double[kMaxFitCtas][kSums]
-constexpr size_t kWsPartRow = kWsPartials + sizeof(double) * kSums * kMaxFitCtas;      // long long[kMaxFitCtas*kFitWarps + 1]
+constexpr size_t kWsPartials = 0;                                                     // double[2][kMaxFitCtas][kSums] (iteration parity)
+constexpr size_t kWsPartRow = kWsPartials + sizeof(double) * kSums * kMaxFitCtas * 2;  // long long[kMaxFitCtas*kFitWarps + 1]
 constexpr size_t kWsPartTile = kWsPartRow + sizeof(long long) * (kMaxFitCtas * kFitWarps + 2);  // int[kMaxFitCtas*kFitWarps + 1]
 constexpr size_t kWsTicket = kWsPartTile + sizeof(int) * (kMaxFitCtas * kFitWarps + 4);  // unsigned ticket, status, iteration flag; 16-aligned
 constexpr int kMaxLoopIters = 1024;   // Adam iterations per launch of the persistent loop (longer runs are split)
@@ -335,7 +335,7 @@ struct FitArgs {
     const long long* part_row;  // per global warp: first row of its stream; [n_warps] = rows of the store
     const int* part_tile;       // per global warp: first tile it owns (finalises); [n_warps] = n_tiles
     double* partials;      // gridDim.x rows of kSums
-    unsigned* ticket;      // ticket[0] = CTA counter, ticket[1] = status bits, ticket[2] = iterations completed by this launch
+    unsigned* ticket;      // ticket[0] = rows published since the launch started (cleared by the host before it), ticket[1] = status bits
     double* sums_out;      // if non-null the last CTA stores the reduced sums here
     float* history;        // if non-null: num_iter rows of {params after the step [9], cost}
     int do_step;           // apply Adam to the 9 scalars in the last CTA
@@ -375,9 +375,9 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 }
 
 // One launch = num_iter Adam iterations (MODE kWriteJ: one sweep).  The grid (one CTA per SM, all resident) stays on the
-// machine: after an iteration every CTA leaves its row of partial sums, the last one (ticket) reduces them, exchanges
-// them with the other GPUs if the target is sharded, takes the Adam step and raises the iteration flag; meanwhile the
-// other CTAs have already started the bulk copies of the next iteration's first rows and wait on the flag.
+// machine: after an iteration every CTA publishes its row of partial sums, waits until all rows are there, reduces them
+// itself (with the other GPUs' rows if the target is sharded) and takes the Adam step on its own copy of the state,
+// while the bulk copies of the next iteration's first rows are already in flight.
 template <int MODE, int REC, bool PRECISE>
 __global__ void __launch_bounds__(kFitThreads, 1)
 fit_kernel(const __grid_constant__ FitArgs A) {
@@ -395,7 +395,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     __shared__ double sm[kFitWarps][kSums];
     __shared__ double tot[kSums];
     __shared__ unsigned ll_half[SUCRE_MAX_PEERS][kLLWords];
-    __shared__ unsigned s_ticket;
+    __shared__ float s_state[27];   // this CTA's copy of the 9 parameters and their Adam moments (m[9], v[9])
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
     const unsigned char* ring = fit_smem + (size_t)warp * kRingBytes;
@@ -407,7 +407,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();  // the park barrier of a warp is waited on by its neighbour
+    if (threadIdx.x < 27) {
+        const bool moments = threadIdx.x >= 9 && A.moments != nullptr;
+        s_state[threadIdx.x] = threadIdx.x < 9 ? A.params[threadIdx.x] : (moments ? A.moments[threadIdx.x - 9] : 0.f);
+    }
+    __syncthreads();  // the park barrier of a warp is waited on by its neighbour; s_state is read by everybody
 
     const long long B0 = A.part_row[gw], B1 = A.part_row[gw + 1];
     const int T0 = A.part_tile[gw], T1 = A.part_tile[gw + 1];
@@ -467,18 +471,13 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     const int n_iter = MODE == kWriteJ ? 1 : A.num_iter;
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
-        if (it > 0) {  // the step of the previous iteration (parameters, moments, ticket) is complete once the flag says so
-            if (threadIdx.x == 0)
-                while (ld_acquire_gpu(A.ticket + 2) < (unsigned)it) __nanosleep(20);
-            __syncthreads();
-        }
         float Bs[3];   // B in the store's units
         typename PixelStats<MODE, PRECISE, REC>::Consts kc;
         {
             float kb[3], kg[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {   // written by another SM between iterations: read through L2
-                const float B = __ldcg(A.params + c), beta = __ldcg(A.params + 3 + c), gamma = __ldcg(A.params + 6 + c);
+            for (int c = 0; c < 3; ++c) {
+                const float B = s_state[c], beta = s_state[3 + c], gamma = s_state[6 + c];
                 Bs[c] = B * kScale;
                 kb[c] = PRECISE ? -beta : -beta * kLog2e;     // e^{-beta z} = 2^{kb z}
                 kg[c] = PRECISE ? -gamma : -gamma * kLog2e;
@@ -574,7 +573,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                 if (p < A.pixels) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        A.J_out[3 * p + c] = seen ? Jref[c] + __fdividef(st.get(c, 0), st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
+                        A.J_out[3 * p + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
                 }
             } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
                 float Jout[3];
@@ -584,7 +583,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                     const float S1 = st.get(c, 0), S3 = st.get(c, 2), S5 = st.get(c, 4), S7 = st.get(c, 6), S9 = st.get(c, 8);
                     float delta = 0.f, rh = S3, rza = S5, rzg = S7, rr = S9;
                     if (MODE == kClosedForm) {
-                        delta = __fdividef(S1, st.get(c, 1));
+                        delta = S1 / st.get(c, 1);
                         rh = fmaf(-delta, st.get(c, 3), S3);
                         rza = fmaf(-delta, st.get(c, 5), S5);
                         rzg = fmaf(-delta, st.get(c, 7), S7);
@@ -621,42 +620,48 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             if (lane == 0) sm[warp][i] = v;
         }
         __syncthreads();
+        double* const rows = A.partials + (size_t)(it & 1) * kMaxFitCtas * kSums;   // two parities: nobody is two iterations ahead
         if (threadIdx.x < kSums) {
             double v = 0.0;
             for (int wi = 0; wi < kFitWarps; ++wi) v += sm[wi][threadIdx.x];
             const double unit = threadIdx.x < 3 ? 1.0 / (double)kScale : 1.0 / ((double)kScale * (double)kScale);
-            A.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v * unit;
+            rows[(size_t)blockIdx.x * kSums + threadIdx.x] = v * unit;
             __threadfence();
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(A.ticket, 1u);
+        // Every CTA waits for all rows, reduces them ITSELF in the same fixed order and takes the same Adam step on its own
+        // copy of the parameters and moments: no CTA waits for another one to publish the result, and the next sweep
+        // starts straight from shared memory.  CTA 0 alone talks to the outside (history, sums, peers, final state).
+        if (threadIdx.x == 0) {
+            atomicAdd(A.ticket, 1u);
+            const unsigned want = (unsigned)(it + 1) * gridDim.x;
+            while (ld_acquire_gpu(A.ticket) < want) __nanosleep(20);
+        }
         __syncthreads();
-        if (s_ticket != gridDim.x - 1) continue;   // (uniform per CTA) on to the next iteration's flag
-
-        // last CTA: fixed-order reduction of the rows, then the Adam step of the 9 scalars
-        __threadfence();
         for (int col = warp; col < kSums; col += kFitWarps) {
             double v = 0.0;
-            for (int r = lane; r < (int)gridDim.x; r += 32) v += __ldcg(A.partials + (size_t)r * kSums + col);
+            for (int r = lane; r < (int)gridDim.x; r += 32) v += __ldcg(rows + (size_t)r * kSums + col);
             for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
             if (lane == 0) tot[col] = v;
         }
         __syncthreads();
         if (A.world > 1) {
-            // One-shot all-reduce over NVLink: every rank stores its 10 sums, as 20 tagged 8-byte words, into every
-            // peer's buffer (slot [epoch & 1][rank]) and polls the words of all ranks in its own buffer until they carry
-            // this epoch; the rows are then added in rank order — the same order on every rank, so all ranks take the
-            // identical Adam step without any host or NCCL round trip.  Two parities: a rank can be at most one
-            // iteration ahead of the slowest reader of its previous message.  The wait is bounded: after
-            // SUCRE_PEER_TIMEOUT_NS a rank gives up on a silent peer, raises status bit 0 and carries on.
+            // One-shot all-reduce over NVLink.  CTA 0 of every rank stores the rank's 10 sums, as 20 tagged 8-byte words,
+            // into every rank's buffer (slot [epoch & 1][rank], its own included); every CTA polls the words of all ranks
+            // in its own GPU's buffer until they carry this epoch and adds the rows in rank order — the same order
+            // everywhere, so all CTAs of all ranks take the identical Adam step without any host or NCCL round trip.
+            // Two parities: a rank can be at most one iteration ahead of the slowest reader of its previous message.
+            // The wait is bounded: after SUCRE_PEER_TIMEOUT_NS a silent peer raises status bit 0 and the loop carries on.
             const unsigned epoch = A.epoch + (unsigned)it;
             const unsigned par = epoch & 1u;
             if (threadIdx.x < A.world * kLLWords) {
                 const int p = threadIdx.x / kLLWords, j = threadIdx.x % kLLWords;
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[j >> 1]);
-                const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
-                PeerSlot* dst = reinterpret_cast<PeerSlot*>(A.peer[p]) + par * SUCRE_MAX_PEERS + A.rank;
-                st_relaxed_sys(&dst->w[j], ((unsigned long long)epoch << 32) | half);
+                if (blockIdx.x == 0) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[j >> 1]);
+                    const unsigned half = (j & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+                    PeerSlot* dst = reinterpret_cast<PeerSlot*>(A.peer[p]) + par * SUCRE_MAX_PEERS + A.rank;
+                    st_relaxed_sys(&dst->w[j], ((unsigned long long)epoch << 32) | half);
+                }
                 const PeerSlot* mine = reinterpret_cast<const PeerSlot*>(A.peer[A.rank]) + par * SUCRE_MAX_PEERS + p;
                 const unsigned long long t0 = globaltimer();
                 unsigned long long word;
@@ -677,26 +682,25 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             }
             __syncthreads();
         }
-        if (threadIdx.x < kSums && A.sums_out) A.sums_out[threadIdx.x] = tot[threadIdx.x];
-        float* history_row = A.history ? A.history + (size_t)it * kSums : nullptr;
+        const bool writer = blockIdx.x == 0;
+        float* history_row = (writer && A.history) ? A.history + (size_t)it * kSums : nullptr;
+        if (writer && threadIdx.x < kSums && A.sums_out) A.sums_out[threadIdx.x] = tot[threadIdx.x];
         if (A.do_step && threadIdx.x < 9) {
             const int i = threadIdx.x;
             // B: -2 r (1-g); beta: +2 r J z a; gamma: -2 r B z g   (all times 1 / 3N)
             const float g = (float)((i >= 3 && i < 6 ? ad.grad_scale : -ad.grad_scale) * tot[i]);
-            float m = A.moments[i], v = A.moments[9 + i];
-            const float pnew = adam_update(__ldcg(A.params + i), g, m, v, ad.neg_step_size, ad.bc2_sqrt);
-            A.moments[i] = m;
-            A.moments[9 + i] = v;
-            A.params[i] = pnew;
+            float m = s_state[9 + i], v = s_state[18 + i];
+            const float pnew = adam_update(s_state[i], g, m, v, ad.neg_step_size, ad.bc2_sqrt);
+            s_state[i] = pnew, s_state[9 + i] = m, s_state[18 + i] = v;
             if (history_row) history_row[i] = pnew;
+            if (writer && it + 1 == n_iter) {   // the state leaves the kernel once
+                A.params[i] = pnew;
+                A.moments[i] = m;
+                A.moments[9 + i] = v;
+            }
         }
         if (threadIdx.x == 9 && history_row) history_row[9] = (float)tot[9];
-        if (threadIdx.x == 0) *A.ticket = 0u;
-        __syncthreads();
-        if (threadIdx.x == 0) {   // everything above is visible to whoever sees the flag
-            __threadfence();
-            st_release_gpu(A.ticket + 2, (unsigned)(it + 1));
-        }
+        __syncthreads();   // s_state is read at the top of the next iteration
     }
 }
 
@@ -893,6 +897,7 @@ extern "C" int sucre_fit_sums(int mode, const sucre_store* store_host, const flo
     a.do_step = 0;
     const AdamScalars one = mode == kParamJ ? adam_scalars(t, lr, n_obs) : AdamScalars{0.f, 1.f, 0.0};
     SUCRE_CUDA(cudaMemcpyAsync((char*)workspace + kWsAdamTab, &one, sizeof one, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    SUCRE_CUDA(cudaMemsetAsync((char*)workspace + kWsTicket, 0, 4, (cudaStream_t)stream));
     if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
     else launch_fit<kParamJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
     return check_launch("fit_kernel");
@@ -939,7 +944,7 @@ static int fit_loop(int mode, const sucre_store* store_host, int64_t n_obs, floa
         AdamScalars tab[kMaxLoopIters];
         for (int it = 0; it < n; ++it) tab[it] = adam_scalars(first_step + done + it, lr, n_obs);
         SUCRE_CUDA(cudaMemcpyAsync((char*)workspace + kWsAdamTab, tab, sizeof(AdamScalars) * n, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
-        SUCRE_CUDA(cudaMemsetAsync((char*)workspace + kWsTicket + 8, 0, 4, st));
+        SUCRE_CUDA(cudaMemsetAsync((char*)workspace + kWsTicket, 0, 4, st));   // rows published: counted from zero per launch
         a.num_iter = n;
         a.history = history ? history + (size_t)done * kSums : nullptr;
         a.epoch = first_epoch + (uint32_t)done;
