@@ -115,6 +115,7 @@ static AdamScalars adam_scalars(int t, double lr, long long n_obs) {
 constexpr int kChunkBytes = SUCRE_FIT_CHUNK_BYTES;   // 16 rows of 8-byte records, 8 rows of 16-byte records
 constexpr int kStages = SUCRE_FIT_STAGES;
 constexpr int kRingBytes = kChunkBytes * kStages;    // 8 KB per warp; a power of two, so a row offset wraps with one AND
+constexpr int kChunkBytesWriteJ = 1024;              // the memory-bound write-J sweep: 8 slots of 1 KB
 constexpr size_t kParkBytes = (size_t)kFitWarps * kStats * 32 * sizeof(float);   // 54 KB: parked statistics of split tiles
 constexpr size_t kFitSmem = (size_t)kFitWarps * kRingBytes + kParkBytes;
 static_assert(kChunkBytes % 512 == 0, "a chunk must hold whole rows of both record sizes");
@@ -384,13 +385,17 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     typedef RecTraits<REC> RT;
     typedef typename RT::raw Raw;
     constexpr int kRowBytes = 32 * RT::kBytes;
-    constexpr int CR = kChunkBytes / kRowBytes;   // rows per chunk
+    // The Adam sweep is bound by arithmetic: few, large copies keep the ring bookkeeping small.  The write-J sweep does a
+    // quarter of the arithmetic and is bound by memory: it wants more copies in flight, so it cuts the same ring finer.
+    constexpr int kChunk = MODE == kWriteJ ? kChunkBytesWriteJ : kChunkBytes;
+    constexpr int kSlots = kRingBytes / kChunk;
+    constexpr int CR = kChunk / kRowBytes;        // rows per chunk
     constexpr float kScale = RT::kScale;
     constexpr float kInv = 1.0f / kScale;
     static_assert(CR >= 2, "a chunk must hold at least two rows");
 
     extern __shared__ __align__(128) unsigned char fit_smem[];
-    __shared__ __align__(8) unsigned long long bars[kFitWarps][kStages];
+    __shared__ __align__(8) unsigned long long bars[kFitWarps][kRingBytes / kChunkBytesWriteJ];
     __shared__ __align__(8) unsigned long long park_bar[kFitWarps];
     __shared__ double sm[kFitWarps][kSums];
     __shared__ double tot[kSums];
@@ -402,7 +407,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     float* const park_all = reinterpret_cast<float*>(fit_smem + (size_t)kFitWarps * kRingBytes);
     const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(&bars[warp][0]);
     if (lane == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(bar_s + 8 * s, 1);
+        for (int s = 0; s < kSlots; ++s) mbar_init(bar_s + 8 * s, 1);
         mbar_init(smem_u32(&park_bar[warp]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -436,18 +441,18 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         const int first = next_issue * CR;
         const uint32_t bytes = (uint32_t)min(CR, n_rows_w - first) * (uint32_t)kRowBytes;
         mbar_expect_tx(bar_s + 8 * issue_slot, bytes);
-        bulk_load(ring_s + issue_slot * (uint32_t)kChunkBytes, src + (size_t)first * kRowBytes, bytes, bar_s + 8 * issue_slot);
+        bulk_load(ring_s + issue_slot * (uint32_t)kChunk, src + (size_t)first * kRowBytes, bytes, bar_s + 8 * issue_slot);
     };
     auto advance_issue = [&]() {
         if (lane == 0) issue();
         ++next_issue;
-        issue_slot = issue_slot + 1 == kStages ? 0 : issue_slot + 1;
+        issue_slot = issue_slot + 1 == kSlots ? 0 : issue_slot + 1;
     };
     auto acquire = [&](int upto) {  // rows [0, upto) of the warp's stream have landed
         while (upto > avail) {
             mbar_wait(bar_s + 8 * wait_slot, wait_parity);
             avail += CR;
-            if (++wait_slot == kStages) {
+            if (++wait_slot == kSlots) {
                 wait_slot = 0;
                 wait_parity ^= 1u;
             }
@@ -463,8 +468,8 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     auto restart_stream = [&]() {  // the cells never change: the first copies of an iteration can start before its parameters exist
         __syncwarp();
         next_issue = 0, avail = 0, release_at = CR, pos = 0;
-        roff = issue_slot * kChunkBytes;
-        for (int c = 0; c < min(kStages, n_chunks); ++c) advance_issue();
+        roff = issue_slot * kChunk;
+        for (int c = 0; c < min(kSlots, n_chunks); ++c) advance_issue();
     };
     restart_stream();
 
