@@ -81,6 +81,8 @@ def parse_args(args: argparse.Namespace):
         targets = shard_targets(targets, rank, world, contiguous=True)
         if args.device == 'cuda':
             args.device = f'cuda:{local}'
+        if args.num_workers > 0:   # the ranks share the host's cores: keep the decode pools from oversubscribing them
+            args.num_workers = max(1, min(args.num_workers, (os.cpu_count() or 1) // world))
         print(f'Rank {rank}/{world}: {len(targets)} target(s) on {args.device}.')
 
     excluded = set(args.filter_images_path.read_text().splitlines()) if args.filter_images_path else set()
