@@ -392,7 +392,9 @@ def ours(args):
                 'whole_view_upload': {'value': pv_per_step / (ms_full / args.steps / 1e3), 'unit': UNIT,
                                       'h2d_bytes_per_step': res_f.h2d_bytes,
                                       's_per_restored_image': ms_full / args.steps / 1e3}},
-        'gpu_launches': args.steps * (api.LAUNCHES_FIXED + args.num_iter),
+        'gpu_launches': args.steps * api.LAUNCHES_PER_IMAGE,
+        'gpu_launches_note': 'per image: gather_match, count_views, tile_count, scan, gather_sample, partition, ONE resident fit_kernel '
+                             f'launch running all {args.num_iter} Adam iterations, fit_kernel<write J>',
         'roofline': {'bound': 'hbm', 'kernel': 'fit_kernel<closed form, 8-byte records>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic_per_launch(n_obs), 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': alg_bytes, 'launch_us': fit_launch_us,
@@ -508,7 +510,7 @@ def ours_pixel_sharded(ctx):
         'e2e': {'value': V * W * H / (ms_e2e / args.steps / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d.item()),
                 'd2h_bytes_per_step': H * W * 3 * 4 + 9 * 4 + args.num_iter * 10 * 4, 's_per_restored_image': ms_e2e / args.steps / 1e3,
                 'api': 'sucre_b200.api.restore_from_host_sharded (every rank uploads the rectangles its band can see; J + parameters read back on rank 0)'},
-        'gpu_launches': args.steps * world * (api.LAUNCHES_FIXED + args.num_iter),
+        'gpu_launches': args.steps * world * api.LAUNCHES_PER_BAND,
         'target_parallel': tp,
         'clocks': clocks,
     }
@@ -558,7 +560,7 @@ def ours_target_parallel(ctx):
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload(args),
             'parallelism': f'{world} ranks, one target image per rank, scene replicated, no data-path collective',
             'observations_rank0': res.n_obs, 's_per_restored_image': ms / args.steps / 1e3 / world,
-            'gpu_launches': args.steps * world * (api.LAUNCHES_FIXED + args.num_iter), 'clocks': clocks}
+            'gpu_launches': args.steps * world * api.LAUNCHES_PER_IMAGE, 'clocks': clocks}
 
 
 if __name__ == '__main__':

@@ -289,8 +289,9 @@ tile_count_kernel(const uint32_t* __restrict__ masks, const long long* __restric
     }
 }
 
-// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA: rounds of 1024 coalesced
-// elements, warp-shuffle scans, running carries
+// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA: rounds of 1024 x kScanPer
+// elements (each thread owns kScanPer consecutive ones), warp-shuffle scans of the thread totals, running carries
+constexpr int kScanPer = 4;
 __global__ void __launch_bounds__(1024)
 scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __restrict__ c, int n,
             long long* __restrict__ totals) {
@@ -298,13 +299,19 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     long long carry[3] = {0, 0, 0};
     long long* arr[3] = {a, b, c};
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + t;
-        long long v[3], incl[3];
+    for (int base = 0; base < n; base += 1024 * kScanPer) {
+        const int i0 = base + t * kScanPer;
+        long long v[3][kScanPer], incl[3], mine[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            v[k] = i < n ? arr[k][i] : 0;
-            incl[k] = v[k];
+            long long run = 0;
+#pragma unroll
+            for (int j = 0; j < kScanPer; ++j) {
+                v[k][j] = i0 + j < n ? arr[k][i0 + j] : 0;
+                run += v[k][j];
+            }
+            mine[k] = run;
+            incl[k] = run;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long up = __shfl_up_sync(kFull, incl[k], o);
@@ -325,8 +332,12 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const long long before = carry[k] + (warp ? wsum[k][warp - 1] : 0);
-            if (i < n) arr[k][i] = before + incl[k] - v[k];
+            long long before = carry[k] + (warp ? wsum[k][warp - 1] : 0) + incl[k] - mine[k];
+#pragma unroll
+            for (int j = 0; j < kScanPer; ++j) {
+                if (i0 + j < n) arr[k][i0 + j] = before;
+                before += v[k][j];
+            }
             carry[k] += wsum[k][31];
         }
         __syncthreads();
@@ -341,23 +352,6 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
     }
 }
 
-// What a probe needs of a source view, staged in shared memory per 32-view chunk of the sample kernel: 28 words,
-// 16-byte aligned, read with seven 128-bit broadcast loads instead of ~30 scalar loads from the global view table.
-// K / Kinv are kept in their PINHOLE-sparse form (entries 0, 2, 4, 5); a view whose matrices are not sparse
-// (SUCRE_VIEW_*_SPARSE clear) is probed from the global table instead.
-struct alignas(16) ViewLite {
-    float Ri[9], ti[3];
-    float K[4], Kinv[4];
-    int width, height, fmt, flags;
-    unsigned long long depth, rgb;
-};
-static_assert(sizeof(ViewLite) == 112, "ViewLite layout");
-constexpr int kLiteWords = sizeof(ViewLite) / 4;
-// word of sucre_view behind every word of ViewLite (sucre_view: K 0, Kinv 9, R 18, t 27, Ri 30, ti 39, width 42,
-// height 43, depth 44-45, rgb 46-47, rgb_format 48, flags 49)
-__constant__ int kLiteMap[kLiteWords] = {30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 0, 2, 4, 5, 9, 11, 13, 14,
-                                         42, 43, 48, 49, 44, 45, 46, 47};
-
 // One (target pixel, source view) observation in two steps, so that two of them can overlap their memory
 // latency: issue() projects the pixel into the view and starts the gathers at the source pixel it lands on,
 // finish() turns the fetched depth / colour into the record.
@@ -369,7 +363,30 @@ struct Probe {
     float raw0, raw1, raw2;     // SUCRE_RGB_F32
     float Kinv[9];
 
-    __device__ __forceinline__ void gathers(const uint16_t* depth, const void* rgb, int Ws) {
+    __device__ __forceinline__ void issue(const sucre_view* S, float w0, float w1, float w2) {  // S: warp-uniform => broadcast loads
+        float Ri[9], ti[3], K[9];
+        const int flags = __ldg(&S->flags);
+        sparse = (flags & (SUCRE_VIEW_K_SPARSE | SUCRE_VIEW_KINV_SPARSE)) == (SUCRE_VIEW_K_SPARSE | SUCRE_VIEW_KINV_SPARSE);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ri[i] = __ldg(&S->Ri[i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ti[i] = __ldg(&S->ti[i]);
+        const int Ws = __ldg(&S->width), Hs = __ldg(&S->height);
+        if (sparse) {
+            K[0] = __ldg(&S->K[0]), K[2] = __ldg(&S->K[2]), K[4] = __ldg(&S->K[4]), K[5] = __ldg(&S->K[5]);
+            Kinv[0] = __ldg(&S->Kinv[0]), Kinv[2] = __ldg(&S->Kinv[2]), Kinv[4] = __ldg(&S->Kinv[4]), Kinv[5] = __ldg(&S->Kinv[5]);
+            project<true>(Ri, ti, K, Ws, Hs, w0, w1, w2, u2, v2);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                K[i] = __ldg(&S->K[i]);
+                Kinv[i] = __ldg(&S->Kinv[i]);
+            }
+            project<false>(Ri, ti, K, Ws, Hs, w0, w1, w2, u2, v2);
+        }
+        const uint16_t* depth = reinterpret_cast<const uint16_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->depth)));
+        const void* rgb = reinterpret_cast<const void*>(__ldg(reinterpret_cast<const unsigned long long*>(&S->rgb)));
+        fmt = __ldg(&S->rgb_format);
         const size_t q = (size_t)v2 * Ws + u2;
         d16 = __ldg(depth + q);                                                // sfm.py:137
         if (fmt == SUCRE_RGB_F32) {  // resampled on the host in float (--image-scale), loader.py:158-163
@@ -379,27 +396,6 @@ struct Probe {
             const uint8_t* px = reinterpret_cast<const uint8_t*>(rgb) + 3 * q;
             rgb8 = (uint32_t)__ldg(px + 0) | ((uint32_t)__ldg(px + 1) << 8) | ((uint32_t)__ldg(px + 2) << 16);
         }
-    }
-
-    // L: the view's staged constants (shared memory, warp-uniform address => broadcast); S: the same view in the global table
-    __device__ __forceinline__ void issue(const ViewLite& L, const sucre_view* S, float w0, float w1, float w2) {
-        fmt = L.fmt;
-        sparse = (L.flags & (SUCRE_VIEW_K_SPARSE | SUCRE_VIEW_KINV_SPARSE)) == (SUCRE_VIEW_K_SPARSE | SUCRE_VIEW_KINV_SPARSE);
-        if (sparse) {
-            float K[9];
-            K[0] = L.K[0], K[2] = L.K[1], K[4] = L.K[2], K[5] = L.K[3];
-            Kinv[0] = L.Kinv[0], Kinv[2] = L.Kinv[1], Kinv[4] = L.Kinv[2], Kinv[5] = L.Kinv[3];
-            project<true>(L.Ri, L.ti, K, L.width, L.height, w0, w1, w2, u2, v2);
-        } else {
-            float K[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                K[i] = __ldg(&S->K[i]);
-                Kinv[i] = __ldg(&S->Kinv[i]);
-            }
-            project<false>(L.Ri, L.ti, K, L.width, L.height, w0, w1, w2, u2, v2);
-        }
-        gathers(reinterpret_cast<const uint16_t*>(L.depth), reinterpret_cast<const void*>(L.rgb), L.width);
     }
 
     // writes the record at slot `at` of a store of the given format (see include/sucre_b200.h)
@@ -448,45 +444,35 @@ __device__ __forceinline__ void write_sentinel(void* cells, long long at, int fo
 
 // ---- sample ----------------------------------------------------------------------------------------------
 // One warp per tile walks the tile's non-empty kept blocks in pairing-list order (lane <-> view over 32-view chunks
-// of the mask row; the constants of the chunk's views are staged in shared memory by the whole CTA); every matched
-// (pixel, view) is re-projected, its source depth + colour fetched, and the record stored at row (lane's running
-// count), column lane — lanes of a warp write the same or neighbouring rows, so the stores coalesce.  The block list
-// (lane mask + view) is written alongside for export / parity checks.
+// of the mask row); every matched (pixel, view) is re-projected, its source depth + colour fetched, and the record
+// stored at row (lane's running count), column lane — lanes of a warp write the same or neighbouring rows, so the
+// stores coalesce.  The block list (lane mask + view) is written alongside for export / parity checks.
 __global__ void __launch_bounds__(256)
 gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                      const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
                      const long long* __restrict__ row_off, const long long* __restrict__ blk_off, const sucre_band band,
                      int format, void* __restrict__ cells, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
                      uint32_t* __restrict__ cell_src) {
-    __shared__ ViewLite lite[32];   // the current 32-view chunk, shared by the CTA's 8 tiles
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * 8 + warp;
-    const bool live = tile < band.n_tiles;   // (warp-uniform) warps past the band still help staging and reach the barriers
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= band.n_tiles) return;
     const uint32_t lt = (1u << lane) - 1u;
     const int P = T.width * T.height;
-    const int p = live ? band_tile(band, tile) * kTile + lane : 0;
+    const int p = band_tile(band, tile) * kTile + lane;
     float w0, w1, w2;
     {
-        const float d1 = __fdiv_rn((float)(live && p < P ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
+        const float d1 = __fdiv_rn((float)(p < P ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
         const int v1 = p / T.width, u1 = p - v1 * T.width;
         float c0, c1, c2;
         unproject<false>(T.Kinv, u1, v1, d1, c0, c1, c2);
         rigid(T.R, T.t, c0, c1, c2, w0, w1, w2);
     }
-    const long long row0 = live ? row_off[tile] : 0;
-    const int n_rows = live ? (int)(row_off[tile + 1] - row0) : 0;
-    long long blk_at = live ? blk_off[tile] : 0;
+    const long long row0 = row_off[tile];
+    const int n_rows = (int)(row_off[tile + 1] - row0);
+    long long blk_at = blk_off[tile];
     long long at = row0 * kTile + lane;  // slot of this lane's next record
     int mine = 0;
     for (int base = 0; base < n_views; base += 32) {
-        __syncthreads();   // everybody is done with the previous chunk's constants
-        for (int i = threadIdx.x; i < 32 * kLiteWords; i += blockDim.x) {
-            const int v = i / kLiteWords, wd = i % kLiteWords;
-            if (base + v < n_views)
-                reinterpret_cast<uint32_t*>(lite)[i] = __ldg(reinterpret_cast<const uint32_t*>(views + base + v) + kLiteMap[wd]);
-        }
-        __syncthreads();
-        if (!live) continue;
         const int view = base + lane;
         uint32_t m = 0;
         if (view < n_views && view_kept[view]) m = __ldg(masks + (size_t)tile * n_views + view);
@@ -507,8 +493,8 @@ gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __r
             const uint32_t bm0 = __shfl_sync(kFull, m, j0), bm1 = __shfl_sync(kFull, m, j1);
             const bool a0 = (bm0 >> lane) & 1u, a1 = two && ((bm1 >> lane) & 1u);
             Probe p0, p1;
-            if (a0) p0.issue(lite[j0], views + base + j0, w0, w1, w2);
-            if (a1) p1.issue(lite[j1], views + base + j1, w0, w1, w2);
+            if (a0) p0.issue(views + base + j0, w0, w1, w2);
+            if (a1) p1.issue(views + base + j1, w0, w1, w2);
             if (a0) {
                 p0.finish(cells, at, format, cell_src);
                 at += kTile;
