@@ -65,6 +65,10 @@ class Band(C.Structure):
     def as_tuple(self) -> tuple:
         return (self.first_tile, self.n_tiles, self.chunk_tiles, self.stride_tiles)
 
+    def tile(self, k: int) -> int:
+        """Global tile index of local tile k."""
+        return self.first_tile + (k // self.chunk_tiles) * self.stride_tiles + k % self.chunk_tiles
+
     def tiles(self) -> np.ndarray:
         """Global tile index of every local tile."""
         k = np.arange(self.n_tiles, dtype=np.int64)

@@ -321,7 +321,7 @@ class ObservationStore:
         """Target pixels covered by this store, in local order; only the image's last tile can be partial, and it is
         the band's last local tile if the band owns it."""
         P = self.width * self.height
-        last_global = int(self.band.tiles()[-1]) if self.band.n_tiles else 0
+        last_global = self.band.tile(self.band.n_tiles - 1) if self.band.n_tiles else 0
         return self.band.n_tiles * TILE - max(0, (last_global + 1) * TILE - P)
 
     def global_pixels(self) -> torch.Tensor:
