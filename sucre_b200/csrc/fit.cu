@@ -46,9 +46,6 @@ constexpr int kMaxFitCtas = 1024;
 constexpr int kSums = 10;
 constexpr int kStats = 27;     // per-pixel statistics: 9 per channel
 constexpr float kLog2e = 1.4426950408889634f;
-#ifndef SUCRE_FIT_MASK_ALU
-#define SUCRE_FIT_MASK_ALU 0
-#endif
 #ifndef SUCRE_FIT_TILE_COST
 #define SUCRE_FIT_TILE_COST 3  // per-tile overhead (J load/store, finalisation, double accumulation) in row-equivalents
 #endif
@@ -280,25 +277,14 @@ struct PixelStats {
     __device__ __forceinline__ void add(const Obs r0, const Obs r1, const Consts& k, const u64 nJ_rg, const float nJ_b) {
         const u64 one = pk(1.0f, 1.0f), neg = pk(-1.0f, -1.0f);
         const u64 bias = pk(RecTraits<REC>::kBias, RecTraits<REC>::kBias);
-#if SUCRE_FIT_MASK_ALU   // tuning variant: mask a with an AND (ALU pipe) instead of a multiplication by w (FMA pipe)
-        const unsigned m0 = __float_as_uint(r0.z) != 0u ? 0xffffffffu : 0u, m1 = __float_as_uint(r1.z) != 0u ? 0xffffffffu : 0u;
-        auto mask2 = [](u64 v, unsigned mlo, unsigned mhi) {
-            return pk(__uint_as_float(__float_as_uint(lo(v)) & mlo), __uint_as_float(__float_as_uint(hi(v)) & mhi));
-        };
-#else
         const float w0 = r0.z != 0.0f ? 1.0f : 0.0f, w1 = r1.z != 0.0f ? 1.0f : 0.0f;
-#endif
         // red + green, row by row
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const Obs& r = i == 0 ? r0 : r1;
             const u64 zz = pk(r.z, r.z);
-#if SUCRE_FIT_MASK_ALU
-            const u64 a = mask2(exp2_pair(mul2(k.kb_rg, zz)), i == 0 ? m0 : m1, i == 0 ? m0 : m1);
-#else
             const float w = i == 0 ? w0 : w1;
             const u64 a = mul2(exp2_pair(mul2(k.kb_rg, zz)), pk(w, w));
-#endif
             const u64 g = exp2_pair(mul2(k.kg_rg, zz));
             const u64 h = fma2(g, neg, one);                               // 1 - g
             u64 x = pk(r.x[0], r.x[1]);
@@ -310,11 +296,7 @@ struct PixelStats {
         // blue, both rows at once
         {
             const u64 zz = pk(r0.z, r1.z);
-#if SUCRE_FIT_MASK_ALU
-            const u64 a = mask2(exp2_pair(mul2(zz, pk(k.kb_b, k.kb_b))), m0, m1);
-#else
             const u64 a = mul2(exp2_pair(mul2(zz, pk(k.kb_b, k.kb_b))), pk(w0, w1));
-#endif
             const u64 g = exp2_pair(mul2(zz, pk(k.kg_b, k.kg_b)));
             const u64 h = fma2(g, neg, one);
             u64 x = pk(r0.x[2], r1.x[2]);

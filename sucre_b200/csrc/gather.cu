@@ -289,9 +289,8 @@ tile_count_kernel(const uint32_t* __restrict__ masks, const long long* __restric
     }
 }
 
-// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA: rounds of 1024 x kScanPer
-// elements (each thread owns kScanPer consecutive ones), warp-shuffle scans of the thread totals, running carries
-constexpr int kScanPer = 4;
+// in-place exclusive scan of three count arrays (n entries -> n+1 offsets), one CTA: rounds of 1024 coalesced
+// elements, warp-shuffle scans, running carries
 __global__ void __launch_bounds__(1024)
 scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __restrict__ c, int n,
             long long* __restrict__ totals) {
@@ -299,19 +298,13 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     long long carry[3] = {0, 0, 0};
     long long* arr[3] = {a, b, c};
-    for (int base = 0; base < n; base += 1024 * kScanPer) {
-        const int i0 = base + t * kScanPer;
-        long long v[3][kScanPer], incl[3], mine[3];
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + t;
+        long long v[3], incl[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            long long run = 0;
-#pragma unroll
-            for (int j = 0; j < kScanPer; ++j) {
-                v[k][j] = i0 + j < n ? arr[k][i0 + j] : 0;
-                run += v[k][j];
-            }
-            mine[k] = run;
-            incl[k] = run;
+            v[k] = i < n ? arr[k][i] : 0;
+            incl[k] = v[k];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long up = __shfl_up_sync(kFull, incl[k], o);
@@ -332,12 +325,8 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            long long before = carry[k] + (warp ? wsum[k][warp - 1] : 0) + incl[k] - mine[k];
-#pragma unroll
-            for (int j = 0; j < kScanPer; ++j) {
-                if (i0 + j < n) arr[k][i0 + j] = before;
-                before += v[k][j];
-            }
+            const long long before = carry[k] + (warp ? wsum[k][warp - 1] : 0);
+            if (i < n) arr[k][i] = before + incl[k] - v[k];
             carry[k] += wsum[k][31];
         }
         __syncthreads();

@@ -568,6 +568,13 @@ class FitState:
     def mode(self) -> int:
         return _lib.FIT_PARAM_J if self.J_moments is not None else _lib.FIT_CLOSED_FORM
 
+    def reset_optimizer(self):
+        """A fresh Adam (what a new torch.optim.Adam starts from): step 0, zero moments; parameters and J are kept."""
+        self.step = 0
+        self.moments.zero_()
+        if self.J_moments is not None:
+            self.J_moments.zero_()
+
     def ensure_J(self, store: 'ObservationStore'):
         if self.J is None:
             self.J = torch.zeros(store.J_shape, dtype=torch.float32, device=store.cells.device)

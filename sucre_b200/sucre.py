@@ -282,6 +282,9 @@ def adam(
     store = matches_data.store
     if sucre.light_model:
         return _adam_light(sucre, matches_data, lr, num_iter, save_dir, save_interval)
+    # the reference builds a fresh torch.optim.Adam on every call (sucre.py:136): step counter and moments start at zero,
+    # the parameters (and J) carry over
+    sucre.state.reset_optimizer()
     # iterations after whose step the reference saves intermediate plots (sucre.py:153-154): it % save_interval == 0
     plot_its = list(range(0, num_iter, save_interval)) if save_dir is not None and save_interval else []
     histories = []

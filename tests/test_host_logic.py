@@ -79,7 +79,13 @@ def test_loaders_match_the_reference_formulas(scene_dir):
     with pytest.raises(FileNotFoundError):
         loader.load_depth_u16(dirs['depth'] / 'nope.png', 64, 48)
     with pytest.raises(ValueError):
-        loader.load_depth_u16(p_rgb, 64, 48)                                # not a 16-bit single-channel map
+        loader.load_depth_u16(p_rgb, 64, 48)                                # not a single-channel map
+    import cv2
+    d8 = (depth_u16.numpy() >> 8).astype('uint8')                            # an 8-bit depth map: the reference divides it by 1000 all the same
+    cv2.imwrite(str(root / 'depth8.png'), d8)
+    assert torch.equal(loader.load_depth_u16(root / 'depth8.png', 64, 48), torch.from_numpy(d8.astype('uint16')))
+    assert torch.equal((loader.load_depth_u16(root / 'depth8.png', 64, 48).to(torch.int32).to(torch.float64) / 1000).to(torch.float32),
+                       loader.load_depth_map(root / 'depth8.png', 64, 48))
 
 
 def test_cli_flags_and_defaults_are_the_reference_ones():

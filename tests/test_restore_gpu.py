@@ -183,3 +183,27 @@ def test_large_survey_decodes_only_overlapping_views(tmp_path):
     ref = engine.gather(full, target.id, [im.id for im in ordered], keep_src=True, cull_views=False)
     assert np.array_equal(ref.view_count, store.view_count) and np.array_equal(ref.view_kept, store.view_kept)
     assert torch.equal(ref.cells, store.cells) and torch.equal(ref.blk_view, store.blk_view)
+
+
+def test_scene_residency_budget_evicts_least_recently_used_views(tmp_path):
+    """The decoded views of a survey stay under COLMAPModel.scene_budget_bytes per GPU: the least recently used views a
+    call does not ask for are dropped and decoded again when a later target needs them; results do not change."""
+    from sucre_b200 import engine
+    from sucre_b200.synth import SyntheticScene
+    scene = SyntheticScene(12, 64, 48, seed=3)
+    dirs = scene.write(tmp_path)
+    model = sfm.COLMAPModel(dirs['model'], dirs['images'], dirs['depth'])
+    ims = list(model.images.values())
+    per_view = 5 * 64 * 48
+    model.scene_budget_bytes = 6 * per_view
+    sc = model.scene('cuda', ims[:5])
+    assert len(sc.geom) == 5
+    sc = model.scene('cuda', ims[3:9])                       # 6 wanted, 2 already there: the other 3 must go
+    assert len(sc.geom) == 6 and set(sc.geom) == {im.id for im in ims[3:9]}
+    sc = model.scene('cuda', ims[:2])                        # budget allows 6: the two oldest of the residents leave
+    assert len(sc.geom) == 6 and {ims[0].id, ims[1].id} <= set(sc.geom)
+    a = engine.gather(sc, ims[0].id, [ims[0].id, ims[1].id])
+    model.scene_budget_bytes = None
+    model.drop_scene()
+    b = engine.gather(model.scene('cuda', ims), ims[0].id, [ims[0].id, ims[1].id])
+    assert a.n_obs == b.n_obs and torch.equal(a.cells, b.cells)
