@@ -66,6 +66,8 @@ def main():
     ap.add_argument('--num-iter', type=int, default=200)
     ap.add_argument('--out', type=Path, default=None)
     ap.add_argument('--keep', type=Path, default=None, help='write the survey here and keep it (default: a temporary directory)')
+    ap.add_argument('--profile', type=Path, default=None,
+                    help='also run the 1-GPU job under cProfile and write the 40 most expensive calls (cumulative) here')
     args = ap.parse_args()
     V, W, H = args.views, args.width, args.height
     tmp = Path(tempfile.mkdtemp(prefix='sucre_survey_')) if args.keep is None else args.keep
@@ -108,6 +110,21 @@ def main():
                 args.out.parent.mkdir(parents=True, exist_ok=True)
                 with open(args.out, 'a') as f:
                     f.write(json.dumps(line) + '\n')
+        if args.profile is not None:
+            out_dir, stats = tmp / 'out_profile', tmp / 'cli.prof'
+            cli = ['-m', 'sucre_b200.sucre', '--image-dir', str(dirs['images']), '--depth-dir', str(dirs['depth']),
+                   '--model-dir', str(dirs['model']), '--output-dir', str(out_dir), '--use-closed-form',
+                   '--num-iter', str(args.num_iter), '--num-workers', '8', *sel]
+            t0 = time.time()
+            subprocess.run([sys.executable, '-m', 'cProfile', '-o', str(stats)] + cli, cwd=ROOT, env=dict(os.environ, PYTHONPATH=str(ROOT)),
+                           capture_output=True, text=True)
+            wall = time.time() - t0
+            import io
+            import pstats
+            buf = io.StringIO()
+            pstats.Stats(str(stats), stream=buf).sort_stats('cumulative').print_stats(40)
+            args.profile.parent.mkdir(parents=True, exist_ok=True)
+            args.profile.write_text(f'wall {wall:.2f} s under cProfile (main thread only)\n' + buf.getvalue())
     finally:
         if args.keep is None:
             shutil.rmtree(tmp, ignore_errors=True)
