@@ -58,16 +58,22 @@ __device__ __forceinline__ LightGeom light_geom(const LightParams& q, const floa
 
 // Walks the observations of this lane's pixel in one tile of a SUCRE_REC_P_* store (ELL rows: the lane's column, top
 // to bottom, until the first sentinel): f({cP_x, cP_y, cP_z, ||cP||}, {I_r, I_g, I_b, 0}).  Returns their number.
+// The loads run two rows ahead of the arithmetic (a column's records are 512 / 1024 bytes apart, a warp's row is one
+// coalesced line set), so the few warps a register-heavy caller leaves per SM still keep HBM busy.
 template <class F>
 __device__ __forceinline__ int walk_tile(const sucre_store& S, int tile, int lane, F&& f) {
     const long long r0 = S.row_off[tile];
     const int n = (int)(S.row_off[tile + 1] - r0);
     const float4* cells = reinterpret_cast<const float4*>(S.cells);
+    const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
     int seen = 0;
     if (S.record_format == SUCRE_REC_P_U8) {
         const float4* col = cells + r0 * kTile + lane;
+        float4 q0 = n > 0 ? __ldg(col) : none, q1 = n > 1 ? __ldg(col + kTile) : none;
         for (int j = 0; j < n; ++j) {
-            const float4 q = __ldg(col + (size_t)j * kTile);
+            const float4 q = q0;
+            q0 = q1;
+            q1 = j + 2 < n ? __ldg(col + (size_t)(j + 2) * kTile) : none;
             if (q.z == 0.0f) break;  // sentinel: a real observation has cP_z = source depth > 0
             // sucre.py:53 cP.norm(dim=0): sequential squares, no fma; loader.py:157: u8 / 255
             const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)));
@@ -79,10 +85,12 @@ __device__ __forceinline__ int walk_tile(const sucre_store& S, int tile, int lan
         }
     } else {
         const float4* col = cells + 2 * (r0 * kTile + lane);
+        float4 c0 = n > 0 ? __ldg(col) : none, i0 = n > 0 ? __ldg(col + 1) : none;
         for (int j = 0; j < n; ++j) {
-            const float4 c = __ldg(col + (size_t)j * 2 * kTile);
+            const float4 c = c0, I4 = i0;
+            if (j + 1 < n) c0 = __ldg(col + (size_t)(j + 1) * 2 * kTile), i0 = __ldg(col + (size_t)(j + 1) * 2 * kTile + 1);
             if (c.z == 0.0f) break;
-            f(c, __ldg(col + (size_t)j * 2 * kTile + 1));
+            f(c, I4);
             ++seen;
         }
     }
@@ -124,15 +132,17 @@ __device__ __forceinline__ float adam_update1(float p, float g, float& m, float&
 
 // residual pass: J given per pixel -> 25 sums (see include/sucre_b200.h); PARAM_J: Adam step of J fused
 template <bool PARAM_J>
-__global__ void __launch_bounds__(kLightThreads)
+__global__ void __launch_bounds__(kLightThreads, 2)
 light_sums_kernel(const __grid_constant__ sucre_store S, const float* __restrict__ params, float* __restrict__ J,
                   float* __restrict__ J_moments, float grad_scale, float neg_step_size, float bc2_sqrt,
                   double* __restrict__ partials) {
     const LightParams q = load_light(params);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double acc[kLightSums];
+    // A thread's running sums stay fp32 over the handful of tiles it owns (a few hundred terms, the same rounding
+    // scale as one tile's) and become double for everything summed across threads.
+    float s[kLightSums];
 #pragma unroll
-    for (int i = 0; i < kLightSums; ++i) acc[i] = 0.0;
+    for (int i = 0; i < kLightSums; ++i) s[i] = 0.f;
 
     for (int tile = blockIdx.x * kLightWarps + warp; tile < S.n_tiles; tile += gridDim.x * kLightWarps) {
         const long long p = (long long)tile * kTile + lane;
@@ -140,9 +150,6 @@ light_sums_kernel(const __grid_constant__ sucre_store S, const float* __restrict
         if (p < S.pixels) {
             Jp[0] = J[3 * p], Jp[1] = J[3 * p + 1], Jp[2] = J[3 * p + 2];
         }
-        float s[kLightSums];
-#pragma unroll
-        for (int i = 0; i < kLightSums; ++i) s[i] = 0.f;
         float gJ[3] = {0.f, 0.f, 0.f};
         const int seen = walk_tile(S, tile, lane, [&](const float4 c, const float4 I4) {
             const LightGeom g = light_geom(q, c);
@@ -168,9 +175,9 @@ light_sums_kernel(const __grid_constant__ sucre_store S, const float* __restrict
             s[12] += gll * g.y * g.y;
             // g_lP = g_l dl/dlP + g_z lP/||lP||;  dl/dlp = -l Sigma^-1 lp, lp = lP.xy / lP.z
             const float dlx = -g.l * (q.S[0] * g.x + q.S[1] * g.y), dly = -g.l * (q.S[1] * g.x + q.S[2] * g.y);
-            const float iz = 1.0f / g.lP[2];
-            const float gP[3] = {g_l * dlx * iz + g_z * g.lP[0] / g.nl, g_l * dly * iz + g_z * g.lP[1] / g.nl,
-                                 -g_l * (dlx * g.x + dly * g.y) * iz + g_z * g.lP[2] / g.nl};
+            const float iz = 1.0f / g.lP[2], zn = g_z / g.nl;
+            const float gP[3] = {g_l * dlx * iz + zn * g.lP[0], g_l * dly * iz + zn * g.lP[1],
+                                 -g_l * (dlx * g.x + dly * g.y) * iz + zn * g.lP[2]};
             const float cP[3] = {c.x, c.y, c.z};
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -180,8 +187,6 @@ light_sums_kernel(const __grid_constant__ sucre_store S, const float* __restrict
             }
         });
         if (seen) {
-#pragma unroll
-            for (int i = 0; i < kLightSums; ++i) acc[i] += (double)s[i];
             if (PARAM_J) {
                 float* mv = J_moments + 6 * p;
 #pragma unroll
@@ -196,7 +201,7 @@ light_sums_kernel(const __grid_constant__ sucre_store S, const float* __restrict
     }
     __shared__ double sm[kLightWarps][kLightSums];
     for (int i = 0; i < kLightSums; ++i) {
-        double v = acc[i];
+        double v = (double)s[i];
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
         if (lane == 0) sm[warp][i] = v;
     }
@@ -248,7 +253,8 @@ extern "C" int sucre_light_sums(int mode, const sucre_store* store_host, const f
     SUCRE_REQUIRE(mode == SUCRE_FIT_CLOSED_FORM || (mode == SUCRE_FIT_PARAM_J && J_moments && n_obs > 0 && t >= 1),
                   "sucre_light_sums: bad mode/arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = min(kLightMaxCtas, (store_host->n_tiles + kLightWarps - 1) / kLightWarps);
+    // two CTAs are resident per SM (launch bounds); two waves of them, each warp striding over the tiles
+    const int ctas = min(min(kLightMaxCtas, 4 * num_sms()), (store_host->n_tiles + kLightWarps - 1) / kLightWarps);
     double* partials = (double*)workspace;
     if (mode == SUCRE_FIT_PARAM_J) {
         const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);

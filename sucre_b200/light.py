@@ -37,8 +37,14 @@ def fit(store: engine.ObservationStore, params: dict, J: torch.Tensor | None, J_
     sc = 2.0 / (3.0 * store.n_obs)
     names = ('B', 'beta', 'gamma', 'cam2light', 'sigma')
     for it in range(num_iter):
+        # R, t, Sigma^-1 are evaluated once per iteration, with the graph the chain rule below walks back through
+        xi = params['cam2light'].detach().clone().requires_grad_(True)
+        sg = params['sigma'].detach().clone().requires_grad_(True)
+        R, t = se3.exp(xi)
+        Sinv = (sg.T @ sg).inverse()
         with torch.no_grad():
-            p24 = derive(*(params[k] for k in names)).to(dev)
+            p24 = torch.cat([params['B'].flatten(), params['beta'].flatten(), params['gamma'].flatten(), R.flatten(), t.flatten(),
+                             torch.stack([Sinv[0, 0], Sinv[0, 1], Sinv[1, 1]])]).to(torch.float32).to(dev)
         if closed_form:
             J = engine.light_J(store, p24)
         engine.light_sums(store, p24, J, sums, J_moments, n_obs=store.n_obs, step=first_step + it, lr=lr)
@@ -48,10 +54,6 @@ def fit(store: engine.ObservationStore, params: dict, J: torch.Tensor | None, J_
         params['beta'].grad = (sc * s[3:6]).to(torch.float32).view(3, 1)
         params['gamma'].grad = (-sc * s[6:9]).to(torch.float32).view(3, 1)
         # chain rule through se3.exp and the inverse: d/d(cam2light, sigma) of <dL/dR, R> + <dL/dt, t> + <dL/dS, S>
-        xi = params['cam2light'].detach().clone().requires_grad_(True)
-        sg = params['sigma'].detach().clone().requires_grad_(True)
-        R, t = se3.exp(xi)
-        Sinv = (sg.T @ sg).inverse()
         dR = (-sc * s[13:22]).to(torch.float32).view(3, 3)
         dt = (-sc * s[22:25]).to(torch.float32).view(3, 1)
         dS = (0.5 * sc * torch.stack([torch.stack([s[10], s[11]]), torch.stack([s[11], s[12]])])).to(torch.float32)
