@@ -50,12 +50,18 @@ constexpr float kLog2e = 1.4426950408889634f;
 #define SUCRE_FIT_TILE_COST 3  // per-tile overhead (J load/store, finalisation, double accumulation) in row-equivalents
 #endif
 constexpr int kTileCost = SUCRE_FIT_TILE_COST;
+#ifndef SUCRE_FIT_UNROLL
+#define SUCRE_FIT_UNROLL 4
+#endif
+constexpr int kRowLoopUnroll = SUCRE_FIT_UNROLL;   // two-row steps per trip of the row loop: unrolled, the accumulators stop
+                                                   // rotating through registers at every back-edge (98 -> 91.5 instructions per step)
 
 // workspace layout (bytes)
-constexpr size_t kWsPartials = 0;                                                     // double[2][kMaxFitCtas][kSums] (iteration parity)
-constexpr size_t kWsPartRow = kWsPartials + sizeof(double) * kSums * kMaxFitCtas * 2;  // long long[kMaxFitCtas*kFitWarps + 1]
+constexpr int kLLWords = 2 * kSums;   // a row of ten doubles as tagged 8-byte words {tag : 32 | half a double : 32}
+constexpr size_t kWsPartials = 0;                                                     // u64[2][kMaxFitCtas][kLLWords] (tag parity); the light kernels keep plain double rows here
+constexpr size_t kWsPartRow = kWsPartials + sizeof(unsigned long long) * kLLWords * kMaxFitCtas * 2;  // long long[kMaxFitCtas*kFitWarps + 1]
 constexpr size_t kWsPartTile = kWsPartRow + sizeof(long long) * (kMaxFitCtas * kFitWarps + 2);  // int[kMaxFitCtas*kFitWarps + 1]
-constexpr size_t kWsTicket = kWsPartTile + sizeof(int) * (kMaxFitCtas * kFitWarps + 4);  // unsigned ticket, status, iteration flag; 16-aligned
+constexpr size_t kWsTicket = kWsPartTile + sizeof(int) * (kMaxFitCtas * kFitWarps + 4);  // unsigned [4]: unused, status bits, tag base, unused; 16-aligned
 constexpr int kMaxLoopIters = 1024;   // Adam iterations per launch of the persistent loop (longer runs are split)
 constexpr size_t kWsAdamTab = kWsTicket + 16;                        // AdamScalars[kMaxLoopIters]
 constexpr size_t kWsBytes = kWsAdamTab + 16 * kMaxLoopIters;
@@ -68,6 +74,25 @@ __device__ __forceinline__ unsigned long long globaltimer() {
 }
 
 enum FitMode { kClosedForm = 0, kParamJ = 1, kWriteJ = 2 };
+
+// Developer build only (-DSUCRE_FIT_TRACE, tools/fit_trace.py): globaltimer stamps of the phases of an iteration, per CTA,
+// and of the end of every warp's sweep, for the first kTraceIters iterations of a launch.
+#if defined(SUCRE_FIT_TRACE)
+constexpr int kTraceIters = 64, kTraceCtas = 160, kTraceStamps = 8;
+__device__ unsigned long long g_trace[kTraceIters][kTraceCtas][kTraceStamps];
+__device__ unsigned long long g_trace_warp[kTraceIters][kTraceCtas][SUCRE_FIT_THREADS / 32];
+#define SUCRE_TRACE(slot)                                                                                   \
+    do {                                                                                                    \
+        if (MODE != kWriteJ && threadIdx.x == 0 && it < kTraceIters && blockIdx.x < kTraceCtas) g_trace[it][blockIdx.x][slot] = globaltimer(); \
+    } while (0)
+#define SUCRE_TRACE_WARP()                                                                                  \
+    do {                                                                                                    \
+        if (MODE != kWriteJ && lane == 0 && it < kTraceIters && blockIdx.x < kTraceCtas) g_trace_warp[it][blockIdx.x][warp] = globaltimer(); \
+    } while (0)
+#else
+#define SUCRE_TRACE(slot) do {} while (0)
+#define SUCRE_TRACE_WARP() do {} while (0)
+#endif
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -335,8 +360,8 @@ struct FitArgs {
     float* J_moments;      // pixels*6: per pixel {m[3], v[3]} (J parameter mode)
     const long long* part_row;  // per global warp: first row of its stream; [n_warps] = rows of the store
     const int* part_tile;       // per global warp: first tile it owns (finalises); [n_warps] = n_tiles
-    double* partials;      // gridDim.x rows of kSums
-    unsigned* ticket;      // ticket[0] = rows published since the launch started (cleared by the host before it), ticket[1] = status bits
+    unsigned long long* rows;   // [2][kMaxFitCtas][kLLWords] tagged words: the CTAs' rows of partial sums
+    unsigned* ticket;      // ticket[1] = status bits, ticket[2] = tag base (iterations run on this workspace so far)
     double* sums_out;      // if non-null the last CTA stores the reduced sums here
     float* history;        // if non-null: num_iter rows of {params after the step [9], cost}
     int do_step;           // apply Adam to the 9 scalars in the last CTA
@@ -352,7 +377,6 @@ struct FitArgs {
 // What rank r leaves in every peer's buffer at [epoch & 1][r]: the 10 sums as 20 words {epoch : 32 | half of a double : 32}.
 // An aligned 8-byte store is atomic, so a word whose tag is the current epoch carries valid data: no fence, no
 // separate flag, one NVLink store latency per exchange (the layout of NCCL's LL protocol).
-constexpr int kLLWords = 2 * kSums;
 struct PeerSlot {
     unsigned long long w[kLLWords];
 };
@@ -366,12 +390,39 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void ld_volatile_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+// Warp-wide: the sum, over the CTAs' rows, of the double whose two tagged words start at `col_words` in every row.  All of
+// a lane's loads are in flight together and are re-issued until each carries the tag: one L2 round trip after the last
+// row lands, not one per row.  Rows are added in a fixed order.  (Not inlined: its registers must not weigh on the
+// allocation of the sweep's inner loop.)
+__device__ __noinline__ double gather_column(const unsigned long long* col_words, unsigned tag, int lane, int n_ctas) {
+    constexpr int kDepth = 5;   // rows per lane and pass: 160 CTAs per pass
+    double v = 0.0;
+    for (int r0 = lane; r0 < n_ctas; r0 += 32 * kDepth) {
+        unsigned long long lo[kDepth], hi[kDepth];
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int k = 0; k < kDepth; ++k) {
+                const int r = r0 + 32 * k;
+                if (r < n_ctas) {
+                    ld_volatile_pair(col_words + (size_t)r * kLLWords, lo[k], hi[k]);
+                    ok = ok && (unsigned)(lo[k] >> 32) == tag && (unsigned)(hi[k] >> 32) == tag;
+                }
+            }
+        } while (!ok);
+#pragma unroll
+        for (int k = 0; k < kDepth; ++k)
+            if (r0 + 32 * k < n_ctas) v += __longlong_as_double((long long)((hi[k] << 32) | (lo[k] & 0xffffffffull)));
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
 }
 
@@ -401,6 +452,8 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     __shared__ double tot[kSums];
     __shared__ unsigned ll_half[SUCRE_MAX_PEERS][kLLWords];
     __shared__ float s_state[27];   // this CTA's copy of the 9 parameters and their Adam moments (m[9], v[9])
+    __shared__ AdamScalars s_ad;
+    __shared__ unsigned s_tag_base; // iterations run on this workspace before this launch (CTA 0 moves it on when the launch ends)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kFitWarps + warp;
     const unsigned char* ring = fit_smem + (size_t)warp * kRingBytes;
@@ -412,6 +465,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (threadIdx.x == 32 && MODE != kWriteJ) s_tag_base = A.ticket[2];
     if (threadIdx.x < 27) {
         const bool moments = threadIdx.x >= 9 && A.moments != nullptr;
         s_state[threadIdx.x] = threadIdx.x < 9 ? A.params[threadIdx.x] : (moments ? A.moments[threadIdx.x - 9] : 0.f);
@@ -476,10 +530,9 @@ fit_kernel(const __grid_constant__ FitArgs A) {
     const int n_iter = MODE == kWriteJ ? 1 : A.num_iter;
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
-        float Bs[3];   // B in the store's units
         typename PixelStats<MODE, PRECISE, REC>::Consts kc;
         {
-            float kb[3], kg[3];
+            float Bs[3], kb[3], kg[3];   // Bs: B in the store's units
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float B = s_state[c], beta = s_state[3 + c], gamma = s_state[6 + c];
@@ -490,7 +543,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             kc.kb_rg = pk(kb[0], kb[1]), kc.kg_rg = pk(kg[0], kg[1]), kc.nB_rg = pk(-Bs[0], -Bs[1]);
             kc.kb_b = kb[2], kc.kg_b = kg[2], kc.nB_b = -Bs[2];
         }
-        const AdamScalars ad = (MODE == kWriteJ || A.adam_tab == nullptr) ? AdamScalars{0.f, 1.f, 0.0} : A.adam_tab[it];
+        // The scalars of this iteration's Adam step wait in shared memory (registers are what the sweep is short of); only
+        // the J-parameter mode needs them inside the sweep.
+        if (MODE != kWriteJ && threadIdx.x == 96) s_ad = A.adam_tab ? A.adam_tab[it] : AdamScalars{0.f, 1.f, 0.0};
+        const AdamScalars ad = (MODE == kParamJ && A.adam_tab) ? A.adam_tab[it] : AdamScalars{0.f, 1.f, 0.0};
+        SUCRE_TRACE(0);
 
         // per-thread partial sums of the ten global sums: fp32 over this warp's tiles (a few dozen per-pixel values,
         // each itself an fp32 sum), promoted to double for everything that follows (warp tree, CTA row, last CTA, peers)
@@ -498,33 +555,37 @@ fit_kernel(const __grid_constant__ FitArgs A) {
 #pragma unroll
         for (int i = 0; i < kSums; ++i) acc[i] = 0.f;
 
+        // tile extents relative to the warp's stream and pixel indices are 32-bit (check_store bounds both): the tile
+        // loop lives at the register limit
         int t = t_first;
-        long long rend_next = t < T1 ? A.row_off[t + 1] : 0;
-        long long p_next = (long long)t * kTile + lane;
+        int rend_next = t < T1 ? (int)(A.row_off[t + 1] - B0) : 0;
+        int p_next = t * kTile + lane;
         float Jnext[3] = {0.f, 0.f, 0.f};
         if (A.J && t < T1 && p_next < A.pixels) {
-            Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
+            const float* Jp = A.J + (size_t)3 * p_next;
+            Jnext[0] = Jp[0], Jnext[1] = Jp[1], Jnext[2] = Jp[2];
         }
 
 #pragma unroll 1
         for (; t < T1; ++t) {
             const bool head = t < T0;
-            const long long rend = rend_next;
-            const long long p = p_next;
+            const int rend = rend_next;
+            const int p = p_next;
             float Jref[3] = {Jnext[0], Jnext[1], Jnext[2]};
-            if (t + 1 < T1) {  // prefetch the next tile's extent and reference J
-                rend_next = A.row_off[t + 2];
+            if (t + 1 < T1) {  // the next tile's extent and reference J: their latency hides behind this tile's rows
+                rend_next = (int)(A.row_off[t + 2] - B0);
                 p_next = p + kTile;
                 if (A.J && p_next < A.pixels) {
-                    Jnext[0] = A.J[3 * p_next], Jnext[1] = A.J[3 * p_next + 1], Jnext[2] = A.J[3 * p_next + 2];
+                    const float* Jp = A.J + (size_t)3 * p_next;
+                    Jnext[0] = Jp[0], Jnext[1] = Jp[1], Jnext[2] = Jp[2];
                 }
             }
             if (MODE == kWriteJ) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) Jref[c] = Jref[c] == Jref[c] ? Jref[c] : 0.f;  // a NaN reference is no reference
             }
-            const bool cut = rend > B1;                           // the tile's last rows are in the next warp's stream
-            const int rb = (int)((cut ? B1 : rend) - B0);         // stream row where this item ends
+            const bool cut = rend > n_rows_w;                     // the tile's last rows are in the next warp's stream
+            const int rb = cut ? n_rows_w : rend;                 // stream row where this item ends
             PixelStats<MODE, PRECISE, REC> st;
             st.clear();
             unsigned seen_bits = 0;   // OR of the z bit patterns of the lane's records: non-zero iff it has an observation
@@ -539,7 +600,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                 // the next chunk is awaited.
                 while (true) {
                     const int lim = min(rb, avail);
-#pragma unroll 1
+#pragma unroll kRowLoopUnroll
                     for (; r + 2 <= lim; r += 2) {
                         const int o1 = (roff + kRowBytes) & (kRingBytes - 1);
                         const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
@@ -578,7 +639,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                 if (p < A.pixels) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        A.J_out[3 * p + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
+                        A.J_out[(size_t)3 * p + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
                 }
             } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
                 float Jout[3];
@@ -598,24 +659,24 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                     Jout[c] = Js * kInv;
                     acc[c] += rh;                                // sum r (1 - e^{-gamma z})    x kScale
                     acc[3 + c] = fmaf(Js, rza, acc[3 + c]);      // sum r J z e^{-beta z}       x kScale^2
-                    acc[6 + c] = fmaf(Bs[c], rzg, acc[6 + c]);   // sum r B z e^{-gamma z}      x kScale^2
+                    acc[6 + c] += rzg;                           // sum r z e^{-gamma z}        x kScale; times B at the end of the sweep
                     acc[9] += rr;                                // sum r^2                     x kScale^2
                     if (MODE == kParamJ) {
                         // dL/dJ = -(2 / 3N) sum r a; the pixel's own Adam step with the pre-step B, beta, gamma (sucre.py:144-148)
-                        float* mv = A.J_moments + 6 * p;
+                        float* mv = A.J_moments + (size_t)6 * p;
                         float m = mv[c], v = mv[3 + c];
                         Jout[c] = adam_update(Jref[c], (float)(-ad.grad_scale) * (S1 * kInv), m, v, ad.neg_step_size, ad.bc2_sqrt);
                         mv[c] = m;
                         mv[3 + c] = v;
                     }
                 }
-                A.J[3 * p + 0] = Jout[0];
-                A.J[3 * p + 1] = Jout[1];
-                A.J[3 * p + 2] = Jout[2];
+                A.J[(size_t)3 * p + 0] = Jout[0];
+                A.J[(size_t)3 * p + 1] = Jout[1];
+                A.J[(size_t)3 * p + 2] = Jout[2];
             }
         }
         if (MODE == kWriteJ) return;
-        if (it + 1 < n_iter) restart_stream();   // next iteration's first rows: in flight while the sums are reduced
+        SUCRE_TRACE_WARP();
 
         // warp tree -> one slot per warp -> one row per CTA (the store's units are divided out here, in double)
 #pragma unroll
@@ -625,31 +686,37 @@ fit_kernel(const __grid_constant__ FitArgs A) {
             if (lane == 0) sm[warp][i] = v;
         }
         __syncthreads();
-        double* const rows = A.partials + (size_t)(it & 1) * kMaxFitCtas * kSums;   // two parities: nobody is two iterations ahead
-        if (threadIdx.x < kSums) {
-            double v = 0.0;
-            for (int wi = 0; wi < kFitWarps; ++wi) v += sm[wi][threadIdx.x];
-            const double unit = threadIdx.x < 3 ? 1.0 / (double)kScale : 1.0 / ((double)kScale * (double)kScale);
-            rows[(size_t)blockIdx.x * kSums + threadIdx.x] = v * unit;
-            __threadfence();
-        }
-        __syncthreads();
-        // Every CTA waits for all rows, reduces them ITSELF in the same fixed order and takes the same Adam step on its own
+        // A CTA's row is published as 20 tagged 8-byte words {tag : 32 | half a double : 32} (two tag parities: nobody is
+        // two iterations ahead).  An aligned 8-byte store is atomic, so a word that carries this iteration's tag IS the
+        // data: no fence, no counter, no second round trip to L2 (the layout of the exchange between GPUs below).
+        // Every CTA polls all rows, reduces them ITSELF in the same fixed order and takes the same Adam step on its own
         // copy of the parameters and moments: no CTA waits for another one to publish the result, and the next sweep
         // starts straight from shared memory.  CTA 0 alone talks to the outside (history, sums, peers, final state).
-        if (threadIdx.x == 0) {
-            atomicAdd(A.ticket, 1u);
-            const unsigned want = (unsigned)(it + 1) * gridDim.x;
-            while (ld_acquire_gpu(A.ticket) < want) __nanosleep(20);
+        SUCRE_TRACE(1);
+        const unsigned tag = s_tag_base + (unsigned)it + 1u;
+        unsigned long long* const rows = A.rows + (size_t)(tag & 1u) * kMaxFitCtas * kLLWords;
+        if (threadIdx.x < kSums) {
+            double part[4] = {0.0, 0.0, 0.0, 0.0};   // four interleaved chains, not one 16-deep chain of dependent double additions
+#pragma unroll
+            for (int wi = 0; wi < kFitWarps; ++wi) part[wi & 3] += sm[wi][threadIdx.x];
+            double unit = threadIdx.x < 3 ? 1.0 / (double)kScale : 1.0 / ((double)kScale * (double)kScale);
+            if (threadIdx.x >= 6 && threadIdx.x < 9) unit = (double)s_state[threadIdx.x - 6] / (double)kScale;   // sum r B z e^{-gamma z}
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(((part[0] + part[1]) + (part[2] + part[3])) * unit);
+            unsigned long long* w = rows + (size_t)blockIdx.x * kLLWords + 2 * threadIdx.x;
+            st_relaxed_gpu(w, ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
+            st_relaxed_gpu(w + 1, ((unsigned long long)tag << 32) | (bits >> 32));
         }
-        __syncthreads();
+        SUCRE_TRACE(2);
+        // The next iteration's first rows are requested now: in flight while the sums are reduced, but behind this CTA's row
+        // (148 SMs x 16 warps x 8 KB of copies ahead of it would hold the row, and with it every other CTA, back).
+        if (it + 1 < n_iter) restart_stream();
         for (int col = warp; col < kSums; col += kFitWarps) {
-            double v = 0.0;
-            for (int r = lane; r < (int)gridDim.x; r += 32) v += __ldcg(rows + (size_t)r * kSums + col);
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            const double v = gather_column(rows + 2 * col, tag, lane, (int)gridDim.x);
             if (lane == 0) tot[col] = v;
         }
+        SUCRE_TRACE(3);
         __syncthreads();
+        SUCRE_TRACE(4);
         if (A.world > 1) {
             // One-shot all-reduce over NVLink.  CTA 0 of every rank stores the rank's 10 sums, as 20 tagged 8-byte words,
             // into every rank's buffer (slot [epoch & 1][rank], its own included); every CTA polls the words of all ranks
@@ -693,9 +760,10 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         if (A.do_step && threadIdx.x < 9) {
             const int i = threadIdx.x;
             // B: -2 r (1-g); beta: +2 r J z a; gamma: -2 r B z g   (all times 1 / 3N)
-            const float g = (float)((i >= 3 && i < 6 ? ad.grad_scale : -ad.grad_scale) * tot[i]);
+            const AdamScalars as = s_ad;
+            const float g = (float)((i >= 3 && i < 6 ? as.grad_scale : -as.grad_scale) * tot[i]);
             float m = s_state[9 + i], v = s_state[18 + i];
-            const float pnew = adam_update(s_state[i], g, m, v, ad.neg_step_size, ad.bc2_sqrt);
+            const float pnew = adam_update(s_state[i], g, m, v, as.neg_step_size, as.bc2_sqrt);
             s_state[i] = pnew, s_state[9 + i] = m, s_state[18 + i] = v;
             if (history_row) history_row[i] = pnew;
             if (writer && it + 1 == n_iter) {   // the state leaves the kernel once
@@ -706,7 +774,10 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         }
         if (threadIdx.x == 9 && history_row) history_row[9] = (float)tot[9];
         __syncthreads();   // s_state is read at the top of the next iteration
+        SUCRE_TRACE(5);
     }
+    // every CTA read the base before the first rendezvous of this launch, so it can move on now
+    if (MODE != kWriteJ && blockIdx.x == 0 && threadIdx.x == 0) A.ticket[2] = s_tag_base + (unsigned)n_iter;
 }
 
 // Adam step of the 9 scalars from already reduced sums (multi-GPU: after the all-reduce)
@@ -857,7 +928,7 @@ static FitArgs base_args(const sucre_store* s, void* workspace) {
     a.n_tiles = s->n_tiles;
     a.pixels = s->pixels;
     char* ws = (char*)workspace;
-    a.partials = (double*)(ws + kWsPartials);
+    a.rows = (unsigned long long*)(ws + kWsPartials);
     a.part_row = (const long long*)(ws + kWsPartRow);
     a.part_tile = (const int*)(ws + kWsPartTile);
     a.ticket = (unsigned*)(ws + kWsTicket);
@@ -874,6 +945,14 @@ using namespace sucre;
 
 extern "C" size_t sucre_fit_workspace_bytes(void) { return kWsBytes; }
 
+#if defined(SUCRE_FIT_TRACE)
+extern "C" int sucre_debug_fit_trace(unsigned long long* cta_stamps, unsigned long long* warp_stamps) {
+    if (cudaMemcpyFromSymbol(cta_stamps, g_trace, sizeof(g_trace)) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(warp_stamps, g_trace_warp, sizeof(g_trace_warp)) != cudaSuccess) return 1;
+    return 0;
+}
+#endif
+
 extern "C" int sucre_fit_prepare(const sucre_store* store_host, void* workspace, void* stream) {
     clear_error();
     if (check_store(store_host, "sucre_fit_prepare")) return 1;
@@ -882,6 +961,8 @@ extern "C" int sucre_fit_prepare(const sucre_store* store_host, void* workspace,
     const int n_ctas = fit_grid();
     const int n_warps = n_ctas * kFitWarps;
     char* ws = (char*)workspace;
+    // rows and tag base start cleared: tags count from 1, so a cleared word is never taken for data
+    SUCRE_CUDA(cudaMemsetAsync(ws + kWsPartials, 0, kWsPartRow - kWsPartials, st));
     SUCRE_CUDA(cudaMemsetAsync(ws + kWsTicket, 0, 16, st));
     partition_kernel<<<(n_warps + 1 + 255) / 256, 256, 0, st>>>((const long long*)store_host->row_off, store_host->n_tiles, n_ctas,
                                                                  (long long*)(ws + kWsPartRow), (int*)(ws + kWsPartTile));
@@ -902,7 +983,6 @@ extern "C" int sucre_fit_sums(int mode, const sucre_store* store_host, const flo
     a.do_step = 0;
     const AdamScalars one = mode == kParamJ ? adam_scalars(t, lr, n_obs) : AdamScalars{0.f, 1.f, 0.0};
     SUCRE_CUDA(cudaMemcpyAsync((char*)workspace + kWsAdamTab, &one, sizeof one, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    SUCRE_CUDA(cudaMemsetAsync((char*)workspace + kWsTicket, 0, 4, (cudaStream_t)stream));
     if (mode == kClosedForm) launch_fit<kClosedForm>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
     else launch_fit<kParamJ>(a, store_host->record_format, fit_grid(), (cudaStream_t)stream);
     return check_launch("fit_kernel");
@@ -949,7 +1029,6 @@ static int fit_loop(int mode, const sucre_store* store_host, int64_t n_obs, floa
         AdamScalars tab[kMaxLoopIters];
         for (int it = 0; it < n; ++it) tab[it] = adam_scalars(first_step + done + it, lr, n_obs);
         SUCRE_CUDA(cudaMemcpyAsync((char*)workspace + kWsAdamTab, tab, sizeof(AdamScalars) * n, cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
-        SUCRE_CUDA(cudaMemsetAsync((char*)workspace + kWsTicket, 0, 4, st));   // rows published: counted from zero per launch
         a.num_iter = n;
         a.history = history ? history + (size_t)done * kSums : nullptr;
         a.epoch = first_epoch + (uint32_t)done;
