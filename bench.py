@@ -393,7 +393,7 @@ def ours(args):
                                       'h2d_bytes_per_step': res_f.h2d_bytes,
                                       's_per_restored_image': ms_full / args.steps / 1e3}},
         'gpu_launches': args.steps * api.LAUNCHES_PER_IMAGE,
-        'gpu_launches_note': 'per image: gather_match, count_views, tile_count, scan, gather_sample, partition, ONE resident fit_kernel '
+        'gpu_launches_note': 'per image: gather_match, count_views, permute, tile_count, scan, gather_sample, partition, ONE resident fit_kernel '
                              f'launch running all {args.num_iter} Adam iterations, fit_kernel<write J>',
         'roofline': {'bound': 'hbm', 'kernel': 'fit_kernel<closed form, 8-byte records>', 'achieved': achieved, 'peak': peak,
                      'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic_per_launch(n_obs), 'peak_source': peak_src,

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SUCRE_ABI_VERSION 9
+#define SUCRE_ABI_VERSION 10
 #define SUCRE_TILE_PIXELS 32
 #define SUCRE_REC_Z_U8 0
 #define SUCRE_REC_Z_F32 1
@@ -82,14 +82,25 @@ typedef struct sucre_view {
 } sucre_view;
 
 /* The observation store of one target (or of a band of its tiles), as the fit reads it.  A host struct of
- * device pointers.  sizeof == 40. */
+ * device pointers.  sizeof == 48.
+ *
+ * Slots and pixels.  Lane i of tile k is SLOT 32k + i.  Without `pix`, slot q is the store's q-th pixel (valid iff
+ * q < pixels).  With `pix` (sucre_gather_permute), the pixels of every group of 32 tiles were dealt to the group's slots
+ * in order of decreasing observation count — neighbouring lanes then have columns of nearly equal height and the ELL
+ * rows hold few sentinels (fill 0.90 -> 0.99 on the benchmark scene) — and pix[q] is the pixel of slot q (-1: none).
+ * The J / J_moments arrays of the Adam-loop entry points (sucre_fit, sucre_fit_sharded, sucre_fit_sums) and J_ref of
+ * sucre_fit_write_J are always in SLOT order (32 * n_tiles entries when pix is set, `pixels` otherwise): they are work
+ * buffers of the loop.  sucre_fit_write_J's output, the light-model entry points and sucre_band_scatter_J address J by
+ * PIXEL (pix[q]; `pixels` = entries of those arrays). */
 typedef struct sucre_store {
     const void* cells;       /* rows of 32 records, 16-byte aligned; may be NULL when n_rows == 0 */
     const int64_t* row_off;  /* [n_tiles+1] rows before tile k */
     int32_t n_tiles;
     int32_t record_format;   /* SUCRE_REC_* */
-    int64_t pixels;          /* target pixels covered: min(n_tiles*32, width*height - first_tile*32) */
+    int64_t pixels;          /* pix == NULL: target pixels covered, min(n_tiles*32, width*height - first_tile*32);
+                                pix != NULL: entries of the pixel-ordered arrays pix indexes (e.g. width*height) */
     int64_t n_rows;          /* host copy of row_off[n_tiles] */
+    const int32_t* pix;      /* [n_tiles*32] pixel of every slot, -1 = none; NULL = the identity */
 } sucre_store;
 
 /* The tiles of a target that one call (one rank) covers.  Local tile k is the target's tile
@@ -138,6 +149,17 @@ int sucre_scene_upload(void* dst, const void* src_host, int n, const int32_t* sr
 int sucre_gather_match(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
                        uint32_t* masks, int64_t* stats, void* stream);
 
+/* sucre_gather_permute (optional, between sucre_gather_match and sucre_gather_plan): deals the pixels of every group
+ * of SUCRE_GROUP_TILES consecutive local tiles to the group's slots in order of decreasing match count (over all listed
+ * views; ties in pixel order, so the result is deterministic).
+ *   pix[n_tiles*32]          (int32) flat index IN THE TARGET IMAGE of the pixel in every slot, -1 for none
+ *   pmasks[n_tiles*n_views]  the masks of the permuted tiles: bit i of pmasks[k*n_views + s] = pixel pix[32k+i] matched
+ *                            in view s.  Hand pmasks (not masks) to sucre_gather_plan and sucre_gather_sample, and pix
+ *                            to sucre_gather_sample and to the store. */
+#define SUCRE_GROUP_TILES 32
+int sucre_gather_permute(const uint32_t* masks, int n_views, const sucre_band* band_host, int64_t target_pixels,
+                         int32_t* pix, uint32_t* pmasks, void* stream);
+
 /* sucre_gather_count: view_count[n_views] (int64) = matches per view over the band (kept or not).
  * Multi-GPU callers all-reduce view_count before sucre_gather_plan: min_cover is a whole-image criterion. */
 int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t* view_count, void* stream);
@@ -159,16 +181,18 @@ int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views, const int
  * load_matches (loader.py:68-87, 103-118) and load_rgb's scaling (loader.py:156-163); the HDF5 spill file is
  * replaced by this device-resident store.  record_format: SUCRE_REC_*; the U8 formats require every kept view to be
  * SUCRE_RGB_U8.  cell_src (optional, may be NULL; one uint32 per record slot, index row*32 + lane) receives
- * u2 | v2 << 16, the integer source pixel (what the reference stores as int16 u2, v2), 0xffffffff at sentinels. */
+ * u2 | v2 << 16, the integer source pixel (what the reference stores as int16 u2, v2), 0xffffffff at sentinels.
+ * pix (optional, may be NULL): the slot -> pixel map of sucre_gather_permute; masks are then its pmasks. */
 int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
-                        const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
+                        const int32_t* pix, const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
                         const int64_t* blk_off, int record_format, void* cells, uint32_t* blk_mask, int32_t* blk_view,
                         uint32_t* cell_src, void* stream);
 
-/* sucre_band_scatter_J: copies a band's J (J_band[pixels_local*3], local tile order) to its place in n_dst whole-image
+/* sucre_band_scatter_J: copies a band's J (J_band[n_tiles*32*3], slot order) to its place in n_dst whole-image
  * J buffers (target_pixels*3 floats each; dst_ptrs_host[i] = device address — this GPU's or a peer's NVLink-mapped
- * buffer).  The assembly step of a target sharded over several GPUs ("the final gather of J") as direct peer writes. */
-int sucre_band_scatter_J(const float* J_band, const sucre_band* band_host, int64_t target_pixels,
+ * buffer).  pix (optional): the band's slot -> image pixel map; NULL = the band's own tile arithmetic.
+ * The assembly step of a target sharded over several GPUs ("the final gather of J") as direct peer writes. */
+int sucre_band_scatter_J(const float* J_band, const sucre_band* band_host, const int32_t* pix, int64_t target_pixels,
                          const uint64_t* dst_ptrs_host, int n_dst, void* stream);
 
 /* ---- stage 2: per-pixel fit of the image formation model ------------------------------------------------
@@ -210,18 +234,18 @@ int sucre_adam_step(float* params, float* adam_state, const double* sums, int64_
                     float* history_row, void* stream);
 
 /* The whole single-GPU loop of adam() (sucre.py:138-148) as ONE launch of a resident grid (one per 1024 iterations):
- * every iteration = one sweep of the store + the Adam step of the 9 scalars in the last CTA to finish, which then raises
- * the flag the other CTAs wait on (steps first_step .. first_step+num_iter-1).  history (optional) = num_iter x 10
+ * every iteration = one sweep of the store, after which every CTA publishes its row of partial sums, gathers all rows
+ * and takes the Adam step of the 9 scalars on its own copy of the state (steps first_step .. first_step+num_iter-1).  history (optional) = num_iter x 10
  * floats.  For the final update_J of closed-form mode (sucre.py:156) call sucre_fit_write_J. */
 int sucre_fit(int mode, const sucre_store* store_host, int64_t n_obs, float* params, float* adam_state, float* J,
               float* J_moments, int first_step, int num_iter, double lr, float* history, void* workspace,
               void* stream);
 
 /* The same loop for ONE target whose tiles are sharded over `world` GPUs (store_host = this rank's band, n_obs_global
- * = observations of all bands): the all-reduce of the 10 sums is fused into the kernel — the last CTA of every rank
- * stores its sums, as 8-byte words tagged with the iteration's epoch, into every peer's exchange buffer over NVLink
+ * = observations of all bands): the all-reduce of the 10 sums is fused into the kernel — CTA 0 of every rank
+ * stores its rank's sums, as 8-byte words tagged with the iteration's epoch, into every peer's exchange buffer over NVLink
  * (peers_host[p] = device address of rank p's buffer, SUCRE_PEER_BUFFER_BYTES each, zeroed once, mapped into this
- * process, e.g. torch symmetric memory), polls its own buffer for the words of all ranks and adds the rows in rank
+ * process, e.g. torch symmetric memory), every CTA polls its own GPU's buffer for the words of all ranks and adds the rows in rank
  * order, so every rank applies the identical Adam step with no host or NCCL round trip.  first_epoch: a tag >= 1 for the first iteration, identical on all ranks, and increasing by num_iter
  * from one call on the same buffers to the next.  All ranks must make the same sequence of calls.  A rank that waits
  * longer than SUCRE_PEER_TIMEOUT_NS for a peer stops waiting, sets bit 0 of the status word
@@ -238,8 +262,9 @@ int sucre_fit_sharded(int mode, const sucre_store* store_host, int64_t n_obs_glo
  * pointer, uint32) on `stream`, and clears it. */
 int sucre_fit_status(void* workspace, uint32_t* status, void* stream);
 
-/* Closed-form J for the current params written to J[pixels*3]; NaN where a pixel has no observation (0/0 like
- * sucre.py:77).  J_ref (optional): a previous J used as the reference point of the statistics. */
+/* Closed-form J for the current params written to J[pixels*3] in PIXEL order (through store->pix when set); NaN where
+ * a pixel has no observation (0/0 like sucre.py:77).  J_ref (optional): a previous J (the loop's work buffer, SLOT
+ * order) used as the reference point of the statistics. */
 int sucre_fit_write_J(const sucre_store* store_host, const float* params, const float* J_ref, float* J,
                       void* workspace, void* stream);
 

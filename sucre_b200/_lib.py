@@ -9,7 +9,7 @@ import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / 'libsucre_b200.so'
-ABI_VERSION = 9
+ABI_VERSION = 10
 TILE = 32
 REC_Z_U8, REC_Z_F32, REC_P_U8, REC_P_F32 = 0, 1, 2, 3
 RECORD_BYTES = {REC_Z_U8: 8, REC_Z_F32: 16, REC_P_U8: 16, REC_P_F32: 32}
@@ -29,12 +29,13 @@ class SucreError(RuntimeError):
 
 
 class SucreStore(C.Structure):
-    """ctypes mirror of `struct sucre_store` (host struct of device pointers, 40 bytes)."""
+    """ctypes mirror of `struct sucre_store` (host struct of device pointers, 48 bytes)."""
     _fields_ = [('cells', C.c_void_p), ('row_off', C.c_void_p), ('n_tiles', C.c_int32), ('record_format', C.c_int32),
-                ('pixels', C.c_int64), ('n_rows', C.c_int64)]
+                ('pixels', C.c_int64), ('n_rows', C.c_int64), ('pix', C.c_void_p)]
 
 
-assert C.sizeof(SucreStore) == 40
+assert C.sizeof(SucreStore) == 48
+GROUP_TILES = 32   # SUCRE_GROUP_TILES: tiles whose pixels sucre_gather_permute deals by observation count
 
 
 class Band(C.Structure):
@@ -95,8 +96,9 @@ _SIGNATURES = {
     'sucre_gather_match': (C.c_int, [_VP, _VP, _I, _VP, _VP, _VP, _VP]),
     'sucre_gather_count': (C.c_int, [_VP, _I, _I, _VP, _VP]),
     'sucre_gather_plan': (C.c_int, [_VP, _I, _I, _VP, _I64, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
-    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
-    'sucre_band_scatter_J': (C.c_int, [_VP, _VP, _I64, _VP, _I, _VP]),
+    'sucre_gather_permute': (C.c_int, [_VP, _I, _VP, _I64, _VP, _VP, _VP]),
+    'sucre_gather_sample': (C.c_int, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    'sucre_band_scatter_J': (C.c_int, [_VP, _VP, _VP, _I64, _VP, _I, _VP]),
     'sucre_fit_workspace_bytes': (C.c_size_t, []),
     'sucre_fit_prepare': (C.c_int, [_VP, _VP, _VP]),
     'sucre_fit_sums': (C.c_int, [_I, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP]),

@@ -352,7 +352,9 @@ struct FitArgs {
     const unsigned char* cells;
     const long long* row_off;
     int n_tiles;
-    long long pixels;
+    long long pixels;          // entries of the slot-ordered J arrays (J, J_moments)
+    const int* pix;            // write-J: slot -> entry of J_out (nullptr: the identity, bounded by out_pixels)
+    long long out_pixels;
     float* params;         // 9: B, beta, gamma (read at the start of every iteration; written by the last CTA when do_step)
     float* moments;        // 18: Adam state of the 9 scalars
     float* J;              // pixels*3: Jref (closed form, in/out), the J parameter (in/out), or Jref (write-J, may be null)
@@ -636,10 +638,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                 st.add_parked(park_all + (size_t)(warp + 1) * kStats * 32, lane);
             }
             if (MODE == kWriteJ) {
-                if (p < A.pixels) {
+                const long long dst = A.pix ? (long long)A.pix[p] : (p < A.out_pixels ? (long long)p : -1);
+                if (dst >= 0) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        A.J_out[(size_t)3 * p + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
+                        A.J_out[(size_t)3 * dst + c] = seen ? Jref[c] + (st.get(c, 0) / st.get(c, 1)) * kInv : __int_as_float(0x7fc00000);
                 }
             } else if (seen) {  // lanes whose pixel has no observation in any kept view contribute nothing and keep their J
                 float Jout[3];
@@ -914,7 +917,7 @@ static int check_store(const sucre_store* s, const char* who) {
     SUCRE_REQUIRE(s != nullptr, "%s: null store", who);
     SUCRE_REQUIRE(s->row_off, "%s: null row_off in store", who);
     SUCRE_REQUIRE(s->n_rows >= 0 && (s->cells || s->n_rows == 0), "%s: null cells in a store of %lld rows", who, (long long)s->n_rows);
-    SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && s->pixels <= (int64_t)s->n_tiles * kTile, "%s: bad store sizes", who);
+    SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && (s->pix || s->pixels <= (int64_t)s->n_tiles * kTile), "%s: bad store sizes", who);
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(s->cells) & 15) == 0, "%s: cells must be 16-byte aligned", who);
     SUCRE_REQUIRE(s->record_format == SUCRE_REC_Z_U8 || s->record_format == SUCRE_REC_Z_F32,
                   "%s: this entry point reads {z, I} stores (SUCRE_REC_Z_U8 / SUCRE_REC_Z_F32), got format %d", who, s->record_format);
@@ -926,7 +929,9 @@ static FitArgs base_args(const sucre_store* s, void* workspace) {
     a.cells = reinterpret_cast<const unsigned char*>(s->cells);
     a.row_off = (const long long*)s->row_off;
     a.n_tiles = s->n_tiles;
-    a.pixels = s->pixels;
+    a.pixels = s->pix ? (long long)s->n_tiles * kTile : s->pixels;   // slot-ordered arrays: every slot of a permuted store is addressable
+    a.pix = s->pix;
+    a.out_pixels = s->pixels;
     char* ws = (char*)workspace;
     a.rows = (unsigned long long*)(ws + kWsPartials);
     a.part_row = (const long long*)(ws + kWsPartRow);

@@ -253,6 +253,80 @@ count_views_kernel(const uint32_t* __restrict__ masks, int n_tiles, int n_views,
     }
 }
 
+// ---- permute -----------------------------------------------------------------------------------------------
+// One CTA per group of SUCRE_GROUP_TILES local tiles (1024 slots).  Thread t starts as natural slot t of the group (warp =
+// natural tile): it counts its pixel's matches over all views, the CTA sorts (count descending, natural order among equals)
+// and thread t ends as slot t of the PERMUTED group: it records its pixel in pix and the warp rebuilds the mask words of
+// its permuted tile from the natural ones, staged in shared memory 256 views at a time.  Pixels with columns of equal
+// height end up in the same tile, so the ELL rows of the store hold few sentinels.
+constexpr int kGroupTiles = SUCRE_GROUP_TILES;
+constexpr int kGroupSlots = kGroupTiles * kTile;
+constexpr int kPermViews = 256;   // views staged per pass: 32 rows x 257 words
+static_assert(kGroupSlots == 1024, "one thread per slot of a group");
+
+__global__ void __launch_bounds__(kGroupSlots)
+permute_kernel(const uint32_t* __restrict__ masks, int n_views, const sucre_band band, long long P, int32_t* __restrict__ pix,
+               uint32_t* __restrict__ pmasks) {
+    __shared__ uint32_t key[kGroupSlots];
+    __shared__ int32_t nat_pix[kGroupSlots];
+    __shared__ uint32_t rows[kGroupTiles][kPermViews + 1];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tile0 = blockIdx.x * kGroupTiles;
+    const int k = tile0 + warp;   // natural local tile of this warp, then its permuted tile
+    const bool tile_ok = k < band.n_tiles;
+    long long p = tile_ok ? (long long)band_tile(band, k) * kTile + lane : -1;
+    if (p >= P) p = -1;
+    int cnt = 0;
+    if (tile_ok) {
+        for (int base = 0; base < n_views; base += 32) {
+            const uint32_t m = base + lane < n_views ? __ldg(masks + (size_t)k * n_views + base + lane) : 0u;
+            for (unsigned nz = __ballot_sync(kFull, m != 0); nz; nz &= nz - 1)
+                cnt += (__shfl_sync(kFull, m, __ffs(nz) - 1) >> lane) & 1u;
+        }
+    }
+    nat_pix[t] = (int32_t)p;
+    // ascending sort of {0x1fffff - count : 21 | natural slot : 10} (< 2^31); slots without a pixel go last
+    key[t] = p < 0 ? 0xffffffffu : ((0x1fffffu - (uint32_t)cnt) << 10) | (uint32_t)t;
+    __syncthreads();
+    for (int size = 2; size <= kGroupSlots; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int other = t ^ stride;
+            if (other > t) {
+                const uint32_t a = key[t], b = key[other];
+                const bool up = (t & size) == 0;
+                if ((a > b) == up) {
+                    key[t] = b;
+                    key[other] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t mine = key[t];
+    const int src = mine == 0xffffffffu ? -1 : (int)(mine & 1023u);   // natural slot whose pixel this slot takes
+    if (tile_ok) pix[(size_t)k * kTile + lane] = src < 0 ? -1 : nat_pix[src];
+    const int src_row = src < 0 ? 0 : src >> 5, src_lane = src & 31;
+    for (int v0 = 0; v0 < n_views; v0 += kPermViews) {
+        const int nv = min(kPermViews, n_views - v0);
+        __syncthreads();   // the previous pass is done with `rows`
+        for (int r = warp; r < kGroupTiles; r += kGroupSlots / 32)   // (one row per warp) coalesced over the views
+            for (int c = lane; c < nv; c += 32)
+                rows[r][c] = tile0 + r < band.n_tiles ? __ldg(masks + (size_t)(tile0 + r) * n_views + v0 + c) : 0u;
+        __syncthreads();
+        if (tile_ok) {
+            for (int base = 0; base < nv; base += 32) {
+                uint32_t out = 0;
+                const int m = min(32, nv - base);
+                for (int j = 0; j < m; ++j) {
+                    const unsigned b = __ballot_sync(kFull, src >= 0 && ((rows[src_row][base + j] >> src_lane) & 1u));
+                    if (lane == j) out = b;
+                }
+                if (lane < m) pmasks[(size_t)k * n_views + v0 + base + lane] = out;
+            }
+        }
+    }
+}
+
 // sfm.py:136: len(matches) / (width * height) > min_cover, python floats = IEEE double
 __device__ __forceinline__ bool view_passes(long long count, double pixels, double min_cover) {
     return (double)count / pixels > min_cover;
@@ -440,14 +514,15 @@ __global__ void __launch_bounds__(256)
 gather_sample_kernel(const __grid_constant__ sucre_view T, const sucre_view* __restrict__ views, int n_views,
                      const uint32_t* __restrict__ masks, const uint8_t* __restrict__ view_kept,
                      const long long* __restrict__ row_off, const long long* __restrict__ blk_off, const sucre_band band,
-                     int format, void* __restrict__ cells, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
+                     const int32_t* __restrict__ pix, int format, void* __restrict__ cells, uint32_t* __restrict__ blk_mask, int32_t* __restrict__ blk_view,
                      uint32_t* __restrict__ cell_src) {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tile >= band.n_tiles) return;
     const uint32_t lt = (1u << lane) - 1u;
     const int P = T.width * T.height;
-    const int p = band_tile(band, tile) * kTile + lane;
+    int p = pix ? __ldg(pix + (size_t)tile * kTile + lane) : band_tile(band, tile) * kTile + lane;
+    if (p < 0) p = P;   // a slot without a pixel: depth 0, never matched
     float w0, w1, w2;
     {
         const float d1 = __fdiv_rn((float)(p < P ? __ldg(T.depth + p) : (uint16_t)0), 1000.0f);
@@ -538,13 +613,14 @@ struct ScatterPtrs {
     unsigned long long p[SUCRE_MAX_PEERS];
 };
 __global__ void __launch_bounds__(256)
-scatter_J_kernel(const float* __restrict__ J_band, const sucre_band band, long long floats_local, long long floats_total,
-                 const ScatterPtrs dst, int n_dst) {
+scatter_J_kernel(const float* __restrict__ J_band, const sucre_band band, const int32_t* __restrict__ pix, long long floats_local,
+                 long long floats_total, const ScatterPtrs dst, int n_dst) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= floats_local) return;
     const long long px = i / 3;
-    const long long g = ((long long)band_tile(band, (int)(px / kTile)) * kTile + px % kTile) * 3 + i % 3;
-    if (g >= floats_total) return;  // beyond the last pixel of the image (its last tile is partial)
+    const long long gp = pix ? (long long)pix[px] : (long long)band_tile(band, (int)(px / kTile)) * kTile + px % kTile;
+    const long long g = gp * 3 + i % 3;
+    if (gp < 0 || g >= floats_total) return;  // a slot without a pixel / beyond the last pixel of the image (partial last tile)
     const float v = J_band[i];
     for (int d = 0; d < n_dst; ++d) reinterpret_cast<float*>(dst.p[d])[g] = v;
 }
@@ -574,6 +650,19 @@ extern "C" int sucre_gather_match(const sucre_view* target_host, const sucre_vie
     return check_launch("gather_match_kernel");
 }
 
+extern "C" int sucre_gather_permute(const uint32_t* masks, int n_views, const sucre_band* band_host, int64_t target_pixels,
+                                    int32_t* pix, uint32_t* pmasks, void* stream) {
+    clear_error();
+    SUCRE_REQUIRE(masks && band_host && pix && pmasks, "sucre_gather_permute: null pointer");
+    SUCRE_REQUIRE(masks != pmasks, "sucre_gather_permute: pmasks must not alias masks");
+    SUCRE_REQUIRE(n_views > 0 && n_views < (1 << 21) && target_pixels > 0 && band_host->n_tiles > 0 && band_host->chunk_tiles > 0,
+                  "sucre_gather_permute: bad sizes");
+    SUCRE_REQUIRE((long long)band_tile(*band_host, band_host->n_tiles - 1) * kTile < target_pixels, "sucre_gather_permute: band outside the image");
+    const int groups = (band_host->n_tiles + kGroupTiles - 1) / kGroupTiles;
+    permute_kernel<<<groups, kGroupSlots, 0, (cudaStream_t)stream>>>(masks, n_views, *band_host, (long long)target_pixels, pix, pmasks);
+    return check_launch("permute_kernel");
+}
+
 extern "C" int sucre_gather_count(const uint32_t* masks, int n_tiles, int n_views, int64_t* view_count, void* stream) {
     clear_error();
     SUCRE_REQUIRE(masks && view_count, "sucre_gather_count: null pointer");
@@ -599,7 +688,7 @@ extern "C" int sucre_gather_plan(const uint32_t* masks, int n_tiles, int n_views
 }
 
 extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_view* views, int n_views, const sucre_band* band_host,
-                                   const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
+                                   const int32_t* pix, const uint32_t* masks, const uint8_t* view_kept, const int64_t* row_off,
                                    const int64_t* blk_off, int record_format, void* cells, uint32_t* blk_mask, int32_t* blk_view,
                                    uint32_t* cell_src, void* stream) {
     clear_error();
@@ -611,12 +700,12 @@ extern "C" int sucre_gather_sample(const sucre_view* target_host, const sucre_vi
     SUCRE_REQUIRE((reinterpret_cast<uintptr_t>(cells) & 15) == 0, "sucre_gather_sample: cells must be 16-byte aligned");
     SUCRE_REQUIRE(sucre_record_bytes(record_format) != 0, "sucre_gather_sample: unknown record format %d", record_format);
     gather_sample_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        *target_host, views, n_views, masks, view_kept, (const long long*)row_off, (const long long*)blk_off, *band_host,
+        *target_host, views, n_views, masks, view_kept, (const long long*)row_off, (const long long*)blk_off, *band_host, pix,
         record_format, cells, blk_mask, blk_view, cell_src);
     return check_launch("gather_sample_kernel");
 }
 
-extern "C" int sucre_band_scatter_J(const float* J_band, const sucre_band* band_host, int64_t target_pixels,
+extern "C" int sucre_band_scatter_J(const float* J_band, const sucre_band* band_host, const int32_t* pix, int64_t target_pixels,
                                     const uint64_t* dst_ptrs_host, int n_dst, void* stream) {
     clear_error();
     SUCRE_REQUIRE(J_band && band_host && dst_ptrs_host, "sucre_band_scatter_J: null pointer");
@@ -629,7 +718,7 @@ extern "C" int sucre_band_scatter_J(const float* J_band, const sucre_band* band_
         ptrs.p[i] = dst_ptrs_host[i];
     }
     const long long floats_local = (long long)band_host->n_tiles * kTile * 3;
-    scatter_J_kernel<<<(unsigned)((floats_local + 255) / 256), 256, 0, (cudaStream_t)stream>>>(J_band, *band_host, floats_local,
+    scatter_J_kernel<<<(unsigned)((floats_local + 255) / 256), 256, 0, (cudaStream_t)stream>>>(J_band, *band_host, pix, floats_local,
                                                                                              target_pixels * 3, ptrs, n_dst);
     return check_launch("scatter_J_kernel");
 }

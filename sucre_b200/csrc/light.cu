@@ -97,6 +97,13 @@ __device__ __forceinline__ int walk_tile(const sucre_store& S, int tile, int lan
     return seen;
 }
 
+// the entry of the pixel-ordered J arrays that lane `lane` of tile `tile` owns, -1 for none
+__device__ __forceinline__ long long pixel_of(const sucre_store& S, int tile, int lane) {
+    const long long q = (long long)tile * kTile + lane;
+    if (S.pix) return (long long)__ldg(S.pix + q);
+    return q < S.pixels ? q : -1;
+}
+
 // closed-form J with the light terms (sucre.py:66-77): absorption = l e^{-beta z}, backscatter = l B (1 - e^{-gamma z})
 __global__ void __launch_bounds__(kLightThreads)
 light_J_kernel(const __grid_constant__ sucre_store S, const float* __restrict__ params, float* __restrict__ J) {
@@ -116,8 +123,8 @@ light_J_kernel(const __grid_constant__ sucre_store S, const float* __restrict__ 
             den[ch] += absorption * absorption;
         }
     });
-    const long long p = (long long)tile * kTile + lane;
-    if (p < S.pixels) {
+    const long long p = pixel_of(S, tile, lane);
+    if (p >= 0) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) J[3 * p + ch] = seen ? num[ch] / den[ch] : __int_as_float(0x7fc00000);
     }
@@ -145,9 +152,9 @@ light_sums_kernel(const __grid_constant__ sucre_store S, const float* __restrict
     for (int i = 0; i < kLightSums; ++i) s[i] = 0.f;
 
     for (int tile = blockIdx.x * kLightWarps + warp; tile < S.n_tiles; tile += gridDim.x * kLightWarps) {
-        const long long p = (long long)tile * kTile + lane;
+        const long long p = pixel_of(S, tile, lane);
         float Jp[3] = {0.f, 0.f, 0.f};
-        if (p < S.pixels) {
+        if (p >= 0) {
             Jp[0] = J[3 * p], Jp[1] = J[3 * p + 1], Jp[2] = J[3 * p + 2];
         }
         float gJ[3] = {0.f, 0.f, 0.f};
@@ -226,7 +233,7 @@ light_reduce_kernel(const double* __restrict__ partials, int n_rows, double* __r
 static int check_light_store(const sucre_store* s, const char* who) {
     SUCRE_REQUIRE(s != nullptr, "%s: null store", who);
     SUCRE_REQUIRE(s->cells && s->row_off, "%s: null pointer in store", who);
-    SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && s->pixels <= (int64_t)s->n_tiles * kTile, "%s: bad store sizes", who);
+    SUCRE_REQUIRE(s->n_tiles > 0 && s->pixels > 0 && (s->pix || s->pixels <= (int64_t)s->n_tiles * kTile), "%s: bad store sizes", who);
     SUCRE_REQUIRE(s->record_format == SUCRE_REC_P_U8 || s->record_format == SUCRE_REC_P_F32,
                   "%s: the light model needs stores with the camera-frame point (SUCRE_REC_P_U8 / SUCRE_REC_P_F32), got format %d",
                   who, s->record_format);

@@ -168,8 +168,12 @@ class CudaBandOps:
     def new_history(self, num_iter):
         return torch.empty((num_iter, 10), dtype=torch.float32, device=self.device)
 
+    def band_pixels(self):
+        """Flat image index of the pixel behind every row of band_J() (int64, -1: none)."""
+        return self.store.global_pixels()
+
     def band_J(self):
-        """(local_pixels, 3) J of this band: closed form with the final parameters, or the optimised parameter."""
+        """J of this band (store.J_shape rows): closed form with the final parameters, or the optimised parameter."""
         if not self.use_closed_form:
             return self.state.J.reshape(-1, 3)
         return engine.closed_form_J(self.store, self.state.params, self.state.J).reshape(-1, 3)
@@ -224,19 +228,27 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
     local = ops.band_J()
     if fused:
         J = peers.assemble_J(ops.store, local, root_only=root_only)
-    else:  # local sizes differ by at most one chunk: pad to the longest, gather, scatter by every rank's pixel list
+    else:  # local sizes differ by at most one chunk: pad to the longest, gather J and every rank's pixel list, scatter
         sizes = [make_band(n_tiles_total, r, world, layout) for r in range(world)]
         longest = max(b.n_tiles for b in sizes) * TILE
+        if hasattr(ops, 'band_pixels'):
+            px_local = ops.band_pixels()
+        else:
+            px_local = torch.from_numpy(band.pixels(P)).to(local.device)
         padded = torch.full((longest, 3), float('nan'), dtype=local.dtype, device=local.device)
         padded[:local.shape[0]] = local
+        px_padded = torch.full((longest,), -1, dtype=torch.int64, device=local.device)
+        px_padded[:px_local.shape[0]] = px_local
         if world > 1:
             parts = [torch.empty_like(padded) for _ in range(world)]
+            px_parts = [torch.empty_like(px_padded) for _ in range(world)]
             dist.all_gather(parts, padded, group=group)
+            dist.all_gather(px_parts, px_padded, group=group)
         else:
-            parts = [padded]
+            parts, px_parts = [padded], [px_padded]
         J = torch.empty((P, 3), dtype=local.dtype, device=local.device)
-        for b, part in zip(sizes, parts):
-            px = torch.from_numpy(b.pixels(P)).to(local.device)
-            J[px] = part[:px.shape[0]]
+        for px, part in zip(px_parts, parts):
+            ok = px >= 0
+            J[px[ok]] = part[ok]
     return BandResult(J=J.reshape(ops.height, ops.width, 3), params=ops.params(), history=history, n_obs=n_obs,
                       view_kept=view_kept, status=status, n_local=n_local)

@@ -6,6 +6,7 @@ libsucre_b200.so reached through ctypes (sucre_b200/_lib.py).  There is no CPU f
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -303,6 +304,8 @@ class ObservationStore:
     band: _lib.Band | None = None  # the tiles of the target this store covers (multi-GPU pixel sharding); None = all
     record_format: int = _lib.REC_Z_U8
     stats: dict = field(default_factory=dict)
+    pix: torch.Tensor | None = None  # (n_tiles*32,) int32: flat index in the target image of the pixel in every slot, -1 = none
+                                     # (sucre_gather_permute); None: slot 32k+i is pixel 32*band.tile(k)+i
 
     def __post_init__(self):
         if self.band is None:
@@ -324,13 +327,45 @@ class ObservationStore:
         last_global = self.band.tile(self.band.n_tiles - 1) if self.band.n_tiles else 0
         return self.band.n_tiles * TILE - max(0, (last_global + 1) * TILE - P)
 
+    @property
+    def n_slots(self) -> int:
+        return self.band.n_tiles * TILE
+
     def global_pixels(self) -> torch.Tensor:
-        """Flat index in the image of every local pixel (device int64)."""
+        """Flat index in the image of the pixel behind every row of a band's J (device int64; -1: a slot without a pixel,
+        only in permuted stores)."""
+        if self.pix is not None:
+            return self.pix.to(torch.int64)
         return torch.from_numpy(self.band.pixels(self.width * self.height)).to(self.cells.device)
 
     @property
     def J_shape(self) -> tuple:
-        return (self.local_pixels, 3) if self.is_band else (self.height, self.width, 3)
+        """Shape of the J arrays callers see: the image for a whole-image store; for a band, one row per slot of a
+        permuted store (see global_pixels) or per local pixel."""
+        if not self.is_band:
+            return (self.height, self.width, 3)
+        return (self.n_slots if self.pix is not None else self.local_pixels, 3)
+
+    @property
+    def slot_J_shape(self) -> tuple:
+        """Shape of the slot-ordered J arrays the Adam loop works on (include/sucre_b200.h, sucre_store)."""
+        return (self.n_slots, 3) if self.pix is not None else self.J_shape
+
+    @property
+    def needs_slot_copy(self) -> bool:
+        """A caller-visible J of this store (image order) is not what the Adam loop addresses (slot order)."""
+        return self.pix is not None and not self.is_band
+
+    def to_slots(self, x: torch.Tensor) -> torch.Tensor:
+        """(pixels..., c) image-ordered values -> (n_slots, c) slot order (slots without a pixel get pixel 0's values; the
+        kernels never touch them)."""
+        return x.reshape(-1, x.shape[-1])[self.pix.to(torch.int64).clamp_(min=0)].contiguous()
+
+    def from_slots(self, slots: torch.Tensor, out: torch.Tensor):
+        """Scatter (n_slots, c) slot-ordered values back into the image-ordered `out` (in place)."""
+        px = self.pix.to(torch.int64)
+        ok = px >= 0
+        out.reshape(-1, out.shape[-1])[px[ok]] = slots[ok]
 
     @property
     def kept_keys(self) -> list:
@@ -358,8 +393,16 @@ class ObservationStore:
         return self.n_obs
 
     def c_struct(self) -> _lib.SucreStore:
+        """Pixel-ordered arrays (sucre_fit_write_J's output, the light model's J) follow J_shape: image order through pix
+        for a whole-image store, slot order for a band."""
+        if self.pix is None:
+            return _lib.SucreStore(self.cells.data_ptr(), self.row_off.data_ptr(), self.n_tiles, self.record_format,
+                                   self.local_pixels, self.n_rows, None)
+        if self.is_band:
+            return _lib.SucreStore(self.cells.data_ptr(), self.row_off.data_ptr(), self.n_tiles, self.record_format,
+                                   self.n_slots, self.n_rows, None)
         return _lib.SucreStore(self.cells.data_ptr(), self.row_off.data_ptr(), self.n_tiles, self.record_format,
-                               self.local_pixels, self.n_rows)
+                               self.width * self.height, self.n_rows, self.pix.data_ptr())
 
     def record_index(self) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """(slot, pixel, view) of every record (device int64 tensors, block-major order); slot = row * 32 + lane.
@@ -375,8 +418,11 @@ class ObservationStore:
         j = cs - bits - cs_pad[self.blk_off[blk_tile]]                            # rank within the lane's column
         slot = (self.row_off[blk_tile][:, None] + j) * TILE + lanes[None, :]
         b, lane = torch.nonzero(bits, as_tuple=True)
-        gtile = torch.from_numpy(self.band.tiles()).to(dev)
-        return slot[b, lane], gtile[blk_tile[b]] * TILE + lane, self.blk_view.to(torch.int64)[b]
+        if self.pix is not None:
+            pixel = self.pix.to(torch.int64)[blk_tile[b] * TILE + lane]
+        else:
+            pixel = torch.from_numpy(self.band.tiles()).to(dev)[blk_tile[b]] * TILE + lane
+        return slot[b, lane], pixel, self.blk_view.to(torch.int64)[b]
 
     def _flat(self) -> torch.Tensor:
         return self.cells.reshape(-1, self.cells.shape[-1])
@@ -440,7 +486,7 @@ def _stream(device) -> int:
 def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
            target_record: np.ndarray | None = None, band: _lib.Band | None = None,
            reduce_counts=None, with_points: bool = False, cull_views: bool | None = None,
-           keep_mask: np.ndarray | None = None) -> ObservationStore:
+           keep_mask: np.ndarray | None = None, permute: bool | None = None) -> ObservationStore:
     """Stage 1 (see _gather_listed) behind a conservative view-level frustum pre-test: source views in which no target
     pixel can land (DeviceScene.possibly_overlapping) are not handed to the kernels at all — on a 1000-view survey a
     target overlaps a few dozen views.  Results are identical with or without it: a culled view has zero matches
@@ -451,7 +497,7 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
     if cull_views is None:
         cull_views = len(source_keys) >= 128
     kw = dict(min_cover=min_cover, keep_src=keep_src, target_record=target_record, band=band,
-              reduce_counts=reduce_counts, with_points=with_points)
+              reduce_counts=reduce_counts, with_points=with_points, permute=permute)
     if keep_mask is None and (not cull_views or len(source_keys) < 2 or target_record is not None
                               or target_key not in scene.geom):
         return _gather_listed(scene, target_key, source_keys, **kw)
@@ -473,8 +519,8 @@ def gather(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6,
 
 def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float = 1e-6, keep_src: bool = False,
                    target_record: np.ndarray | None = None, band: _lib.Band | None = None,
-                   reduce_counts=None, with_points: bool = False) -> ObservationStore:
-    """Stage 1 on the device: match -> count -> plan -> (one 40-byte D2H to size the store) -> sample.
+                   reduce_counts=None, with_points: bool = False, permute: bool | None = None) -> ObservationStore:
+    """Stage 1 on the device: match -> count -> permute -> plan -> (one 40-byte D2H to size the store) -> sample.
     Replaces Image.match_images + MatchesFile.prepare_matches + load_matches
     (sfm.py:127-138, loader.py:78-87, 103-118).
 
@@ -483,7 +529,10 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
     min_cover is a whole-image criterion (sfm.py:136).
     with_points: keep the camera-frame point cP of every observation, which the light model needs (sucre.py:57); the
     default store keeps only its norm.  Colour stays u8 in the records unless a listed view carries float colour
-    (--image-scale)."""
+    (--image-scale).
+    permute (default on; SUCRE_PERMUTE=0 turns it off): within every group of 32 tiles the pixels are dealt to the slots
+    by decreasing match count (sucre_gather_permute), which removes most sentinels from the ELL rows; the store then
+    carries the slot -> pixel map `pix`."""
     L = _lib.lib()
     dev = scene.device
     source_keys = tuple(source_keys)
@@ -514,6 +563,15 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
         _lib.check(L.sucre_gather_count(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), st), 'sucre_gather_count')
         if reduce_counts is not None:
             reduce_counts(view_count)
+        if permute is None:
+            permute = os.environ.get('SUCRE_PERMUTE', '1') != '0'
+        pix = None
+        if permute:
+            pix = torch.empty(n_tiles * TILE, dtype=torch.int32, device=dev)
+            pmasks = torch.empty_like(masks)
+            _lib.check(L.sucre_gather_permute(masks.data_ptr(), V, C.byref(band), P, pix.data_ptr(), pmasks.data_ptr(), st),
+                       'sucre_gather_permute')
+            masks = pmasks
         _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), P, float(min_cover),
                                        view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(), row_off.data_ptr(),
                                        totals.data_ptr(), st), 'sucre_gather_plan')
@@ -526,7 +584,8 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
             missing = [k for k in source_keys if k not in scene.rgb]
             if missing:
                 raise _lib.SucreError(f'gather: views without colour on the device: {missing[:3]}...')
-            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, C.byref(band), masks.data_ptr(),
+            _lib.check(L.sucre_gather_sample(tptr, table.data_ptr(), V, C.byref(band), 0 if pix is None else pix.data_ptr(),
+                                             masks.data_ptr(),
                                              view_kept.data_ptr(), row_off.data_ptr(), blk_off.data_ptr(), fmt,
                                              cells.data_ptr(), blk_mask.data_ptr(), blk_view.data_ptr(),
                                              0 if cell_src is None else cell_src.data_ptr(), st), 'sucre_gather_sample')
@@ -537,7 +596,7 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
                             n_blocks=n_blocks, n_rows=n_rows, cells=cells, row_off=row_off, blk_off=blk_off, rec_off=rec_off,
                             blk_mask=blk_mask[:n_blocks], blk_view=blk_view[:n_blocks],
                             cell_src=None if cell_src is None else cell_src[:n_rows * TILE], band=band,
-                            record_format=fmt, stats=stats)
+                            record_format=fmt, stats=stats, pix=pix)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -576,9 +635,23 @@ class FitState:
             self.J_moments.zero_()
 
     def ensure_J(self, store: 'ObservationStore'):
+        """closed-form mode: J is the loop's work buffer, in slot order; J-parameter mode: the caller's J (J_shape)."""
         if self.J is None:
-            self.J = torch.zeros(store.J_shape, dtype=torch.float32, device=store.cells.device)
-        assert tuple(self.J.shape) == store.J_shape and self.J.is_contiguous()
+            self.J = torch.zeros(store.slot_J_shape, dtype=torch.float32, device=store.cells.device)
+        want = store.slot_J_shape if self.J_moments is None else store.J_shape
+        assert tuple(self.J.shape) == want and self.J.is_contiguous(), (tuple(self.J.shape), want)
+
+    def slot_arrays(self, store: 'ObservationStore'):
+        """(J, J_moments or None, write_back) as the Adam-loop entry points address them.  Only the J-parameter mode on a
+        permuted whole-image store needs copies: its J is the user's image-ordered parameter."""
+        if self.J_moments is None or not store.needs_slot_copy:
+            return self.J, self.J_moments, lambda: None
+        J, Jm = store.to_slots(self.J), store.to_slots(self.J_moments)
+
+        def write_back():
+            store.from_slots(J, self.J)
+            store.from_slots(Jm, self.J_moments)
+        return J, Jm, write_back
 
 
 def _workspace(store: ObservationStore) -> torch.Tensor:
@@ -604,21 +677,23 @@ def fit(store: ObservationStore, state: FitState, num_iter: int, lr: float = 0.0
     dev = store.cells.device
     state.ensure_J(store)
     history = torch.empty((num_iter, 10), dtype=torch.float32, device=dev)
-    jm = 0 if state.J_moments is None else state.J_moments.data_ptr()
     with torch.cuda.device(dev):
+        J, Jm, write_back = state.slot_arrays(store)
+        jm = 0 if Jm is None else Jm.data_ptr()
         cs = store.c_struct()
         if peers is None:
             _lib.check(_lib.lib().sucre_fit(
                 state.mode, C.byref(cs), store.n_obs, state.params.data_ptr(), state.moments.data_ptr(),
-                state.J.data_ptr(), jm, state.step + 1, num_iter, float(lr), history.data_ptr(),
+                J.data_ptr(), jm, state.step + 1, num_iter, float(lr), history.data_ptr(),
                 _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit')
         else:
             ptrs = (C.c_uint64 * peers.world)(*peers.buffer_ptrs)
             _lib.check(_lib.lib().sucre_fit_sharded(
                 state.mode, C.byref(cs), int(n_obs_global), state.params.data_ptr(), state.moments.data_ptr(),
-                state.J.data_ptr(), jm, state.step + 1, num_iter, float(lr), history.data_ptr(),
+                J.data_ptr(), jm, state.step + 1, num_iter, float(lr), history.data_ptr(),
                 _workspace(store).data_ptr(), ptrs, peers.rank, peers.world, peers.take_epochs(num_iter), _stream(dev)),
                 'sucre_fit_sharded')
+        write_back()
     state.step += num_iter
     return history
 
@@ -635,13 +710,16 @@ def fit_status(store: ObservationStore) -> torch.Tensor:
 
 
 def scatter_J(store: ObservationStore, J_band: torch.Tensor, dst_ptrs: list[int]):
-    """Writes a band's J (local order) to its place in whole-image J buffers given by device address — this GPU's or
-    peers' NVLink-mapped ones (sucre_band_scatter_J)."""
+    """Writes a band's J (store.J_shape: slot order) to its place in whole-image J buffers given by device address — this
+    GPU's or peers' NVLink-mapped ones (sucre_band_scatter_J)."""
     dev = store.cells.device
     ptrs = (C.c_uint64 * len(dst_ptrs))(*dst_ptrs)
+    assert J_band.shape[0] == (store.n_slots if store.pix is not None else store.local_pixels)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().sucre_band_scatter_J(J_band.data_ptr(), C.byref(store.band), store.width * store.height, ptrs,
-                                                   len(dst_ptrs), _stream(dev)), 'sucre_band_scatter_J')
+        _lib.check(_lib.lib().sucre_band_scatter_J(J_band.data_ptr(), C.byref(store.band),
+                                                   0 if store.pix is None else store.pix.data_ptr(),
+                                                   store.width * store.height, ptrs, len(dst_ptrs), _stream(dev)),
+                   'sucre_band_scatter_J')
 
 
 def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs_global: int | None = None,
@@ -652,11 +730,12 @@ def fit_sums(store: ObservationStore, state: FitState, sums: torch.Tensor, n_obs
     state.ensure_J(store)
     with torch.cuda.device(dev):
         cs = store.c_struct()
+        J, Jm, write_back = state.slot_arrays(store)
         _lib.check(_lib.lib().sucre_fit_sums(
-            state.mode, C.byref(cs), state.params.data_ptr(), state.J.data_ptr(),
-            0 if state.J_moments is None else state.J_moments.data_ptr(),
+            state.mode, C.byref(cs), state.params.data_ptr(), J.data_ptr(), 0 if Jm is None else Jm.data_ptr(),
             store.n_obs if n_obs_global is None else n_obs_global, state.step + 1, float(lr), sums.data_ptr(),
             _workspace(store).data_ptr(), _stream(dev)), 'sucre_fit_sums')
+        write_back()
 
 
 def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, history_row: torch.Tensor | None = None):
@@ -669,11 +748,13 @@ def adam_step(state: FitState, sums: torch.Tensor, n_obs: int, lr: float, histor
 
 
 def closed_form_J(store: ObservationStore, params: torch.Tensor, J_ref: torch.Tensor | None = None) -> torch.Tensor:
-    """update_J (sucre.py:66-77) with the given parameters: (H,W,3) f32 on the device, NaN where unobserved."""
+    """update_J (sucre.py:66-77) with the given parameters: store.J_shape f32 on the device, NaN where unobserved.
+    J_ref: the work buffer of a closed-form fit (slot order), the reference point of the statistics."""
     dev = store.cells.device
     J = torch.empty(store.J_shape, dtype=torch.float32, device=dev)
     if store.n_obs == 0:
         return J.fill_(float('nan'))
+    assert J_ref is None or tuple(J_ref.shape) == store.slot_J_shape, 'J_ref is the closed-form work buffer (slot order)'
     with torch.cuda.device(dev):
         cs = store.c_struct()
         _lib.check(_lib.lib().sucre_fit_write_J(C.byref(cs), params.data_ptr(), 0 if J_ref is None else J_ref.data_ptr(),

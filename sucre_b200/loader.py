@@ -201,7 +201,7 @@ class MatchesFile:
                  blk_off=s.blk_off.cpu().numpy(), row_off=s.row_off.cpu().numpy(), blk_mask=s.blk_mask.cpu().numpy(),
                  blk_view=s.blk_view.cpu().numpy(),
                  cell_src=np.zeros(0, np.int32) if s.cell_src is None else s.cell_src.cpu().numpy(),
-                 record_format=s.record_format)
+                 record_format=s.record_format, pix=np.zeros(0, np.int32) if s.pix is None else s.pix.cpu().numpy())
         self.path.touch()  # the reference's file name marks "matches exist" (sucre.py:185)
 
     def unlink(self):
@@ -223,4 +223,4 @@ class MatchesFile:
             n_blocks=int(z['blk_mask'].shape[0]), n_rows=int(z['row_off'][-1]), cells=t(z['cells']),
             rec_off=t(z['rec_off']), blk_off=t(z['blk_off']), row_off=t(z['row_off']), blk_mask=t(z['blk_mask']),
             blk_view=t(z['blk_view']), cell_src=t(z['cell_src']) if z['cell_src'].size else None,
-            record_format=int(z['record_format']))
+            record_format=int(z['record_format']), pix=t(z['pix']) if 'pix' in z.files and z['pix'].size else None)

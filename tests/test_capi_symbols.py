@@ -35,9 +35,10 @@ def test_store_struct_and_record_formats_match_header():
         assert f'#define SUCRE_REC_{name} {fmt}' in header
         assert L.sucre_record_bytes(fmt) == _lib.RECORD_BYTES[fmt]
     assert L.sucre_record_bytes(17) == 0
-    assert ctypes.sizeof(_lib.SucreStore) == 40 and 'sizeof == 40' in header
-    assert [getattr(_lib.SucreStore, f).offset for f in ('cells', 'row_off', 'n_tiles', 'record_format', 'pixels', 'n_rows')] \
-        == [0, 8, 16, 20, 24, 32]
+    assert ctypes.sizeof(_lib.SucreStore) == 48 and 'sizeof == 48' in header
+    assert [getattr(_lib.SucreStore, f).offset for f in ('cells', 'row_off', 'n_tiles', 'record_format', 'pixels', 'n_rows', 'pix')] \
+        == [0, 8, 16, 20, 24, 32, 40]
+    assert f'#define SUCRE_GROUP_TILES {_lib.GROUP_TILES}' in header
 
 
 def test_pinhole_flags_come_from_the_values():

@@ -94,6 +94,50 @@ def test_view_culling_changes_nothing():
     assert helpers.compare_store_with_oracle(a, kept) == dict(idx=0, z=0, I=0, n=a.n_obs)
 
 
+@pytest.mark.parametrize('shape', [(7, 150, 101), (5, 64, 48), (9, 320, 240)])
+def test_slot_permutation_changes_only_the_layout(shape):
+    """sucre_gather_permute deals the pixels of every 32-tile group to the slots by observation count: the store then
+    holds the same records (per view, in target order), every pixel exactly once in `pix`, columns of non-increasing
+    height inside a group, fewer rows — and the fit gives the same J and parameters up to fp32 summation order."""
+    V, W, H = shape
+    scene = SyntheticScene(V, W, H, seed=21)
+    ds, host = helpers.build_device_scene(scene, range(V))
+    keys = list(range(V))
+    t = V // 2
+    a = engine.gather(ds, t, keys, keep_src=True, permute=True)
+    b = engine.gather(ds, t, keys, keep_src=True, permute=False)
+    assert a.pix is not None and b.pix is None and a.n_obs == b.n_obs and a.n_rows <= b.n_rows
+    assert np.array_equal(a.view_count, b.view_count) and np.array_equal(a.view_kept, b.view_kept)
+    pix = a.pix.cpu().numpy()
+    assert pix.shape == (a.n_tiles * 32,) and np.array_equal(np.sort(pix[pix >= 0]), np.arange(W * H))
+    la, lb = a.to_reference_layout(), b.to_reference_layout()
+    assert la.keys() == lb.keys()
+    for key in la:
+        for f in ('u1', 'v1', 'u2', 'v2', 'z', 'I'):
+            assert np.array_equal(la[key][f], lb[key][f]), (key, f)
+    # column heights: non-increasing over the slots of a group (count over ALL listed views decides; here all are kept)
+    if a.view_kept.all():
+        _, pixel, _ = a.record_index()
+        cnt = torch.bincount(pixel, minlength=W * H).cpu().numpy()
+        per_slot = np.where(pix >= 0, cnt[np.maximum(pix, 0)], -1)
+        for g in range(0, len(per_slot), 1024):
+            grp = per_slot[g:g + 1024]
+            assert (np.diff(grp) <= 0).all(), g
+    kept, _ = helpers.oracle_gather(host, t, keys)
+    assert helpers.compare_store_with_oracle(a, kept) == dict(idx=0, z=0, I=0, n=a.n_obs)
+    for closed in (True, False):
+        out = []
+        for store in (a, b):
+            J0 = None if closed else ds.rgb_float(t)
+            st = engine.FitState.initial(ds.device, J0=J0)
+            hist = engine.fit(store, st, 30)
+            J = engine.closed_form_J(store, st.params, st.J) if closed else st.J
+            out.append((hist.cpu().numpy(), J.cpu().numpy()))
+        assert np.allclose(out[0][0], out[1][0], rtol=2e-5, atol=1e-7)
+        assert np.array_equal(np.isnan(out[0][1]), np.isnan(out[1][1]))
+        assert np.nanmax(np.abs(out[0][1] - out[1][1])) < 2e-5
+
+
 def test_degenerate_inputs_follow_the_reference_rules():
     """NaN pose -> every comparison false -> no match (the reference's .long() of NaN is INT64_MIN, rejected);
     a target without any valid depth -> nothing to restore; oversized images are refused (int16 indices)."""

@@ -52,6 +52,13 @@ import ctypes as C  # noqa: E402
 band = store.band
 mn, av, _ = timed(lambda: L.sucre_gather_match(trec.ctypes.data, table.data_ptr(), V, C.byref(band), masks.data_ptr(), 0, st))
 print(f'  match kernel: min {mn:.3f} ms avg {av:.3f}')
+pix = torch.empty(nt * 32, dtype=torch.int32, device='cuda')
+pmasks = torch.empty_like(masks)
+permuted = store.pix is not None
+if permuted:
+    mn, av, _ = timed(lambda: L.sucre_gather_permute(masks.data_ptr(), V, C.byref(band), W * H, pix.data_ptr(), pmasks.data_ptr(), st))
+    print(f'  permute kernel: min {mn:.3f} ms avg {av:.3f}')
+    masks = pmasks
 vc = torch.empty(V, dtype=torch.int64, device='cuda')
 vk = torch.empty(V, dtype=torch.uint8, device='cuda')
 ro, bo, wo = (torch.empty(nt + 1, dtype=torch.int64, device='cuda') for _ in range(3))
@@ -63,7 +70,8 @@ print(f'  count + plan kernels: min {mn:.3f} ms avg {av:.3f}')
 cells = torch.empty_like(store.cells)
 bm = torch.empty(max(1, store.n_blocks), dtype=torch.int32, device='cuda')
 bv = torch.empty_like(bm)
-mn, av, _ = timed(lambda: L.sucre_gather_sample(trec.ctypes.data, table.data_ptr(), V, C.byref(band), masks.data_ptr(), vk.data_ptr(),
+mn, av, _ = timed(lambda: L.sucre_gather_sample(trec.ctypes.data, table.data_ptr(), V, C.byref(band), pix.data_ptr() if permuted else 0,
+                                                masks.data_ptr(), vk.data_ptr(),
                                                 wo.data_ptr(), bo.data_ptr(), store.record_format, cells.data_ptr(),
                                                 bm.data_ptr(), bv.data_ptr(), 0, st))
 print(f'  sample kernel: min {mn:.3f} ms avg {av:.3f}  ({store.stream_bytes/mn/1e6:.0f} GB/s of rows written)')
