@@ -372,12 +372,16 @@ scan_kernel(long long* __restrict__ a, long long* __restrict__ b, long long* __r
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     long long carry[3] = {0, 0, 0};
     long long* arr[3] = {a, b, c};
+    long long nxt[3];   // the next round's elements are requested a round ahead: their latency hides behind this round
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nxt[k] = t < n ? arr[k][t] : 0;
     for (int base = 0; base < n; base += 1024) {
         const int i = base + t;
         long long v[3], incl[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            v[k] = i < n ? arr[k][i] : 0;
+            v[k] = nxt[k];
+            nxt[k] = i + 1024 < n ? arr[k][i + 1024] : 0;
             incl[k] = v[k];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
