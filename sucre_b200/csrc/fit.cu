@@ -1,10 +1,11 @@
 // Stage 2 — per-pixel fit of the underwater image formation model for sm_100a.
 //
-// One warp owns a run of tiles (32 consecutive target pixels each), one lane one pixel.  The observation store is
-// a stream of ELL ROWS (include/sucre_b200.h): row j of a tile holds, for every lane, the j-th observation of its
-// pixel or an all-zero sentinel; a tile has as many rows as its fullest pixel has observations.  A row is one
-// coalesced, bank-conflict-free 256-byte access (8-byte records {z, u8 r, g, b}), every lane of the warp walks the
-// same rows, and there is nothing to decode: no headers, offsets or masks in the inner loop.
+// One warp owns a run of tiles (32 slots each), one lane one slot = one target pixel (the pixel behind a slot is the
+// store's business: sucre_gather_permute deals pixels to slots by observation count; the loop never needs to know).
+// The observation store is a stream of ELL ROWS (include/sucre_b200.h): row j of a tile holds, for every lane, the
+// j-th observation of its pixel or an all-zero sentinel; a tile has as many rows as its fullest pixel has
+// observations.  A row is one coalesced, bank-conflict-free 256-byte access (8-byte records {z, u8 r, g, b}), every
+// lane of the warp walks the same rows, and there is nothing to decode: no headers, offsets or masks in the inner loop.
 //
 // Every Adam iteration reads every row exactly ONCE.  The reference makes two passes (update_J, then
 // forward/backward with J held constant, sucre.py:141-146); here both come out of one sweep through per-pixel
@@ -28,11 +29,12 @@
 // adds them before finalising the pixel — so the per-warp work differs by one row at most, whatever the tile sizes,
 // and the summation order stays fixed (bit-reproducible results run to run).
 //
-// Global sums: per-pixel values are promoted to double per thread, reduced by warp shuffles, one double row per
-// CTA; the last CTA to finish (ticket counter) reduces the rows in a fixed order and applies torch.optim.Adam's
-// update to the 9 scalars, so an iteration is ONE kernel and 200 iterations need no host round trip.  Inside the
-// Adam loop the launches are chained with programmatic dependent launch, and for a target sharded over several
-// GPUs the all-reduce of the sums runs inside the last CTA over NVLink peer memory (sucre_fit_sharded).
+// Global sums and the loop: a thread's partial sums are fp32 over its handful of tiles, then double: warp shuffles, one
+// row of ten doubles per CTA.  The grid (one CTA per SM) is resident and runs ALL iterations of a call: every CTA
+// publishes its row as tagged 8-byte words, polls all rows, reduces them in a fixed order and applies
+// torch.optim.Adam's update to its own shared-memory copy of the 9 scalars — 200 iterations are one launch, with no
+// host round trip and no CTA waiting for another one's result.  For a target sharded over several GPUs the all-reduce
+// of the rank totals runs inside the same kernel over NVLink peer memory (sucre_fit_sharded).
 #include "common.cuh"
 
 namespace sucre {
@@ -355,7 +357,7 @@ struct FitArgs {
     long long pixels;          // entries of the slot-ordered J arrays (J, J_moments)
     const int* pix;            // write-J: slot -> entry of J_out (nullptr: the identity, bounded by out_pixels)
     long long out_pixels;
-    float* params;         // 9: B, beta, gamma (read at the start of every iteration; written by the last CTA when do_step)
+    float* params;         // 9: B, beta, gamma (read when the launch starts; written by CTA 0 when it ends, if do_step)
     float* moments;        // 18: Adam state of the 9 scalars
     float* J;              // pixels*3: Jref (closed form, in/out), the J parameter (in/out), or Jref (write-J, may be null)
     float* J_out;          // pixels*3: write-J mode output
@@ -364,13 +366,13 @@ struct FitArgs {
     const int* part_tile;       // per global warp: first tile it owns (finalises); [n_warps] = n_tiles
     unsigned long long* rows;   // [2][kMaxFitCtas][kLLWords] tagged words: the CTAs' rows of partial sums
     unsigned* ticket;      // ticket[1] = status bits, ticket[2] = tag base (iterations run on this workspace so far)
-    double* sums_out;      // if non-null the last CTA stores the reduced sums here
+    double* sums_out;      // if non-null CTA 0 stores the reduced sums here
     float* history;        // if non-null: num_iter rows of {params after the step [9], cost}
-    int do_step;           // apply Adam to the 9 scalars in the last CTA
+    int do_step;           // apply Adam to the 9 scalars (every CTA, on its own copy)
     int num_iter;          // iterations this launch runs (the grid stays resident and meets at a flag between them)
     const AdamScalars* adam_tab;   // num_iter entries (device)
     // pixel-band sharding over several GPUs: one-shot all-reduce of the 10 sums over NVLink peer memory, fused
-    // into the last CTA (world == 1: single GPU, nothing exchanged)
+    // into the loop (world == 1: single GPU, nothing exchanged)
     int rank, world;
     unsigned epoch;                           // tag of the first iteration; unique and increasing on every rank
     unsigned long long peer[SUCRE_MAX_PEERS]; // peer[p] = address of rank p's exchange buffer (PeerSlot[2][SUCRE_MAX_PEERS])
@@ -552,7 +554,7 @@ fit_kernel(const __grid_constant__ FitArgs A) {
         SUCRE_TRACE(0);
 
         // per-thread partial sums of the ten global sums: fp32 over this warp's tiles (a few dozen per-pixel values,
-        // each itself an fp32 sum), promoted to double for everything that follows (warp tree, CTA row, last CTA, peers)
+        // each itself an fp32 sum), promoted to double for everything that follows (warp tree, CTA row, rows of all CTAs, peers)
         float acc[kSums];
 #pragma unroll
         for (int i = 0; i < kSums; ++i) acc[i] = 0.f;
