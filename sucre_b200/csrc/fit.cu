@@ -334,6 +334,49 @@ struct PixelStats {
         }
     }
 
+    // A single row (the odd last row of a tile): red + green packed as in add(), blue in scalar arithmetic on the
+    // even-row halves of Q — about half the instructions of a step whose second row would be an all-zero record.
+    __device__ __forceinline__ void add_one(const Obs r, const Consts& k, const u64 nJ_rg, const float nJ_b) {
+        const u64 one = pk(1.0f, 1.0f), neg = pk(-1.0f, -1.0f);
+        const float w = r.z != 0.0f ? 1.0f : 0.0f;
+        {
+            const u64 zz = pk(r.z, r.z);
+            const u64 a = mul2(exp2_pair(mul2(k.kb_rg, zz)), pk(w, w));
+            const u64 g = exp2_pair(mul2(k.kg_rg, zz));
+            const u64 h = fma2(g, neg, one);
+            u64 x = pk(r.x[0], r.x[1]);
+            if (RecTraits<REC>::kBias != 0.0f) x = add2(x, pk(RecTraits<REC>::kBias, RecTraits<REC>::kBias));
+            const u64 D = fma2(k.nB_rg, h, x);
+            const u64 Dp = fma2(nJ_rg, a, D);
+            accumulate(P, Dp, a, g, h, zz);
+        }
+        {
+            const float z = r.z;
+            const float a = (PRECISE ? expf(k.kb_b * z) : fast_exp2(k.kb_b * z)) * w;
+            const float g = PRECISE ? expf(k.kg_b * z) : fast_exp2(k.kg_b * z);
+            const float h = 1.0f - g;
+            const float x = r.x[2] + RecTraits<REC>::kBias;
+            const float Dp = fmaf(nJ_b, a, fmaf(k.nB_b, h, x));
+            float q[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) q[i] = lo(Q[i]);
+            q[0] = fmaf(Dp, a, q[0]);
+            q[1] = fmaf(a, a, q[1]);
+            if (MODE != kWriteJ) {
+                const float Dz = Dp * z, az = a * z;
+                q[2] = fmaf(Dp, h, q[2]);
+                q[3] = fmaf(a, h, q[3]);
+                q[4] = fmaf(Dz, a, q[4]);
+                q[5] = fmaf(az, a, q[5]);
+                q[6] = fmaf(Dz, g, q[6]);
+                q[7] = fmaf(az, g, q[7]);
+                q[8] = fmaf(Dp, Dp, q[8]);
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Q[i] = pk(q[i], hi(Q[i]));
+        }
+    }
+
     // parked form: kStats floats per lane, [9 * c + k][lane]
     __device__ __forceinline__ void park(float* slot, int lane) const {
 #pragma unroll
@@ -623,7 +666,11 @@ fit_kernel(const __grid_constant__ FitArgs A) {
                     const Raw q0 = *reinterpret_cast<const Raw*>(lane_ring + roff);
                     roff = (roff + kRowBytes) & (kRingBytes - 1);
                     seen_bits |= __float_as_uint(RT::range(q0));
+#if defined(SUCRE_FIT_ODD_AS_PAIR)
                     st.add(RT::unpack(q0), RT::unpack(Raw{}), kc, nJ_rg, nJ_b);
+#else
+                    st.add_one(RT::unpack(q0), kc, nJ_rg, nJ_b);
+#endif
                     pos = r + 1;
                     if (pos >= release_at) release();
                 }
