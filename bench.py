@@ -475,14 +475,24 @@ def ours_pixel_sharded(ctx):
     ms_step, ms_single, parity, res = sharded_block(ctx, ctx['resident'], ctx['keys'], target, args.num_iter, args.steps, warm, peers, sdist)
     clocks = sampler.stop() if sampler else None
 
-    # end to end: every rank copies what ITS band needs from pinned host memory, restores, rank 0 reads J back
-    J_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+    # end to end: every rank copies what ITS band needs from pinned host memory, restores, rank 0 reads J back; the
+    # copies of step k+1 / k-1 overlap the fit of step k (api.restore_stream_sharded); one blocking call per step beside it
+    J_pair = [torch.empty((H, W, 3), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+
+    def stream_host(n):
+        last = None
+        for last in api.restore_stream_sharded(ctx['host'], [target] * n, ctx['keys'], device=dev, peers=peers, out_J=J_pair,
+                                               upload=args.upload, **ctx['kw']):
+            pass
+        return last
 
     def step_host():
-        return api.restore_from_host_sharded(ctx['host'], target, ctx['keys'], device=dev, peers=peers, out_J=J_host,
-                                             upload=args.upload, **ctx['kw'])
+        return api.restore_from_host_sharded(ctx['host'], target, ctx['keys'], device=dev, peers=peers,
+                                             out_J=None if J_pair is None else J_pair[0], upload=args.upload, **ctx['kw'])
+    ctx['run_steps'](stream_host, 1, 3)
+    ms_e2e, res_h = ctx['run_steps'](stream_host, 1, args.steps)
     ctx['run_steps'](step_host, 2)
-    ms_e2e, res_h = ctx['run_steps'](step_host, args.steps)
+    ms_single_call, _ = ctx['run_steps'](step_host, args.steps)
     h2d = torch.tensor([res_h.h2d_bytes], dtype=torch.int64, device=dev)
     import torch.distributed as dist
     dist.all_reduce(h2d)
@@ -509,7 +519,10 @@ def ours_pixel_sharded(ctx):
         'parity': parity,
         'e2e': {'value': V * W * H / (ms_e2e / args.steps / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d.item()),
                 'd2h_bytes_per_step': H * W * 3 * 4 + 9 * 4 + args.num_iter * 10 * 4, 's_per_restored_image': ms_e2e / args.steps / 1e3,
-                'api': 'sucre_b200.api.restore_from_host_sharded (every rank uploads the rectangles its band can see; J + parameters read back on rank 0)'},
+                'api': 'sucre_b200.api.restore_stream_sharded (every rank uploads the rectangles its band can see; J + parameters '
+                       'read back on rank 0; double-buffered: the copies of step k+1 / k-1 overlap the fit of step k)',
+                'single_call': {'s_per_restored_image': ms_single_call / args.steps / 1e3,
+                                'api': 'sucre_b200.api.restore_from_host_sharded, one blocking call per step (no overlap across steps)'}},
         'gpu_launches': args.steps * world * api.LAUNCHES_PER_BAND,
         'target_parallel': tp,
         'clocks': clocks,

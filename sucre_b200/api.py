@@ -211,6 +211,106 @@ def _finish(pending) -> RestoreResult:
                          view_kept=res.view_kept, h2d_bytes=h2d)
 
 
+def _band_rects(host: HostScene, target: int, needed: list, rank: int, world: int, upload: str) -> np.ndarray:
+    """Per view of `needed`, the rectangle rank `rank` of `world` must hold to restore its (contiguous) band of `target`:
+    the band's rows of the target itself and the footprint of that band in every view."""
+    from . import dist as sdist
+    g = host.geoms[target]
+    if upload == 'full':
+        return np.array([[0, 0, host.geoms[i].width, host.geoms[i].height] for i in needed], dtype=np.int32)
+    n_tiles = (g.width * g.height + engine.TILE - 1) // engine.TILE
+    lo, n = sdist.tile_band(n_tiles, rank, world)   # contiguous bands: a rank then needs a small part of every source view
+    v0, v1 = lo * engine.TILE // g.width, min(g.height, ((lo + n) * engine.TILE - 1) // g.width + 1)
+    rects = engine.DeviceScene.footprints(g, host_depth_range(host.depth[target]), None, rows_only=upload == 'rows',
+                                          stacks=host.projection_stacks(needed), band_rows=(v0, v1))
+    t = needed.index(target)   # the target is read as the target (its band's rows) and as a source (its footprint)
+    ft = rects[t]
+    rects[t] = [0, min(v0, int(ft[1])) if ft[3] > ft[1] else v0, g.width, max(v1, int(ft[3]))]
+    return rects
+
+
+def restore_stream_sharded(host: HostScene, targets, sources=None, *, device='cuda', peers=None, upload: str = 'footprint',
+                           out_J=None, min_cover: float = 1e-6, use_closed_form: bool = True, num_iter: int = 200,
+                           lr: float = 0.05, params=None):
+    """restore_stream for targets sharded over all ranks of the default process group (a COLLECTIVE generator: every rank
+    iterates it in step).  Per rank two device scene buffers and a copy stream: while the ranks fit their bands of target
+    k, every rank's rectangles for target k+1 are already crossing PCIe and rank 0 reads J of target k-1 back.  Yields a
+    RestoreResult per target (J on rank 0 only), the same as restore_from_host_sharded's bit for bit.
+    out_J: optional list of two pinned (H,W,3) float32 tensors rank 0's results alternate between."""
+    import torch.distributed as tdist
+    from . import dist as sdist
+    targets = list(targets)
+    if not targets:
+        return
+    sources = list(range(len(host.geoms))) if sources is None else list(sources)
+    world = tdist.get_world_size() if tdist.is_initialized() else 1
+    rank = tdist.get_rank() if tdist.is_initialized() else 0
+    dev = torch.device(device)
+    needed = sorted(set(sources) | set(targets))
+    geoms = [host.geoms[i] for i in needed]
+    assert all(g.width == geoms[0].width and g.height == geoms[0].height for g in geoms), 'restore_stream_sharded needs equally sized views'
+    copy_stream = torch.cuda.Stream(dev)
+    compute = torch.cuda.current_stream(dev)
+    scenes, planes = [], []
+    for _ in range(2):
+        sc = engine.DeviceScene(dev)
+        planes.append(sc.allocate_views(needed, geoms, host.depth.dtype))
+        scenes.append(sc)
+    uploaded = [torch.cuda.Event() for _ in targets]
+    consumed = [torch.cuda.Event() for _ in targets]
+    h2d = [0] * len(targets)
+
+    def start_upload(k):
+        rects = _band_rects(host, targets[k], needed, rank, world, upload)
+        with torch.cuda.stream(copy_stream):
+            if k >= 2:
+                copy_stream.wait_event(consumed[k - 2])
+            h2d[k] = scenes[k % 2].upload_rects(planes[k % 2], host.depth, host.rgb, needed, rects)
+            uploaded[k].record(copy_stream)
+
+    def finish(pending):
+        res, J_host, small, done, nbytes = pending
+        done.synchronize()
+        if small[-1] != 0:
+            raise engine._lib.SucreError('restore_stream_sharded: a peer went silent during the in-kernel all-reduce')
+        return RestoreResult(J=J_host, params=small[:9].clone(), history=small[9:-1].reshape(-1, 10).clone(), n_obs=res.n_obs,
+                             view_kept=res.view_kept, h2d_bytes=nbytes)
+
+    pending = None
+    start_upload(0)
+    for k, t in enumerate(targets):
+        if k + 1 < len(targets):
+            start_upload(k + 1)
+        compute.wait_event(uploaded[k])
+        ops = sdist.CudaBandOps(scenes[k % 2], t, sources, use_closed_form=use_closed_form)
+        res = sdist.restore_band_sharded(ops, min_cover=min_cover, num_iter=num_iter, lr=lr, params=params, peers=peers,
+                                         root_only=peers is not None, layout='contiguous')
+        consumed[k].record(compute)
+        if pending is not None:
+            yield finish(pending)
+        status = torch.zeros(1, device=dev) if res.status is None else res.status.to(torch.float32).reshape(1)
+        small_dev = torch.cat([res.params, res.history.reshape(-1), status])
+        small = torch.empty(small_dev.shape, dtype=torch.float32).pin_memory()
+        J_host = J_dev = None
+        if rank == 0:
+            # the assembled J lives in the symmetric buffer every rank writes the NEXT target into: a device copy (microseconds)
+            # is what crosses PCIe while the next target is fitted
+            J_dev = res.J.clone()
+            J_host = out_J[k % 2] if out_J is not None else torch.empty(tuple(J_dev.shape), dtype=torch.float32).pin_memory()
+        ready, done = torch.cuda.Event(), torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            if J_dev is not None:
+                J_host.copy_(J_dev, non_blocking=True)
+                J_dev.record_stream(copy_stream)
+            small.copy_(small_dev, non_blocking=True)
+            done.record(copy_stream)
+        small_dev.record_stream(copy_stream)
+        pending = (res, J_host, small, done, h2d[k])
+    yield finish(pending)
+
+
 def restore_from_host_sharded(host: HostScene, target: int, sources=None, *, device='cuda', peers=None,
                               out_J: torch.Tensor | None = None, upload: str = 'footprint', min_cover: float = 1e-6,
                               use_closed_form: bool = True, num_iter: int = 200, lr: float = 0.05, params=None) -> RestoreResult:
@@ -223,20 +323,9 @@ def restore_from_host_sharded(host: HostScene, target: int, sources=None, *, dev
     sources = list(range(len(host.geoms))) if sources is None else list(sources)
     world = tdist.get_world_size() if tdist.is_initialized() else 1
     rank = tdist.get_rank() if tdist.is_initialized() else 0
-    g = host.geoms[target]
-    n_tiles = (g.width * g.height + engine.TILE - 1) // engine.TILE
-    lo, n = sdist.tile_band(n_tiles, rank, world)   # contiguous bands: a rank then needs a small part of every source view
-    v0, v1 = lo * engine.TILE // g.width, min(g.height, ((lo + n) * engine.TILE - 1) // g.width + 1)
     needed = sorted(set(sources) | {target})
     scene = engine.DeviceScene(device)
-    if upload == 'full':
-        rects = np.array([[0, 0, host.geoms[i].width, host.geoms[i].height] for i in needed], dtype=np.int32)
-    else:
-        rects = engine.DeviceScene.footprints(g, host_depth_range(host.depth[target]), None, rows_only=upload == 'rows',
-                                              stacks=host.projection_stacks(needed), band_rows=(v0, v1))
-        t = needed.index(target)   # the target is read as the target (its band's rows) and as a source (its footprint)
-        ft = rects[t]
-        rects[t] = [0, min(v0, int(ft[1])) if ft[3] > ft[1] else v0, g.width, max(v1, int(ft[3]))]
+    rects = _band_rects(host, target, needed, rank, world, upload)
     d, c = scene.allocate_views(needed, [host.geoms[i] for i in needed], host.depth.dtype)
     h2d = scene.upload_rects((d, c), host.depth, host.rgb, needed, rects)
     ops = sdist.CudaBandOps(scene, target, sources, use_closed_form=use_closed_form)

@@ -134,3 +134,45 @@ def test_band_sharded_matches_single_gpu(closed_form, fused, empty_band):
     assert np.max(np.abs(z['params'] - p1) / np.abs(p1)) < 1e-5
     J1 = one.J.cpu().numpy()
     assert np.array_equal(np.isnan(z['J']), np.isnan(J1)) and np.nanmax(np.abs(z['J'] - J1)) < 1e-5
+
+
+def _stream_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from test_footprint import _host_scene
+        scene = SyntheticScene(10, 320, 240, seed=11)
+        views = list(range(10))
+        host, _ = _host_scene(scene, views)
+        host = host.pin()
+        dev = f'cuda:{rank}'
+        peers = sdist.PeerExchange(torch.device(dev))
+        kw = dict(device=dev, peers=peers, num_iter=12, use_closed_form=True)
+        targets = [4, 7, 2, 4]
+        singles = [api.restore_from_host_sharded(host, t, views, **kw) for t in targets]
+        got = list(api.restore_stream_sharded(host, targets, views, **kw))
+        assert len(got) == len(targets)
+        for a, b in zip(singles, got):
+            assert a.n_obs == b.n_obs and a.h2d_bytes == b.h2d_bytes
+            assert torch.equal(a.params.view(torch.int32), b.params.view(torch.int32))
+            assert torch.equal(a.history.view(torch.int32), b.history.view(torch.int32))
+            if rank == 0:
+                assert torch.equal(a.J.view(torch.int32), b.J.reshape(a.J.shape).view(torch.int32))
+            else:
+                assert b.J is None
+        if rank == 0:
+            np.savez(out_path, ok=1)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+def test_sharded_stream_matches_single_calls():
+    """api.restore_stream_sharded (per-rank double-buffered uploads, read-back on rank 0 overlapped with the next target)
+    yields, target after target and bit for bit, what api.restore_from_host_sharded returns."""
+    world = 2
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, 'ok.npz')
+        mp.spawn(_stream_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert os.path.exists(out)
