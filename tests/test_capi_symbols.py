@@ -57,6 +57,12 @@ def test_argument_errors_without_gpu():
     assert L.sucre_gather_plan(0, 1, 1, 0, 1, 0.0, 0, 0, 0, 0, 0, 0) != 0
     assert b'null' in L.sucre_last_error()
     assert L.sucre_adam_step(0, 0, 0, 1, 1, 0.05, 0, 0) != 0
+    assert L.sucre_gather_permute(0, 1, 0, 1, 0, 0, 0) != 0 and b'null' in L.sucre_last_error()
+    band = _lib.Band.whole(4)
+    import ctypes as C
+    buf = (C.c_uint32 * 8)()
+    assert L.sucre_gather_permute(buf, 1, C.byref(band), 128, buf, buf, 0) != 0 and b'alias' in L.sucre_last_error()
+    assert L.sucre_gather_permute(buf, 1 << 21, C.byref(band), 128, buf, (C.c_uint32 * 8)(), 0) != 0 and b'sizes' in L.sucre_last_error()
 
 
 def test_product_never_imports_the_oracle():
