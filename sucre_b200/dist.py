@@ -229,8 +229,10 @@ def restore_band_sharded(ops, *, min_cover: float = 1e-6, num_iter: int = 200, l
     if fused:
         J = peers.assemble_J(ops.store, local, root_only=root_only)
     else:  # local sizes differ by at most one chunk: pad to the longest, gather J and every rank's pixel list, scatter
-        sizes = [make_band(n_tiles_total, r, world, layout) for r in range(world)]
-        longest = max(b.n_tiles for b in sizes) * TILE
+        rows = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        if world > 1:
+            dist.all_reduce(rows, op=dist.ReduceOp.MAX, group=group)
+        longest = int(rows.item())
         if hasattr(ops, 'band_pixels'):
             px_local = ops.band_pixels()
         else:

@@ -129,12 +129,34 @@ class OracleBandOps:
         return torch.from_numpy(self.p.copy())
 
 
-def _worker(rank, world, port, case, out_path):
+class SlotOrderedBandOps(OracleBandOps):
+    """Like a CudaBandOps on a permuted store: the band's J comes in SLOT order — the band's pixels shuffled, with a few
+    slots that hold no pixel — and band_pixels() tells restore_band_sharded which image pixel every row belongs to."""
+
+    def _slots(self):
+        n = len(self.px)
+        rng = np.random.default_rng(n)
+        order = np.concatenate([rng.permutation(n), np.full(5, -1)])
+        return order[rng.permutation(len(order))]
+
+    def band_pixels(self):
+        o = self._slots()
+        return torch.from_numpy(np.where(o >= 0, self.px[np.maximum(o, 0)], -1).astype(np.int64))
+
+    def band_J(self):
+        o = self._slots()
+        J = self._J().astype(np.float32)[np.maximum(o, 0)]
+        J[o < 0] = 123.0   # a slot without a pixel: whatever it holds must never reach the image
+        return torch.from_numpy(J)
+
+
+def _worker(rank, world, port, case, out_path, slot_order=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         g = Golden(case)
-        res = sdist.restore_band_sharded(OracleBandOps(g), min_cover=float(g['min_cover']), num_iter=int(g['num_iter']))
+        ops = SlotOrderedBandOps(g) if slot_order else OracleBandOps(g)
+        res = sdist.restore_band_sharded(ops, min_cover=float(g['min_cover']), num_iter=int(g['num_iter']))
         gathered = [None] * world
         dist.all_gather_object(gathered, res.params.numpy().tolist())
         assert all(p == gathered[0] for p in gathered)  # every rank holds identical parameters
@@ -145,13 +167,15 @@ def _worker(rank, world, port, case, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('case,world', [('tiny6_closed', 2), ('mixed8_image0004', 2), ('tiny6_closed', 3)])
-def test_band_sharded_restore_over_gloo(case, world):
-    """Cyclic bands (the default layout of restore_band_sharded) over gloo."""
+@pytest.mark.parametrize('case,world,slot_order', [('tiny6_closed', 2, False), ('mixed8_image0004', 2, False),
+                                                   ('tiny6_closed', 3, False), ('tiny6_closed', 2, True)])
+def test_band_sharded_restore_over_gloo(case, world, slot_order):
+    """Cyclic bands (the default layout of restore_band_sharded) over gloo; slot_order: the bands' J rows come in the
+    slot order of a permuted store, assembled through the gathered pixel lists."""
     g = Golden(case)
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, 'res.npz')
-        mp.spawn(_worker, args=(world, _free_port(), case, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), case, out, slot_order), nprocs=world, join=True)
         z = np.load(out)
     # the reference's own result for the same scene
     ref_p = np.concatenate([g['B'].ravel(), g['beta'].ravel(), g['gamma'].ravel()])
