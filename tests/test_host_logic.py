@@ -181,3 +181,43 @@ def test_async_writer_runs_jobs_and_reraises(tmp_path):
     w.submit(boom)
     with pytest.raises(OSError):
         w.close()
+
+
+def test_store_slot_and_pixel_views_of_a_permuted_store():
+    """Host-side bookkeeping of a store whose slots were dealt by observation count (engine.ObservationStore.pix): the
+    shapes callers see, the struct the C ABI gets, and the image <-> slot copies of the J-parameter mode."""
+    import numpy as np
+    import torch
+    from sucre_b200 import _lib, engine
+    W, H = 10, 7                                   # 70 pixels -> 3 tiles, 96 slots, 26 of them without a pixel
+    n_tiles = 3
+    rng = np.random.default_rng(0)
+    pix = np.full(n_tiles * 32, -1, np.int32)
+    pix[rng.permutation(96)[:70]] = rng.permutation(70)
+    z64 = torch.zeros(n_tiles + 1, dtype=torch.int64)
+
+    def store(pix_t, band=None):
+        return engine.ObservationStore(width=W, height=H, source_keys=(0,), view_count=np.zeros(1, np.int64), view_kept=np.ones(1, bool),
+                                       n_obs=0, n_blocks=0, n_rows=0, cells=torch.zeros((1, 32, 2)), row_off=z64, blk_off=z64, rec_off=z64,
+                                       blk_mask=torch.zeros(0, dtype=torch.int32), blk_view=torch.zeros(0, dtype=torch.int32), cell_src=None,
+                                       band=band, pix=pix_t)
+
+    s = store(torch.from_numpy(pix))
+    assert s.n_slots == 96 and s.J_shape == (H, W, 3) and s.slot_J_shape == (96, 3) and s.needs_slot_copy and not s.is_band
+    cs = s.c_struct()
+    assert cs.pixels == W * H and cs.pix == s.pix.data_ptr() and cs.n_tiles == n_tiles
+    img = torch.arange(W * H * 3, dtype=torch.float32).reshape(H, W, 3)
+    slots = s.to_slots(img)
+    ok = pix >= 0
+    assert slots.shape == (96, 3) and torch.equal(slots[torch.from_numpy(ok)], img.reshape(-1, 3)[pix[ok].astype(np.int64)])
+    back = torch.full_like(img, -1.0)
+    s.from_slots(slots + 1000.0, back)             # every pixel written exactly once, nothing from the empty slots
+    assert torch.equal(back, img + 1000.0)
+    assert torch.equal(s.global_pixels(), torch.from_numpy(pix.astype(np.int64)))
+    plain = store(None)                            # no permutation: slot q is pixel q
+    assert plain.J_shape == plain.slot_J_shape == (H, W, 3) and not plain.needs_slot_copy
+    assert plain.c_struct().pix is None and plain.c_struct().pixels == W * H
+    band = _lib.Band(1, 2, 2, 0)                   # tiles 1..2 of the image as a band: J arrays are per slot, pix is not passed
+    b = store(torch.from_numpy(pix[:64]), band=band)
+    assert b.is_band and b.J_shape == b.slot_J_shape == (64, 3) and not b.needs_slot_copy
+    assert b.c_struct().pix is None and b.c_struct().pixels == 64
