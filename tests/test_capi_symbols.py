@@ -69,3 +69,38 @@ def test_product_never_imports_the_oracle():
     for path in (ROOT / 'sucre_b200').rglob('*'):
         if path.suffix in ('.py', '.cu', '.cuh', '.h'):
             assert 'oracle' not in path.read_text().lower(), f'{path} mentions the oracle'
+
+
+def test_fit_kernel_sass_keeps_its_shape():
+    """Guards what the fit kernel's speed rests on, on the built library (cuobjdump, no GPU needed): 1-D TMA bulk copies
+    and mbarriers, packed fp32x2 arithmetic, MUFU.EX2, no tensor-core and no local-memory traffic inside the row loop, and
+    a row loop of four two-row steps at no more than 93 instructions per step (ptxas drifts to 98 and spills the next
+    tile's J when the register budget of the sweep is disturbed)."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not installed')
+    out = subprocess.run(['cuobjdump', '-sass', str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    m = re.search(r'Function : (\S*fit_kernelILi0ELi0ELb0\S*)', out)
+    assert m, 'closed-form u8 fit kernel not found'
+    txt = out[m.start():out.find('Function :', m.start() + 10)]
+    ins = [(int(a, 16), t.strip()) for a, t in re.findall(r'/\*([0-9a-f]{4})\*/\s+(.*?);', txt)]
+    ops = [t.split()[1] if t.startswith('@') else t.split()[0] for _, t in ins]
+    assert any(o.startswith('UBLKCP') for o in ops) and any(o.startswith('SYNCS') for o in ops)
+    assert not any(o.startswith(('HMMA', 'UTCHMMA', 'UTCQMMA', 'IMMA')) for o in ops)
+    addr = {a: i for i, (a, _) in enumerate(ins)}
+    loops = []
+    for i, (a, t) in enumerate(ins):
+        b = re.search(r'BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)', t)
+        if b and int(b.group(1), 16) < a and int(b.group(1), 16) in addr:
+            body = ops[addr[int(b.group(1), 16)]:i + 1]
+            if sum(o.startswith('FFMA2') for o in body) >= 30:
+                loops.append(body)
+    assert loops, 'row loop not found'
+    body = min(loops, key=len)
+    steps = sum(o.startswith('FFMA2') for o in body) // 36
+    assert steps == 4, steps
+    assert len(body) <= 93 * steps, len(body)
+    assert sum(o.startswith('MUFU.EX2') for o in body) == 12 * steps
+    assert not any(o.startswith(('LDL', 'STL', 'LDG', 'STG')) for o in body)
