@@ -575,7 +575,11 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
         _lib.check(L.sucre_gather_plan(masks.data_ptr(), n_tiles, V, view_count.data_ptr(), P, float(min_cover),
                                        view_kept.data_ptr(), rec_off.data_ptr(), blk_off.data_ptr(), row_off.data_ptr(),
                                        totals.data_ptr(), st), 'sucre_gather_plan')
-        n_obs, n_blocks, n_rows, culled, n_inb = (int(x) for x in totals.cpu())  # the one host sync of the gather: sizes the store
+        # the one host sync of the gather: the totals size the store; the per-view results ride along, so that nothing
+        # after the sample launch makes the host wait for it
+        host_side = torch.cat([totals, view_count, view_kept.to(torch.int64)]).cpu().numpy()
+        n_obs, n_blocks, n_rows, culled, n_inb = (int(x) for x in host_side[:5])
+        vc, vk = host_side[5:5 + V].copy(), host_side[5 + V:].astype(bool)
         cells = torch.empty((max(n_rows, 1), TILE, words), dtype=torch.float32, device=dev)
         blk_mask = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
         blk_view = torch.empty(max(n_blocks, 1), dtype=torch.int32, device=dev)
@@ -589,8 +593,6 @@ def _gather_listed(scene: DeviceScene, target_key, source_keys, min_cover: float
                                              view_kept.data_ptr(), row_off.data_ptr(), blk_off.data_ptr(), fmt,
                                              cells.data_ptr(), blk_mask.data_ptr(), blk_view.data_ptr(),
                                              0 if cell_src is None else cell_src.data_ptr(), st), 'sucre_gather_sample')
-        vc = view_count.cpu().numpy()
-        vk = view_kept.cpu().numpy().astype(bool)
     stats = {'tile_views_culled': culled, 'tile_views': n_tiles * V, 'n_inbounds': n_inb}
     return ObservationStore(width=W, height=H, source_keys=source_keys, view_count=vc, view_kept=vk, n_obs=n_obs,
                             n_blocks=n_blocks, n_rows=n_rows, cells=cells, row_off=row_off, blk_off=blk_off, rec_off=rec_off,
