@@ -17,8 +17,11 @@
  *
  * Observation store produced by the gather and consumed by the fit ("tile-major ELL rows"):
  *   `cells` is an array of ROWS of 32 records, one record per lane of a tile.  Within tile k, row j holds for lane
- *   i the j-th observation of target pixel 32k+i (its kept source views in pairing-list order) or, when the pixel
- *   has fewer than j+1 observations, an all-zero sentinel record (a real observation always has z > 0).  Tile k has
+ *   i the j-th observation of the target pixel in SLOT 32k+i (its kept source views in pairing-list order) or, when
+ *   the pixel has fewer than j+1 observations, an all-zero sentinel record (a real observation always has z > 0).
+ *   The pixel in a slot is pixel 32k+i itself, or, after sucre_gather_permute, the one the store's `pix` map names
+ *   (struct sucre_store below): the pixels of 32 consecutive tiles dealt to the slots by observation count, which
+ *   leaves few sentinels.  Tile k has
  *   rows(k) = max over its 32 pixels of the observation count and starts at row row_off[k]; tiles follow each other,
  *   so any run of rows is one contiguous byte range (the fit streams it with 1-D TMA bulk copies), a warp reads a
  *   row as one fully coalesced, bank-conflict-free access, and there are no headers, lane offsets or segment
